@@ -1,0 +1,530 @@
+// tcgen05 engine for the three dense contractions of the TCN (the 1x1 convolutions):
+//   MODE 0  conv1d      256 -> 256 : A = GN(stream) computed on load;  epilogue +bias, PReLU, stats
+//   MODE 1  dconv+conv3 512 -> 256 : A = PReLU(depthwise-dilated-conv(GN1(p))) computed on load
+//                                    (q never leaves the SM); epilogue raw accumulators + row/col sums
+//   MODE 2  output conv 256 -> 514 : A = GN(PReLU(GN(stream))) on load; epilogue +bias
+// One CTA = one 128-frame tile (UMMA M = 128, cta_group::1) x one N tile (256, or 192 x 3 for MODE 2).
+// fp16 operands in shared memory (K-major, 128-byte swizzle), fp32 accumulators in TMEM.
+//   warps 0-7 : produce the A operand chunk by chunk (global fp32 -> transform -> fp16 -> swizzled
+//               st.shared), then run the epilogue (tcgen05.ld -> shared staging -> coalesced stores)
+//   warp 8    : streams the pre-swizzled weight image with cp.async.bulk (TMA bulk copy) + mbarrier
+//   warp 9    : allocates TMEM, issues tcgen05.mma (one elected thread), tcgen05.commit -> mbarriers
+// Reference semantics: model/model.py:130-149 (DepthConv1d), :322-325,357 (TCN.output).
+#include <cstdio>
+#include "kernels.h"
+
+namespace septfa {
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kAChunkBytes = kTileM * 128;  // one K-chunk (64 halves = 128 B) of the A tile
+constexpr int kStages = 2;
+constexpr int kThreads = 320;
+constexpr int kAuxBytes = 4096;
+constexpr int kStgPitch = 36;               // floats per staged row (32 + 4 pad, 16 B aligned)
+
+struct TcParams {
+  int M, T, B;
+  const __half* w_img;
+  const float* in;
+  StreamNorm norm;
+  // MODE 2 prologue
+  float slope_o; const Stat2* st_o; const float* g_o; const float* b_o;
+  // MODE 1 prologue
+  const Stat2* st_p; const float* g1; const float* be1; const float4* w2b; float slope2; int dil; Stat2* st_q;
+  // epilogue
+  const float* bias; float slope;
+  float* out; int out_stride;
+  Stat2* st_out;
+  float* rowsum; float* colsum;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (and fails the launch) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("septfa: mbarrier timeout tag=%d block=(%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 x fp16 -> fp32, M = 128, N from idesc, K = 16.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier when all previously issued tcgen05 ops of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 B, 8-row groups
+// 1024 B apart (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout_type SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=F16 [7,10)=0, B=F16 [10,13)=0,
+// A/B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// Byte offset of the 16-byte chunk c8 (8 halves) of row r inside one swizzled K-chunk tile.
+__device__ __forceinline__ uint32_t sw128_offset(int r, int c8) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
+}
+
+struct LaneStat {  // per-lane running (sum, sumsq) with utterance-segment tracking
+  float s = 0.f, ss = 0.f;
+  int seg = -1;
+  __device__ __forceinline__ void add(int sg, float v, float* sm) {
+    if (sg != seg) { flush(sm); seg = sg; }
+    s += v;
+    ss += v * v;
+  }
+  __device__ __forceinline__ void flush(float* sm) {
+    if (seg >= 0 && (s != 0.f || ss != 0.f)) {
+      atomicAdd(sm + 2 * seg, s);
+      atomicAdd(sm + 2 * seg + 1, ss);
+    }
+    s = ss = 0.f;
+  }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
+  constexpr int NT = (MODE == 2) ? 192 : 256;
+  constexpr int KDIM = (MODE == 1) ? 512 : 256;
+  constexpr int NCH = KDIM / 64;
+  constexpr int WCH = NT * 128;
+  constexpr int STAGE = kAChunkBytes + WCH;
+  constexpr uint32_t IDESC = make_idesc_f16(kTileM, NT);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE);
+  uint64_t* full_a = bars;          // [kStages] producers -> MMA
+  uint64_t* full_w = bars + 2;      // [kStages] bulk copy -> MMA
+  uint64_t* empty = bars + 4;       // [kStages] MMA -> producers / loader
+  uint64_t* acc_full = bars + 6;    // MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  float2* tab_a = reinterpret_cast<float2*>(bars + 8);
+  float2* tab_b = tab_a + kMaxSegs;
+  float* seg_acc = reinterpret_cast<float*>(tab_b + kMaxSegs);
+  float* rs_x = seg_acc + 2 * kMaxSegs;  // [128] row-sum exchange between the two column halves
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * kTileM;
+  const int nrows = min(kTileM, p.M - r0);
+  const int b_first = r0 / p.T;
+  const int nseg = (r0 + nrows - 1) / p.T - b_first + 1;
+  const __half* w_img = p.w_img + (size_t)blockIdx.y * NCH * (WCH / 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_a + s, 256);
+      mbar_init(full_w + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 256);
+  {
+    const double inv_n = 1.0 / ((double)kC * p.T);
+    for (int i = threadIdx.x; i < nseg; i += kThreads) {
+      if (MODE == 1) {
+        tab_a[i] = stat_mean_rstd(p.st_p + b_first + i, inv_n, 1e-8f);
+      } else {
+        tab_a[i] = p.norm.gamma != nullptr ? stat_mean_rstd(p.norm.st + b_first + i, p.norm.inv_n, p.norm.eps)
+                                           : make_float2(0.f, 1.f);
+        if (MODE == 2) tab_b[i] = stat_mean_rstd(p.st_o + b_first + i, inv_n, 1e-5f);
+      }
+    }
+    for (int i = threadIdx.x; i < 2 * nseg; i += kThreads) seg_acc[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------ weight loader (TMA bulk copies)
+    if (lane == 0) {
+      for (int j = 0; j < NCH; ++j) {
+        const int s = j % kStages, u = j / kStages;
+        if (u > 0) mbar_wait(empty + s, (u - 1) & 1, 100 + j);
+        mbar_expect_tx(full_w + s, WCH);
+        bulk_copy_g2s(smem + s * STAGE + kAChunkBytes, reinterpret_cast<const uint8_t*>(w_img) + (size_t)j * WCH, WCH,
+                      full_w + s);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      for (int j = 0; j < NCH; ++j) {
+        const int s = j % kStages, u = j / kStages;
+        mbar_wait(full_w + s, u & 1, 200 + j);
+        mbar_wait(full_a + s, u & 1, 300 + j);
+        tc_fence_after();
+        const uint64_t a_desc = make_sw128_desc(smem_u32(smem + s * STAGE));
+        const uint64_t b_desc = make_sw128_desc(smem_u32(smem + s * STAGE + kAChunkBytes));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // UMMA_K = 16 halves = 32 B -> +2 in the (addr >> 4) field
+          umma_f16(tmem_base, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESC, (j | kk) != 0);
+        umma_commit(empty + s);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ A-operand producers (warps 0-7)
+    const int c8 = lane & 7, rg = lane >> 3;
+    LaneStat qstat;
+    for (int j = 0; j < NCH; ++j) {
+      const int s = j % kStages, u = j / kStages;
+      if (u > 0) mbar_wait(empty + s, (u - 1) & 1, 400 + j);
+      uint8_t* a_tile = smem + s * STAGE;
+      if (MODE != 1) {
+        const int kc = j * 64 + c8 * 8;
+        const bool has_norm = p.norm.gamma != nullptr;
+        float ga[8], be[8], go[8], bo[8];
+        if (has_norm) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { ga[i] = __ldg(p.norm.gamma + kc + i); be[i] = __ldg(p.norm.beta + kc + i); }
+        }
+        if (MODE == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { go[i] = __ldg(p.g_o + kc + i); bo[i] = __ldg(p.b_o + kc + i); }
+        }
+        float4 x0[4], x1[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 32 + warp * 4 + rg;
+          if (rl < nrows) {
+            const float4* src = reinterpret_cast<const float4*>(p.in + (int64_t)(r0 + rl) * kC + kc);
+            x0[it] = __ldg(src);
+            x1[it] = __ldg(src + 1);
+          } else {
+            x0[it] = x1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 32 + warp * 4 + rg;
+          float y[8] = {x0[it].x, x0[it].y, x0[it].z, x0[it].w, x1[it].x, x1[it].y, x1[it].z, x1[it].w};
+          if (rl < nrows) {
+            const int sg = (r0 + rl) / p.T - b_first;
+            const float2 mr = tab_a[sg];
+            if (has_norm) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = ((y[i] - mr.x) * mr.y) * ga[i] + be[i];
+            }
+            if (MODE == 2) {
+              const float2 mo = tab_b[sg];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = ((prelu(y[i], p.slope_o) - mo.x) * mo.y) * go[i] + bo[i];
+            }
+          }
+          const uint4 pk = make_uint4(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]),
+                                      pack_half2(y[6], y[7]));
+          *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
+        }
+      } else {
+        // q channels 64j + 8*c8 .. +7  <-  in-channels g0 .. g0+3 (out-channel o reads in-channel o/2)
+        const int g0 = j * 32 + c8 * 4;
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.g1 + g0));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(p.be1 + g0));
+        float4 wb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wb[i] = __ldg(p.w2b + 2 * g0 + i);
+        float4 xm[4], xc[4], xp[4];
+        int okm[4], okp[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 32 + warp * 4 + rg;
+          xm[it] = xc[it] = xp[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          okm[it] = okp[it] = 0;
+          if (rl < nrows) {
+            const int row = r0 + rl;
+            const int t = row - (row / p.T) * p.T;
+            const float* src = p.in + (int64_t)row * kC + g0;
+            xc[it] = __ldg(reinterpret_cast<const float4*>(src));
+            if (t - p.dil >= 0) { okm[it] = 1; xm[it] = __ldg(reinterpret_cast<const float4*>(src - (int64_t)p.dil * kC)); }
+            if (t + p.dil < p.T) { okp[it] = 1; xp[it] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)p.dil * kC)); }
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 32 + warp * 4 + rg;
+          float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (rl < nrows) {
+            const int sg = (r0 + rl) / p.T - b_first;
+            const float2 mr = tab_a[sg];
+            const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
+            const float vm[4] = {xm[it].x, xm[it].y, xm[it].z, xm[it].w};
+            const float vc[4] = {xc[it].x, xc[it].y, xc[it].z, xc[it].w};
+            const float vp[4] = {xp[it].x, xp[it].y, xp[it].z, xp[it].w};
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              // GroupNorm reg1 on load; taps outside the utterance are zero padding of the *normalised* signal
+              const float hm = okm[it] ? ((vm[g] - mr.x) * mr.y) * gam[g] + bet[g] : 0.f;
+              const float hc = ((vc[g] - mr.x) * mr.y) * gam[g] + bet[g];
+              const float hp = okp[it] ? ((vp[g] - mr.x) * mr.y) * gam[g] + bet[g] : 0.f;
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float4 w = wb[2 * g + e];
+                const float v = prelu(w.w + w.x * hm + w.y * hc + w.z * hp, p.slope2);
+                q[2 * g + e] = v;
+                qstat.add(sg, v, seg_acc);
+              }
+            }
+          }
+          const uint4 pk = make_uint4(pack_half2(q[0], q[1]), pack_half2(q[2], q[3]), pack_half2(q[4], q[5]),
+                                      pack_half2(q[6], q[7]));
+          *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(full_a + s);
+    }
+    if (MODE == 1) qstat.flush(seg_acc);
+
+    // ------------------------------------------------------------ epilogue (warps 0-7)
+    // warp w reads TMEM lanes 32*(w%4).. (rows) and columns (w/4)*NT/2 .. in chunks of 32.
+    mbar_wait(acc_full, 0, 500);
+    tc_fence_after();
+    const int lq = warp & 3, ch = warp >> 2;
+    float* stg = reinterpret_cast<float*>(smem) + warp * (32 * kStgPitch);  // aliases the (now idle) stage buffers
+    const int my_rl = lq * 32 + lane;       // the row this thread owns in TMEM
+    float rowacc = 0.f;
+    LaneStat ostat;
+    constexpr int NCC = NT / 64;            // 32-column chunks per column half
+    for (int cc = 0; cc < NCC; ++cc) {
+      const int col0 = ch * (NT / 2) + cc * 32;
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)col0, v);
+      if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rowacc += v[i];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(stg + lane * kStgPitch + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      __syncwarp();
+      // coalesced copy-out: 8 lanes x float4 = one 128 B row segment, 4 rows per instruction
+      const int c4 = (lane & 7) * 4;
+      const int gcol = (MODE == 2 ? (int)blockIdx.y * NT : 0) + col0 + c4;
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE != 1) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+      float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cseg = -1;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int i = it * 4 + (lane >> 3);
+        const int rl = lq * 32 + i;
+        if (rl < nrows) {
+          float4 o = *reinterpret_cast<const float4*>(stg + i * kStgPitch + c4);
+          const int row = r0 + rl;
+          const int sg = row / p.T - b_first;
+          if (MODE == 0) {
+            o.x = prelu(o.x + bias4.x, p.slope); o.y = prelu(o.y + bias4.y, p.slope);
+            o.z = prelu(o.z + bias4.z, p.slope); o.w = prelu(o.w + bias4.w, p.slope);
+            ostat.add(sg, o.x, seg_acc); ostat.add(sg, o.y, seg_acc);
+            ostat.add(sg, o.z, seg_acc); ostat.add(sg, o.w, seg_acc);
+          } else if (MODE == 2) {
+            o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
+          } else {
+            if (sg != cseg) {
+              if (cseg >= 0) {
+                float* dst = p.colsum + (size_t)(b_first + cseg) * kC + col0 + c4;
+                atomicAdd(dst, csum.x); atomicAdd(dst + 1, csum.y); atomicAdd(dst + 2, csum.z); atomicAdd(dst + 3, csum.w);
+              }
+              csum = make_float4(0.f, 0.f, 0.f, 0.f);
+              cseg = sg;
+            }
+            csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w;
+          }
+          *reinterpret_cast<float4*>(p.out + (int64_t)row * p.out_stride + gcol) = o;
+        }
+      }
+      if (MODE == 1) {
+        // column sums: combine the 4 row groups of the warp when they all belong to one utterance
+        const int seg0 = __shfl_sync(0xffffffffu, cseg, 0);
+        const bool uniform = __all_sync(0xffffffffu, cseg == seg0);
+        if (uniform) {
+          if (seg0 >= 0) {
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+              csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+            }
+            if (lane < 8) {
+              float* dst = p.colsum + (size_t)(b_first + seg0) * kC + col0 + c4;
+              atomicAdd(dst, csum.x); atomicAdd(dst + 1, csum.y); atomicAdd(dst + 2, csum.z); atomicAdd(dst + 3, csum.w);
+            }
+          }
+        } else if (cseg >= 0) {
+          float* dst = p.colsum + (size_t)(b_first + cseg) * kC + col0 + c4;
+          atomicAdd(dst, csum.x); atomicAdd(dst + 1, csum.y); atomicAdd(dst + 2, csum.z); atomicAdd(dst + 3, csum.w);
+        }
+      }
+    }
+    if (MODE == 0) ostat.flush(seg_acc);
+    if (MODE == 1) {
+      // row sums: the two column halves (warps w and w+4) own the same rows
+      if (ch == 1) rs_x[my_rl] = rowacc;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ch == 0 && my_rl < nrows) p.rowsum[r0 + my_rl] = rowacc + rs_x[my_rl];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 256);
+  Stat2* sdst = (MODE == 0) ? p.st_out : (MODE == 1 ? p.st_q : nullptr);
+  if (sdst != nullptr && blockIdx.y == 0) {
+    for (int i = threadIdx.x; i < nseg; i += kThreads) {
+      atomicAdd(&sdst[b_first + i].s, (double)seg_acc[2 * i]);
+      atomicAdd(&sdst[b_first + i].ss, (double)seg_acc[2 * i + 1]);
+    }
+  }
+}
+
+template <int MODE>
+void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
+  constexpr int NT = (MODE == 2) ? 192 : 256;
+  constexpr int smem = kStages * (kAChunkBytes + NT * 128) + kAuxBytes + 1024;
+  dim3 grid((p.M + kTileM - 1) / kTileM, ntiles_n);
+  k_tc_gemm<MODE><<<grid, kThreads, smem, st>>>(p);
+  ++g_launch_count;
+}
+
+}  // namespace
+
+cudaError_t tc_gemm_setup() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_tc_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kStages * (kAChunkBytes + 192 * 128) + kAuxBytes + 1024);
+  return e;
+}
+
+void launch_tc_conv1(const Conv1Params& c, cudaStream_t st) {
+  TcParams p{};
+  p.M = c.M; p.T = c.T; p.B = c.B;
+  p.w_img = c.w_img; p.in = c.w_in; p.norm = c.norm;
+  p.bias = c.bias; p.slope = c.slope;
+  p.out = c.p_out; p.out_stride = kC; p.st_out = c.st_p;
+  launch_mode<0>(p, 1, st);
+}
+
+void launch_tc_dconv(const DconvParams& c, cudaStream_t st) {
+  TcParams p{};
+  p.M = c.M; p.T = c.T; p.B = c.B;
+  p.w_img = c.w_img; p.in = c.p_in;
+  p.st_p = c.st_p; p.g1 = c.g1; p.be1 = c.be1; p.w2b = c.w2b; p.slope2 = c.slope2; p.dil = c.dil; p.st_q = c.st_q;
+  p.out = c.racc; p.out_stride = kC; p.rowsum = c.rowsum; p.colsum = c.colsum;
+  launch_mode<1>(p, 1, st);
+}
+
+void launch_tc_outconv(const OutConvParams& c, cudaStream_t st) {
+  TcParams p{};
+  p.M = c.M; p.T = c.T; p.B = c.B;
+  p.w_img = c.w_img; p.in = c.w_in; p.norm = c.norm;
+  p.slope_o = c.slope_o; p.st_o = c.st_o; p.g_o = c.g_o; p.b_o = c.b_o;
+  p.bias = c.bias;
+  p.out = c.logits; p.out_stride = kLogitStride;
+  launch_mode<2>(p, 3, st);
+}
+
+}  // namespace septfa

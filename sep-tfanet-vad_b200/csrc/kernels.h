@@ -1,0 +1,153 @@
+// Host-side launcher declarations shared by the septfa translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace septfa {
+
+// ---- parameters of the three dense contractions (shared by the tcgen05 and the fp32 engines)
+
+// Residual-stream affine: y = (w - mean_b) * rstd_b * gamma[c] + beta[c]; gamma == nullptr means y = w.
+struct StreamNorm {
+  const Stat2* st;     // [B] accumulators of the producing stage (ignored if gamma == nullptr)
+  const float* gamma;  // [256]
+  const float* beta;   // [256]
+  float eps;
+  double inv_n;        // 1 / (256 * T)
+};
+
+// DepthConv1d first half (model/model.py:132/138): p = PReLU(W1 y + b1), stats of p.
+struct Conv1Params {
+  const float* w_in;   // [M,256] residual stream (pre-norm)
+  StreamNorm norm;
+  int M, T, B;
+  const float* bias;   // [256]
+  float slope;
+  const __half* w_img; // tcgen05 image: 4 K-chunks x [256 rows x 128 B], 128B-swizzled K-major
+  const float* w_t;    // fp32 [256 k][256 n]
+  float* p_out;        // [M,256]
+  Stat2* st_p;         // [B]
+};
+
+// DepthConv1d second half (model/model.py:136/142,144) with GroupNorm reg2 folded into W3:
+// q = PReLU(dconv(GN1(p))), racc = (W3*diag(g2)) q  (raw accumulators), row/column sums of racc.
+struct DconvParams {
+  const float* p_in;   // [M,256]
+  const Stat2* st_p;   // [B]
+  const float* g1;     // reg1 gamma/beta [256]
+  const float* be1;
+  const float4* w2b;   // [512] {w[o][0], w[o][1], w[o][2], b2[o]}
+  float slope2;
+  int dil;
+  int M, T, B;
+  const __half* w_img; // 8 K-chunks x [256 rows x 128 B]
+  const float* w_t;    // fp32 [512 k][256 n] (gamma2-folded)
+  float* racc;         // [M,256]
+  float* rowsum;       // [M]
+  float* colsum;       // [B,256] (pre-zeroed, accumulated with atomics)
+  Stat2* st_q;         // [B]
+};
+
+// TCN.output (model/model.py:322-325,357): logits = Wo GN(PReLU(y)) + bo, N = 514 padded to 576.
+struct OutConvParams {
+  const float* w_in;   // [M,256]
+  StreamNorm norm;
+  float slope_o;
+  const Stat2* st_o;   // [B] stats of PReLU(y)
+  const float* g_o;    // output.1 gamma/beta [256], eps 1e-5
+  const float* b_o;
+  int M, T, B;
+  const float* bias;   // [576] (zero padded)
+  const __half* w_img; // 3 N-tiles x 4 K-chunks x [192 rows x 128 B]
+  const float* w_t;    // fp32 [256 k][576 n]
+  float* logits;       // [M,576]
+};
+
+// TF_Attention scalars (model/model.py:182-208).
+struct TfParams {
+  float wt1[3], bt1, wt2[3], bt2, at;
+  float wf1[3], bf1, wf2[3], bf2, af;
+  int enabled;
+};
+
+// r[c,t] = racc[t,c] * ra[b] + rb[b,c];  residual = r * gf[b,c] * gt[row]
+struct GateParams {
+  const Stat2* st_q;   // [B], over 512*T elements, eps 1e-8
+  const float* s3;     // [256] sum_o W3g[c,o]
+  const float* c03;    // [256] sum_o W3[c,o]*beta2[o] + b3[c]
+  const float* rowsum; // [M]
+  const float* colsum; // [B,256]
+  TfParams tf;
+  int M, T, B;
+  float* ra;           // [B]
+  float* rb;           // [B,256]
+  float* gf;           // [B,256]
+  float* gt;           // [M]
+};
+
+enum LnMode { LN_NONE = 0, LN_RECURSIVE = 1, LN_RESIDUAL = 2 };
+
+struct ResidParams {
+  float* w;            // [M,256] residual stream, updated in place by resid_apply
+  StreamNorm norm;     // affine that turns w into y
+  const float* racc;   // [M,256]
+  const float* ra; const float* rb; const float* gf; const float* gt;
+  int M, T, B;
+  int mode;            // LnMode
+  Stat2* st_v;         // [B] stats of v (y + r*g for recursive, r*g for residual)
+  const float* g_a;    // ln_first (recursive) or ln_modules (residual) gamma/beta, eps 1e-5
+  const float* b_a;
+  Stat2* st_w;         // [B] stats of the new stream (recursive only)
+};
+
+// ---- launchers ---------------------------------------------------------------------------
+// frontend.cu
+void make_twiddles(float2* host256);
+void launch_stft(const float* x, int B, int64_t L, int T, const float* window, const float2* twiddle, float2* S, float* P,
+                 cudaStream_t st);
+void launch_activity_gate(const float* P, int B, int T, int enabled, const float* k3x3, float bias, float slope,
+                          float* z0, float* dc_gated, Stat2* st0, cudaStream_t st);
+// tcn.cu
+void launch_ref_conv1(const Conv1Params& p, cudaStream_t st);
+void launch_ref_dconv(const DconvParams& p, cudaStream_t st);
+void launch_ref_outconv(const OutConvParams& p, cudaStream_t st);
+void launch_tf_gate(const GateParams& p, cudaStream_t st);
+void launch_resid_stats(const ResidParams& p, cudaStream_t st);
+void launch_resid_apply(const ResidParams& p, cudaStream_t st);
+void launch_out_stats(const float* w, StreamNorm norm, float slope, int M, int T, Stat2* st_o, cudaStream_t st);
+// gemm_tc.cu
+void launch_tc_conv1(const Conv1Params& p, cudaStream_t st);
+void launch_tc_dconv(const DconvParams& p, cudaStream_t st);
+void launch_tc_outconv(const OutConvParams& p, cudaStream_t st);
+cudaError_t tc_gemm_setup();  // opt-in shared memory attributes; call once per device
+// backend.cu
+struct VadParams {
+  const float* logits;   // [M,576]
+  int M, T, B;
+  const float* w1t;      // [5 k][4 j][257 f] folded conv1_1 weights
+  float b1[4]; float slope; float g[4]; float be[4];
+  float w2[12]; float b2;  // output_layer_vad [4 j][3 k]
+  float* c4;             // [B*2*T, 4] scratch
+  Stat2* st_v;           // [B*2]
+  float* prob;           // [B,2,T]
+  float* smooth;         // [B,2,T]
+  float thr;
+  int do_smooth;
+};
+void launch_vad(const VadParams& p, cudaStream_t st);
+void launch_mask_istft(const float2* S, const float* logits, const float* gate /*[B,2,T] or null*/, const float* window,
+                       const float2* twiddle, int B, int64_t L, int T, float* out, cudaStream_t st);
+void launch_export(const float2* S, const float* logits, const float* gate, const float* z0, const float* dc_gated,
+                   int B, int T, float2* est, float* mask, float* spectrum, float* logits_out, cudaStream_t st);
+// online.cu
+void launch_pit(const float* a, int64_t a_bstride, int64_t a_sstride, const float* b, int64_t b_bstride, int64_t b_sstride,
+                int S, int64_t n, double* acc /*[S,4] zeroed*/, int32_t* perm, cudaStream_t st);
+void launch_online_emit(const float* pred /*[S,2,Lw]*/, int64_t Lw, const int32_t* perm, int S, int hop, int tail_cap,
+                        const float* tail_in /*[S,2,tail_cap]*/, int tail_len, float* tail_out, float* emitted /*[S,2,hop]*/,
+                        cudaStream_t st);
+
+extern int g_launch_count;  // kernels launched since last reset (host counter)
+
+}  // namespace septfa

@@ -1,0 +1,709 @@
+// C ABI of libseptfa.so (include/septfa.h): handle, weight folding / packing, workspace carving,
+// the forward pass orchestration and the online (sliding-window) step.
+// Reference: model/model.py:360-461 (SeparationModel), model/online_class_unknown_targets.py:72-105.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/septfa.h"
+#include "kernels.h"
+
+using namespace septfa;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct KeySpec {
+  std::string name;
+  int64_t numel;
+};
+
+struct DevBlock {
+  const __half* w1_img; const float* w1_t; const float* b1; float a1; const float* g1; const float* be1;
+  const float4* w2b; float a2; int dil;
+  const __half* w3_img; const float* w3_t; const float* s3_tc; const float* s3_ref; const float* c03;
+  TfParams tf;
+  const float* lf_g; const float* lf_b; const float* ls_g; const float* ls_b;  // recursive
+  const float* lm_g; const float* lm_b;                                        // residual
+};
+
+}  // namespace
+
+struct septfa_handle {
+  septfa_config cfg{};
+  int device = 0;
+  int nblk = 0;
+  int ln_mode = LN_NONE;
+  int engine = SEPTFA_ENGINE_TCGEN05_F16;
+  bool committed = false;
+  std::string err;
+  std::vector<KeySpec> keys;
+  std::map<std::string, std::vector<float>> host;
+  std::vector<void*> allocs;
+  // device weights
+  std::vector<DevBlock> blocks;
+  const float* ln_g = nullptr; const float* ln_b = nullptr;
+  float out_a = 0.f; const float* out_g = nullptr; const float* out_be = nullptr;
+  const __half* out_img = nullptr; const float* out_wt = nullptr; const float* out_bias = nullptr;
+  const float* vad_w1t = nullptr; float vad_b1[4]{}; float vad_a = 0.f; float vad_g[4]{}; float vad_be[4]{};
+  float vad_w2[12]{}; float vad_b2 = 0.f;
+  float act_k[9]{}; float act_b = 0.f; float act_a = 0.f;
+  const float* win_fwd = nullptr; const float* win_inv = nullptr; const float2* twiddle = nullptr;
+  int last_launches = 0;
+  // forward_host resources
+  cudaStream_t hstream = nullptr;
+  float* hx_dev = nullptr; float* hout_dev = nullptr; float* hvad_dev = nullptr; void* hws = nullptr;
+  float* hx_pin = nullptr; float* hout_pin = nullptr; float* hvad_pin = nullptr;
+  size_t hcap_x = 0, hcap_out = 0, hcap_vad = 0, hcap_ws = 0;
+  // pit scratch
+  double* pit_acc = nullptr; int pit_cap = 0;
+};
+
+struct septfa_online {
+  septfa_handle* h = nullptr;
+  int S = 0;
+  int hops = 0;
+  int tail_len = 0;
+  int cur = 0;
+  float* tail[2] = {nullptr, nullptr};
+  double* acc = nullptr;
+};
+
+namespace {
+
+constexpr int kFs = 16000, kWinLen = 48000, kHopLen = 16000, kTailCap = 32000;
+
+int fail(septfa_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                                     \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(h, SEPTFA_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+void add_wn_conv(std::vector<KeySpec>& k, const std::string& p, int co, int ci, int ks) {
+  k.push_back({p + ".bias", co});
+  k.push_back({p + ".weight_g", co});
+  k.push_back({p + ".weight_v", (int64_t)co * ci * ks});
+}
+void add_gn(std::vector<KeySpec>& k, const std::string& p, int c) {
+  k.push_back({p + ".weight", c});
+  k.push_back({p + ".bias", c});
+}
+
+// Key families and shapes of the reference state_dict (model/model.py:210-325,153-171,376-400).
+void build_keys(septfa_handle* h) {
+  auto& k = h->keys;
+  const auto& c = h->cfg;
+  k.push_back({"spec_input.spec.window", 512});
+  k.push_back({"spec_output.window", 512});
+  k.push_back({"inv_spec.window", 512});
+  add_gn(k, "TCN.LN", kC);
+  for (int i = 0; i < h->nblk; ++i) {
+    const std::string p = "TCN.TCN." + std::to_string(i);
+    add_wn_conv(k, p + ".conv1d", kC, kC, 1);
+    add_wn_conv(k, p + ".dconv1d", kH, 1, 3);
+    add_wn_conv(k, p + ".res_out", kC, kH, 1);
+    k.push_back({p + ".nonlinearity1.weight", 1});
+    k.push_back({p + ".nonlinearity2.weight", 1});
+    add_gn(k, p + ".reg1", kC);
+    add_gn(k, p + ".reg2", kH);
+  }
+  if (c.tf_attention)
+    for (int i = 0; i < h->nblk; ++i) {
+      const std::string p = "TCN.time_freq_attnetion." + std::to_string(i);  // (sic) model.py:279
+      for (const char* n : {"conv1d_t_1", "conv1d_t_2", "conv1d_f_1", "conv1d_f_2"}) {
+        k.push_back({p + "." + n + ".weight", 3});
+        k.push_back({p + "." + n + ".bias", 1});
+      }
+      k.push_back({p + ".prelu_t.weight", 1});
+      k.push_back({p + ".prelu_f.weight", 1});
+    }
+  if (c.apply_recursive_ln)
+    for (int i = 0; i < h->nblk; ++i) {
+      add_gn(k, "TCN.ln_first_modules." + std::to_string(i), kC);
+      add_gn(k, "TCN.ln_second_modules." + std::to_string(i), kC);
+    }
+  if (c.apply_residual_ln)
+    for (int i = 0; i < h->nblk; ++i) add_gn(k, "TCN.ln_modules." + std::to_string(i), kC);
+  k.push_back({"TCN.output.0.weight", 1});
+  add_gn(k, "TCN.output.1", kC);
+  add_wn_conv(k, "TCN.output.2", kBins * 2, kC, 1);
+  if (c.final_vad) {
+    add_wn_conv(k, "vad.common.conv1_1", 4, kBins, 5);
+    k.push_back({"vad.common.relu_1.weight", 1});
+    add_gn(k, "vad.common.BN_1", 4);
+    add_wn_conv(k, "vad.output_layer_vad", 1, 4, 3);
+  }
+  if (c.activity_input_bool) {
+    k.push_back({"activity_input.weight", 9});
+    k.push_back({"activity_input.bias", 1});
+    k.push_back({"prelu.weight", 1});
+  }
+}
+
+// torch.nn.utils.weight_norm (dim 0): w[o,:] = g[o] * v[o,:] / ||v[o,:]||_2  (model.py:104-127,159-163,324)
+std::vector<double> fold_wn(const std::vector<float>& g, const std::vector<float>& v, int co) {
+  const size_t per = v.size() / co;
+  std::vector<double> w(v.size());
+  for (int o = 0; o < co; ++o) {
+    double n2 = 0.0;
+    for (size_t i = 0; i < per; ++i) n2 += (double)v[o * per + i] * (double)v[o * per + i];
+    const double sc = (double)g[o] / std::sqrt(n2);
+    for (size_t i = 0; i < per; ++i) w[o * per + i] = sc * (double)v[o * per + i];
+  }
+  return w;
+}
+
+template <typename T>
+int upload(septfa_handle* h, const std::vector<T>& src, const T** dst) {
+  void* d = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d, src.size() * sizeof(T)));
+  h->allocs.push_back(d);
+  CUDA_TRY(h, cudaMemcpy(d, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = reinterpret_cast<const T*>(d);
+  return 0;
+}
+
+// tcgen05 operand image of W[n][k] (n < nrows_valid, K = kdim): tiles of NT rows, K-chunks of 64 halves,
+// each chunk = NT rows x 128 B, K-major with the 128-byte swizzle (16-byte chunk index XOR row%8).
+std::vector<__half> pack_image(const std::vector<double>& w, int nvalid, int kdim, int ntiles, int NT) {
+  const int nch = kdim / 64;
+  std::vector<__half> img((size_t)ntiles * nch * NT * 64, __float2half(0.f));
+  for (int tile = 0; tile < ntiles; ++tile)
+    for (int j = 0; j < nch; ++j)
+      for (int r = 0; r < NT; ++r) {
+        const int n = tile * NT + r;
+        if (n >= nvalid) continue;
+        for (int kk = 0; kk < 64; ++kk) {
+          const int k = j * 64 + kk;
+          const size_t byte = ((size_t)(tile * nch + j) * NT) * 128 + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 +
+                              (size_t)(((kk >> 3) ^ (r & 7)) << 4) + (size_t)(kk & 7) * 2;
+          img[byte / 2] = __float2half((float)w[(size_t)n * kdim + k]);
+        }
+      }
+  return img;
+}
+
+const std::vector<float>& T_(septfa_handle* h, const std::string& k) { return h->host.at(k); }
+
+struct Workspace {
+  float2* S; float* P; float* w; float* dcg; float* p; float* racc; float* rowsum; float* gt; float* logits;
+  float* ra; float* rb; float* gf; float* c4; float* prob; float* smooth;
+  uint8_t* zero_begin; size_t zero_bytes;
+  Stat2* st0; Stat2* st_blk; Stat2* st_o; Stat2* st_vad; float* colsum;
+  size_t total;
+};
+
+Workspace carve(const septfa_handle* h, void* base, int B, int64_t L) {
+  Workspace w{};
+  const int64_t T = septfa_num_frames(L), M = (int64_t)B * T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = reinterpret_cast<uint8_t*>(base) + off;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  w.S = (float2*)take(M * kBins * sizeof(float2));
+  w.P = (float*)take(M * kBins * sizeof(float));
+  w.w = (float*)take(M * kC * sizeof(float));
+  w.dcg = (float*)take(M * sizeof(float));
+  w.p = (float*)take(M * kC * sizeof(float));
+  w.racc = (float*)take(M * kC * sizeof(float));
+  w.rowsum = (float*)take(M * sizeof(float));
+  w.gt = (float*)take(M * sizeof(float));
+  w.logits = (float*)take(M * kLogitStride * sizeof(float));
+  w.ra = (float*)take(B * sizeof(float));
+  w.rb = (float*)take((size_t)B * kC * sizeof(float));
+  w.gf = (float*)take((size_t)B * kC * sizeof(float));
+  w.c4 = (float*)take(M * 2 * 4 * sizeof(float));
+  w.prob = (float*)take(M * 2 * sizeof(float));
+  w.smooth = (float*)take(M * 2 * sizeof(float));
+  w.zero_begin = reinterpret_cast<uint8_t*>(base) + off;
+  w.st0 = (Stat2*)take(B * sizeof(Stat2));
+  w.st_blk = (Stat2*)take((size_t)h->nblk * 4 * B * sizeof(Stat2));
+  w.st_o = (Stat2*)take(B * sizeof(Stat2));
+  w.st_vad = (Stat2*)take((size_t)B * 2 * sizeof(Stat2));
+  w.colsum = (float*)take((size_t)h->nblk * B * kC * sizeof(float));
+  w.zero_bytes = (reinterpret_cast<uint8_t*>(base) + off) - w.zero_begin;
+  w.total = off;
+  return w;
+}
+
+int check_forward_args(septfa_handle* h, int B, int64_t L) {
+  if (!h) return SEPTFA_E_INVALID;
+  if (!h->committed) return fail(h, SEPTFA_E_STATE, "weights not committed");
+  if (B < 1) return fail(h, SEPTFA_E_INVALID, "B must be >= 1");
+  if (L < 257) return fail(h, SEPTFA_E_INVALID, "L must be >= 257 (reflect padding of 256 samples needs a longer input)");
+  if ((int64_t)B * septfa_num_frames(L) > (int64_t)1 << 30) return fail(h, SEPTFA_E_INVALID, "B*T too large");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* septfa_version(void) { return "septfa-b200 0.1 (sm_100a)"; }
+
+const char* septfa_last_error(const septfa_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t septfa_num_frames(int64_t L) { return 1 + L / kHop; }
+
+int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
+  if (!out || !cfg) return fail(nullptr, SEPTFA_E_INVALID, "null argument");
+  *out = nullptr;
+  const septfa_config& c = *cfg;
+  // Configurations outside the shipped ones are rejected loudly ("unused-at-these-configs").
+  if (c.n_fft_bins != 512 || c.bn_dim != 256 || c.h_dim != 512 || c.num_spk != 2)
+    return fail(nullptr, SEPTFA_E_INVALID, "unsupported sizes: need n_fftBins=512, BN_dim=256, H_dim=512, num_spk=2");
+  if (!c.weight_norm) return fail(nullptr, SEPTFA_E_INVALID, "unsupported config: weight_norm=false");
+  if (c.skip) return fail(nullptr, SEPTFA_E_INVALID, "unsupported config: skip=true");
+  if (!c.dilated) return fail(nullptr, SEPTFA_E_INVALID, "unsupported config: dilated=false");
+  if (c.causal) return fail(nullptr, SEPTFA_E_INVALID, "unsupported config: casual=true (cLN)");
+  if (c.final_vad_masked_speakers) return fail(nullptr, SEPTFA_E_INVALID, "unsupported config: final_vad_masked_speakers=true");
+  if (c.layer < 1 || c.stack < 1 || c.layer * c.stack > 256) return fail(nullptr, SEPTFA_E_INVALID, "bad layer/stack");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, SEPTFA_E_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(nullptr, SEPTFA_E_INVALID, "bad device index");
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, SEPTFA_E_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(nullptr, SEPTFA_E_CUDA, "device is not sm_100 (Blackwell B200); this build targets sm_100a only");
+  auto* h = new septfa_handle();
+  h->cfg = c;
+  h->device = device;
+  h->nblk = c.layer * c.stack;
+  h->ln_mode = c.apply_recursive_ln ? LN_RECURSIVE : (c.apply_residual_ln ? LN_RESIDUAL : LN_NONE);  // model.py:347-352
+  build_keys(h);
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, "cudaSetDevice failed"); }
+  cudaError_t e = tc_gemm_setup();
+  if (e != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, std::string("tc_gemm_setup: ") + cudaGetErrorString(e)); }
+  *out = h;
+  return 0;
+}
+
+void septfa_destroy(septfa_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  cudaFree(h->hx_dev); cudaFree(h->hout_dev); cudaFree(h->hvad_dev); cudaFree(h->hws); cudaFree(h->pit_acc);
+  cudaFreeHost(h->hx_pin); cudaFreeHost(h->hout_pin); cudaFreeHost(h->hvad_pin);
+  if (h->hstream) cudaStreamDestroy(h->hstream);
+  delete h;
+}
+
+int septfa_num_keys(const septfa_handle* h) { return h ? (int)h->keys.size() : 0; }
+const char* septfa_key_name(const septfa_handle* h, int i) {
+  return (h && i >= 0 && i < (int)h->keys.size()) ? h->keys[i].name.c_str() : nullptr;
+}
+int64_t septfa_key_numel(const septfa_handle* h, int i) {
+  return (h && i >= 0 && i < (int)h->keys.size()) ? h->keys[i].numel : -1;
+}
+
+int septfa_set_tensor(septfa_handle* h, const char* key, const float* data, int64_t numel) {
+  if (!h || !key || !data) return SEPTFA_E_INVALID;
+  for (const auto& k : h->keys)
+    if (k.name == key) {
+      if (k.numel != numel)
+        return fail(h, SEPTFA_E_KEY, std::string("size mismatch for ") + key + ": expected " + std::to_string(k.numel) +
+                                         " elements, got " + std::to_string(numel));
+      h->host[key].assign(data, data + numel);
+      h->committed = false;
+      return 0;
+    }
+  return fail(h, SEPTFA_E_KEY, std::string("unexpected key ") + key);
+}
+
+int septfa_set_option(septfa_handle* h, const char* name, int value) {
+  if (!h || !name) return SEPTFA_E_INVALID;
+  if (std::strcmp(name, "engine") == 0) {
+    if (value < 0 || value > 7) return fail(h, SEPTFA_E_INVALID, "bad engine");
+    h->engine = value;
+    return 0;
+  }
+  return fail(h, SEPTFA_E_INVALID, std::string("unknown option ") + name);
+}
+int septfa_get_option(const septfa_handle* h, const char* name) {
+  if (h && name && std::strcmp(name, "engine") == 0) return h->engine;
+  return SEPTFA_E_INVALID;
+}
+
+int septfa_commit_weights(septfa_handle* h) {
+  if (!h) return SEPTFA_E_INVALID;
+  for (const auto& k : h->keys)
+    if (!h->host.count(k.name)) return fail(h, SEPTFA_E_KEY, "missing key " + k.name);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+  h->blocks.assign(h->nblk, DevBlock{});
+  const auto& c = h->cfg;
+
+  // The two analysis windows must agree (they always do: both are hann buffers, model.py:383-385);
+  // the STFT is then computed once instead of twice (model.py:408-409).
+  if (T_(h, "spec_input.spec.window") != T_(h, "spec_output.window"))
+    return fail(h, SEPTFA_E_INVALID, "spec_input.spec.window and spec_output.window differ: unsupported");
+  if (upload(h, T_(h, "spec_output.window"), &h->win_fwd)) return SEPTFA_E_CUDA;
+  if (upload(h, T_(h, "inv_spec.window"), &h->win_inv)) return SEPTFA_E_CUDA;
+  {
+    std::vector<float2> tw(256);
+    make_twiddles(tw.data());
+    if (upload(h, tw, &h->twiddle)) return SEPTFA_E_CUDA;
+  }
+  if (upload(h, T_(h, "TCN.LN.weight"), &h->ln_g) || upload(h, T_(h, "TCN.LN.bias"), &h->ln_b)) return SEPTFA_E_CUDA;
+
+  for (int i = 0; i < h->nblk; ++i) {
+    DevBlock& d = h->blocks[i];
+    const std::string p = "TCN.TCN." + std::to_string(i);
+    d.dil = (i % c.layer) % 4 + 1;  // model.py:285-293
+    // conv1d 256 -> 256
+    {
+      const auto w = fold_wn(T_(h, p + ".conv1d.weight_g"), T_(h, p + ".conv1d.weight_v"), kC);
+      std::vector<float> wt((size_t)kC * kC);
+      for (int n = 0; n < kC; ++n)
+        for (int k = 0; k < kC; ++k) wt[(size_t)k * kC + n] = (float)w[(size_t)n * kC + k];
+      if (upload(h, pack_image(w, kC, kC, 1, 256), &d.w1_img) || upload(h, wt, &d.w1_t) ||
+          upload(h, T_(h, p + ".conv1d.bias"), &d.b1))
+        return SEPTFA_E_CUDA;
+      d.a1 = T_(h, p + ".nonlinearity1.weight")[0];
+      if (upload(h, T_(h, p + ".reg1.weight"), &d.g1) || upload(h, T_(h, p + ".reg1.bias"), &d.be1)) return SEPTFA_E_CUDA;
+    }
+    // depthwise 256 -> 512, k3
+    {
+      const auto w = fold_wn(T_(h, p + ".dconv1d.weight_g"), T_(h, p + ".dconv1d.weight_v"), kH);
+      const auto& b2 = T_(h, p + ".dconv1d.bias");
+      std::vector<float4> w2b(kH);
+      for (int o = 0; o < kH; ++o) w2b[o] = make_float4((float)w[o * 3], (float)w[o * 3 + 1], (float)w[o * 3 + 2], b2[o]);
+      if (upload(h, w2b, &d.w2b)) return SEPTFA_E_CUDA;
+      d.a2 = T_(h, p + ".nonlinearity2.weight")[0];
+    }
+    // res_out 512 -> 256 with GroupNorm reg2 folded in:  r = rstd2 * (W3g q - mu2 * s3) + c03
+    {
+      const auto w = fold_wn(T_(h, p + ".res_out.weight_g"), T_(h, p + ".res_out.weight_v"), kC);
+      const auto& g2 = T_(h, p + ".reg2.weight");
+      const auto& be2 = T_(h, p + ".reg2.bias");
+      const auto& b3 = T_(h, p + ".res_out.bias");
+      std::vector<double> wg((size_t)kC * kH);
+      std::vector<float> wt((size_t)kH * kC), s3_tc(kC), s3_ref(kC), c03(kC);
+      for (int n = 0; n < kC; ++n) {
+        double s_tc = 0.0, s_ref = 0.0, c0 = (double)b3[n];
+        for (int o = 0; o < kH; ++o) {
+          const double v = w[(size_t)n * kH + o] * (double)g2[o];
+          wg[(size_t)n * kH + o] = v;
+          wt[(size_t)o * kC + n] = (float)v;
+          s_tc += (double)__half2float(__float2half((float)v));  // matches the fp16 operand the tensor core sees
+          s_ref += (double)(float)v;
+          c0 += w[(size_t)n * kH + o] * (double)be2[o];
+        }
+        s3_tc[n] = (float)s_tc;
+        s3_ref[n] = (float)s_ref;
+        c03[n] = (float)c0;
+      }
+      if (upload(h, pack_image(wg, kC, kH, 1, 256), &d.w3_img) || upload(h, wt, &d.w3_t) || upload(h, s3_tc, &d.s3_tc) ||
+          upload(h, s3_ref, &d.s3_ref) || upload(h, c03, &d.c03))
+        return SEPTFA_E_CUDA;
+    }
+    d.tf.enabled = c.tf_attention;
+    if (c.tf_attention) {
+      const std::string q = "TCN.time_freq_attnetion." + std::to_string(i);
+      for (int k = 0; k < 3; ++k) {
+        d.tf.wt1[k] = T_(h, q + ".conv1d_t_1.weight")[k];
+        d.tf.wt2[k] = T_(h, q + ".conv1d_t_2.weight")[k];
+        d.tf.wf1[k] = T_(h, q + ".conv1d_f_1.weight")[k];
+        d.tf.wf2[k] = T_(h, q + ".conv1d_f_2.weight")[k];
+      }
+      d.tf.bt1 = T_(h, q + ".conv1d_t_1.bias")[0];
+      d.tf.bt2 = T_(h, q + ".conv1d_t_2.bias")[0];
+      d.tf.bf1 = T_(h, q + ".conv1d_f_1.bias")[0];
+      d.tf.bf2 = T_(h, q + ".conv1d_f_2.bias")[0];
+      d.tf.at = T_(h, q + ".prelu_t.weight")[0];
+      d.tf.af = T_(h, q + ".prelu_f.weight")[0];
+    }
+    if (c.apply_recursive_ln) {
+      const std::string a = "TCN.ln_first_modules." + std::to_string(i), b = "TCN.ln_second_modules." + std::to_string(i);
+      if (upload(h, T_(h, a + ".weight"), &d.lf_g) || upload(h, T_(h, a + ".bias"), &d.lf_b) ||
+          upload(h, T_(h, b + ".weight"), &d.ls_g) || upload(h, T_(h, b + ".bias"), &d.ls_b))
+        return SEPTFA_E_CUDA;
+    } else if (c.apply_residual_ln) {
+      const std::string a = "TCN.ln_modules." + std::to_string(i);
+      if (upload(h, T_(h, a + ".weight"), &d.lm_g) || upload(h, T_(h, a + ".bias"), &d.lm_b)) return SEPTFA_E_CUDA;
+    }
+  }
+  // output layer 256 -> 514 (padded to 576 = 3 x 192)
+  {
+    h->out_a = T_(h, "TCN.output.0.weight")[0];
+    const auto w = fold_wn(T_(h, "TCN.output.2.weight_g"), T_(h, "TCN.output.2.weight_v"), kBins * 2);
+    std::vector<float> wt((size_t)kC * kLogitStride, 0.f), bias(kLogitStride, 0.f);
+    for (int n = 0; n < kBins * 2; ++n) {
+      bias[n] = T_(h, "TCN.output.2.bias")[n];
+      for (int k = 0; k < kC; ++k) wt[(size_t)k * kLogitStride + n] = (float)w[(size_t)n * kC + k];
+    }
+    if (upload(h, T_(h, "TCN.output.1.weight"), &h->out_g) || upload(h, T_(h, "TCN.output.1.bias"), &h->out_be) ||
+        upload(h, pack_image(w, kBins * 2, kC, 3, 192), &h->out_img) || upload(h, wt, &h->out_wt) ||
+        upload(h, bias, &h->out_bias))
+      return SEPTFA_E_CUDA;
+  }
+  if (c.final_vad) {
+    const auto w1 = fold_wn(T_(h, "vad.common.conv1_1.weight_g"), T_(h, "vad.common.conv1_1.weight_v"), 4);  // [4][257][5]
+    std::vector<float> w1t((size_t)5 * 4 * kBins);
+    for (int j = 0; j < 4; ++j)
+      for (int f = 0; f < kBins; ++f)
+        for (int k = 0; k < 5; ++k) w1t[((size_t)k * 4 + j) * kBins + f] = (float)w1[((size_t)j * kBins + f) * 5 + k];
+    if (upload(h, w1t, &h->vad_w1t)) return SEPTFA_E_CUDA;
+    const auto w2 = fold_wn(T_(h, "vad.output_layer_vad.weight_g"), T_(h, "vad.output_layer_vad.weight_v"), 1);  // [1][4][3]
+    for (int j = 0; j < 4; ++j) {
+      h->vad_b1[j] = T_(h, "vad.common.conv1_1.bias")[j];
+      h->vad_g[j] = T_(h, "vad.common.BN_1.weight")[j];
+      h->vad_be[j] = T_(h, "vad.common.BN_1.bias")[j];
+      for (int k = 0; k < 3; ++k) h->vad_w2[j * 3 + k] = (float)w2[j * 3 + k];
+    }
+    h->vad_a = T_(h, "vad.common.relu_1.weight")[0];
+    h->vad_b2 = T_(h, "vad.output_layer_vad.bias")[0];
+  }
+  if (c.activity_input_bool) {
+    for (int i = 0; i < 9; ++i) h->act_k[i] = T_(h, "activity_input.weight")[i];
+    h->act_b = T_(h, "activity_input.bias")[0];
+    h->act_a = T_(h, "prelu.weight")[0];
+  }
+  h->committed = true;
+  return 0;
+}
+
+size_t septfa_workspace_bytes(const septfa_handle* h, int B, int64_t L) {
+  if (!h || B < 1 || L < 257) return 0;
+  return carve(h, nullptr, B, L).total + 256;
+}
+
+int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const septfa_infer_kw* kw, float* out_wav,
+                   float* out_vad, void* est_stft, float* mask, float* spectrum, float* logits_out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  if (int rc = check_forward_args(h, B, L)) return rc;
+  if (!x || !out_wav || !workspace) return fail(h, SEPTFA_E_INVALID, "null x / out_wav / workspace");
+  if (h->cfg.final_vad && !out_vad) return fail(h, SEPTFA_E_INVALID, "out_vad is required when final_vad is set");
+  if (workspace_bytes < septfa_workspace_bytes(h, B, L)) return fail(h, SEPTFA_E_WORKSPACE, "workspace too small");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  void* base = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  const Workspace ws = carve(h, base, B, L);
+  const int T = (int)septfa_num_frames(L);
+  const int M = B * T;
+  // engine is a bit mask of the contractions that run on the fp32 CUDA-core kernels
+  const bool tc_conv1 = !(h->engine & 1), tc_dconv = !(h->engine & 2), tc_out = !(h->engine & 4);
+  const auto& c = h->cfg;
+  g_launch_count = 0;
+
+  CUDA_TRY(h, cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, st));
+  launch_stft(x, B, L, T, h->win_fwd, h->twiddle, ws.S, ws.P, st);
+  launch_activity_gate(ws.P, B, T, c.activity_input_bool, h->act_k, h->act_b, h->act_a, ws.w, ws.dcg, ws.st0, st);
+  if (spectrum) launch_export(ws.S, ws.logits, nullptr, ws.w, ws.dcg, B, T, nullptr, nullptr, spectrum, nullptr, st);
+
+  const double inv_n = 1.0 / ((double)kC * T);
+  StreamNorm norm{ws.st0, h->ln_g, h->ln_b, 1e-8f, inv_n};  // TCN.LN, model.py:333
+  for (int i = 0; i < h->nblk; ++i) {
+    const DevBlock& d = h->blocks[i];
+    Stat2* st_p = ws.st_blk + (size_t)(i * 4 + 0) * B;
+    Stat2* st_q = ws.st_blk + (size_t)(i * 4 + 1) * B;
+    Stat2* st_v = ws.st_blk + (size_t)(i * 4 + 2) * B;
+    Stat2* st_w = ws.st_blk + (size_t)(i * 4 + 3) * B;
+    float* colsum = ws.colsum + (size_t)i * B * kC;
+
+    Conv1Params c1{ws.w, norm, M, T, B, d.b1, d.a1, d.w1_img, d.w1_t, ws.p, st_p};
+    if (tc_conv1) launch_tc_conv1(c1, st); else launch_ref_conv1(c1, st);
+
+    DconvParams dc{ws.p, st_p, d.g1, d.be1, d.w2b, d.a2, d.dil, M, T, B, d.w3_img, d.w3_t, ws.racc, ws.rowsum, colsum, st_q};
+    if (tc_dconv) launch_tc_dconv(dc, st); else launch_ref_dconv(dc, st);
+
+    GateParams gp{st_q, tc_dconv ? d.s3_tc : d.s3_ref, d.c03, ws.rowsum, colsum, d.tf, M, T, B, ws.ra, ws.rb, ws.gf, ws.gt};
+    launch_tf_gate(gp, st);
+
+    ResidParams rp{};
+    rp.w = ws.w; rp.norm = norm; rp.racc = ws.racc; rp.ra = ws.ra; rp.rb = ws.rb; rp.gf = ws.gf; rp.gt = ws.gt;
+    rp.M = M; rp.T = T; rp.B = B; rp.mode = h->ln_mode; rp.st_v = st_v; rp.st_w = st_w;
+    if (h->ln_mode == LN_RECURSIVE) {         // output = ln_second(output + ln_first(output + residual)), model.py:347-348
+      rp.g_a = d.lf_g; rp.b_a = d.lf_b;
+      launch_resid_stats(rp, st);
+      launch_resid_apply(rp, st);
+      norm = StreamNorm{st_w, d.ls_g, d.ls_b, 1e-5f, inv_n};
+    } else if (h->ln_mode == LN_RESIDUAL) {   // output = output + ln(residual), model.py:349-350
+      rp.g_a = d.lm_g; rp.b_a = d.lm_b;
+      launch_resid_stats(rp, st);
+      launch_resid_apply(rp, st);
+      norm = StreamNorm{nullptr, nullptr, nullptr, 0.f, inv_n};
+    } else {                                  // output = output + residual, model.py:351-352
+      launch_resid_apply(rp, st);
+      norm = StreamNorm{nullptr, nullptr, nullptr, 0.f, inv_n};
+    }
+  }
+  // output layer: PReLU -> GroupNorm -> conv (model.py:322-325,357)
+  launch_out_stats(ws.w, norm, h->out_a, M, T, ws.st_o, st);
+  OutConvParams oc{ws.w, norm, h->out_a, ws.st_o, h->out_g, h->out_be, M, T, B, h->out_bias, h->out_img, h->out_wt, ws.logits};
+  if (tc_out) launch_tc_outconv(oc, st); else launch_ref_outconv(oc, st);
+
+  const bool use_kw = kw != nullptr && c.final_vad;  // `if inference_kw and self.final_vad`, model.py:444
+  const float* gate = nullptr;
+  if (c.final_vad) {
+    VadParams vp{};
+    vp.logits = ws.logits; vp.M = M; vp.T = T; vp.B = B; vp.w1t = h->vad_w1t;
+    std::memcpy(vp.b1, h->vad_b1, sizeof(vp.b1)); vp.slope = h->vad_a;
+    std::memcpy(vp.g, h->vad_g, sizeof(vp.g)); std::memcpy(vp.be, h->vad_be, sizeof(vp.be));
+    std::memcpy(vp.w2, h->vad_w2, sizeof(vp.w2)); vp.b2 = h->vad_b2;
+    vp.c4 = ws.c4; vp.st_v = ws.st_vad; vp.prob = ws.prob; vp.smooth = ws.smooth;
+    vp.thr = use_kw ? kw->threshold_activated_vad : 0.f;
+    vp.do_smooth = use_kw ? 1 : 0;
+    launch_vad(vp, st);
+    if (use_kw && (kw->filter_signals_by_smo_vad || kw->filter_signals_by_unsmo_vad)) gate = ws.smooth;  // model.py:452-455
+    const float* vsrc = (use_kw && kw->return_smoothed_vad) ? ws.smooth : ws.prob;                      // model.py:456-457
+    CUDA_TRY(h, cudaMemcpyAsync(out_vad, vsrc, (size_t)M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  launch_mask_istft(ws.S, ws.logits, gate, h->win_inv, h->twiddle, B, L, T, out_wav, st);
+  launch_export(ws.S, ws.logits, gate, ws.w, ws.dcg, B, T, reinterpret_cast<float2*>(est_stft), mask, nullptr, logits_out, st);
+  h->last_launches = g_launch_count;
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L, const septfa_infer_kw* kw,
+                        float* out_wav_host, float* out_vad_host) {
+  if (int rc = check_forward_args(h, B, L)) return rc;
+  if (!x_host || !out_wav_host) return fail(h, SEPTFA_E_INVALID, "null host buffer");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (!h->hstream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+  const int64_t T = septfa_num_frames(L);
+  const size_t nx = (size_t)B * L * sizeof(float), nout = nx * 2, nvad = (size_t)B * 2 * T * sizeof(float);
+  const size_t nws = septfa_workspace_bytes(h, B, L);
+  auto grow = [&](float** dev, float** pin, size_t* cap, size_t need) -> cudaError_t {
+    if (*cap >= need) return cudaSuccess;
+    cudaFree(*dev); cudaFreeHost(*pin);
+    *dev = nullptr; *pin = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dev), need);
+    if (e != cudaSuccess) return e;
+    e = cudaMallocHost(reinterpret_cast<void**>(pin), need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+  };
+  CUDA_TRY(h, grow(&h->hx_dev, &h->hx_pin, &h->hcap_x, nx));
+  CUDA_TRY(h, grow(&h->hout_dev, &h->hout_pin, &h->hcap_out, nout));
+  CUDA_TRY(h, grow(&h->hvad_dev, &h->hvad_pin, &h->hcap_vad, nvad));
+  if (h->hcap_ws < nws) {
+    cudaFree(h->hws); h->hws = nullptr; h->hcap_ws = 0;
+    CUDA_TRY(h, cudaMalloc(&h->hws, nws));
+    h->hcap_ws = nws;
+  }
+  std::memcpy(h->hx_pin, x_host, nx);
+  CUDA_TRY(h, cudaMemcpyAsync(h->hx_dev, h->hx_pin, nx, cudaMemcpyHostToDevice, h->hstream));
+  if (int rc = septfa_forward(h, h->hx_dev, B, L, kw, h->hout_dev, h->hvad_dev, nullptr, nullptr, nullptr, nullptr, h->hws,
+                              h->hcap_ws, h->hstream))
+    return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->hout_pin, h->hout_dev, nout, cudaMemcpyDeviceToHost, h->hstream));
+  if (h->cfg.final_vad && out_vad_host)
+    CUDA_TRY(h, cudaMemcpyAsync(h->hvad_pin, h->hvad_dev, nvad, cudaMemcpyDeviceToHost, h->hstream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->hstream));
+  std::memcpy(out_wav_host, h->hout_pin, nout);
+  if (h->cfg.final_vad && out_vad_host) std::memcpy(out_vad_host, h->hvad_pin, nvad);
+  return 0;
+}
+
+int septfa_last_launch_count(const septfa_handle* h) { return h ? h->last_launches : 0; }
+
+// ------------------------------------------------------------------------------------------ online
+int septfa_online_create(septfa_handle* h, int S, septfa_online** out) {
+  if (!h || !out || S < 1) return fail(h, SEPTFA_E_INVALID, "bad arguments");
+  if (!h->committed) return fail(h, SEPTFA_E_STATE, "weights not committed");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  auto* o = new septfa_online();
+  o->h = h;
+  o->S = S;
+  const size_t tb = (size_t)S * 2 * kTailCap * sizeof(float);
+  if (cudaMalloc(reinterpret_cast<void**>(&o->tail[0]), tb) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&o->tail[1]), tb) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&o->acc), (size_t)S * 4 * sizeof(double)) != cudaSuccess) {
+    cudaFree(o->tail[0]); cudaFree(o->tail[1]); cudaFree(o->acc);
+    delete o;
+    return fail(h, SEPTFA_E_CUDA, "online state allocation failed");
+  }
+  *out = o;
+  return 0;
+}
+
+void septfa_online_destroy(septfa_online* o) {
+  if (!o) return;
+  cudaSetDevice(o->h->device);
+  cudaFree(o->tail[0]); cudaFree(o->tail[1]); cudaFree(o->acc);
+  delete o;
+}
+
+int septfa_online_reset(septfa_online* o, void*) {
+  if (!o) return SEPTFA_E_INVALID;
+  o->hops = 0; o->tail_len = 0; o->cur = 0;
+  return 0;
+}
+
+int septfa_online_hops_done(const septfa_online* o) { return o ? o->hops : 0; }
+
+size_t septfa_online_workspace_bytes(const septfa_online* o) {
+  if (!o) return 0;
+  const size_t pred = ((size_t)o->S * 2 * kWinLen * sizeof(float) + 255) & ~(size_t)255;
+  const size_t vad = ((size_t)o->S * 2 * septfa_num_frames(kWinLen) * sizeof(float) + 255) & ~(size_t)255;
+  return pred + vad + septfa_workspace_bytes(o->h, o->S, kWinLen) + 256;
+}
+
+int septfa_online_step(septfa_online* o, const float* win, const septfa_infer_kw* kw, float* emitted, int32_t* perm,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (!o || !win || !emitted || !perm || !workspace) return SEPTFA_E_INVALID;
+  septfa_handle* h = o->h;
+  if (workspace_bytes < septfa_online_workspace_bytes(o)) return fail(h, SEPTFA_E_WORKSPACE, "online workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  const size_t pred_b = ((size_t)o->S * 2 * kWinLen * sizeof(float) + 255) & ~(size_t)255;
+  const size_t vad_b = ((size_t)o->S * 2 * septfa_num_frames(kWinLen) * sizeof(float) + 255) & ~(size_t)255;
+  float* pred = reinterpret_cast<float*>(base);
+  float* vad = reinterpret_cast<float*>(base + pred_b);
+  void* fws = base + pred_b + vad_b;
+  // pred_separation, _, _ = self.model(truncated_signal_mix, inference_kw)   online_class_unknown_targets.py:84
+  if (int rc = septfa_forward(h, win, o->S, kWinLen, kw, pred, vad, nullptr, nullptr, nullptr, nullptr, fws,
+                              workspace_bytes - pred_b - vad_b - 256, st))
+    return rc;
+  int launches = h->last_launches;
+  g_launch_count = 0;
+  const int64_t Lw = kWinLen;
+  if (o->hops == 0) {
+    // indx == 0: online_signal = pred[..., -fs:] (not yet reordered) is what the overlap is compared to (:85-88)
+    launch_pit(pred + (Lw - 2 * kHopLen), 2 * Lw, Lw, pred + (Lw - kHopLen), 2 * Lw, Lw, o->S, kHopLen, o->acc, perm, st);
+  } else {
+    const int n = o->tail_len;  // min(emitted so far, 2 s)
+    launch_pit(pred + (Lw - kHopLen - n), 2 * Lw, Lw, o->tail[o->cur], 2 * (int64_t)kTailCap, kTailCap, o->S, n, o->acc,
+               perm, st);
+  }
+  // pred = reorder_source_mse(pred, perm); online_signal = cat(online_signal, pred[..., -fs:])   (:93-94)
+  launch_online_emit(pred, Lw, perm, o->S, kHopLen, kTailCap, o->tail[o->cur], o->tail_len, o->tail[o->cur ^ 1], emitted, st);
+  o->cur ^= 1;
+  o->tail_len = std::min(o->tail_len + kHopLen, kTailCap);
+  o->hops += 1;
+  h->last_launches = launches + g_launch_count;
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+int septfa_pit_l1(septfa_handle* h, const float* a, const float* b, int S, int64_t n, int32_t* perm, double* pw_sums,
+                  void* stream) {
+  if (!h || !a || !b || !perm || S < 1 || n < 1) return SEPTFA_E_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->pit_cap < S) {
+    cudaFree(h->pit_acc); h->pit_acc = nullptr; h->pit_cap = 0;
+    CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->pit_acc), (size_t)S * 4 * sizeof(double)));
+    h->pit_cap = S;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  launch_pit(a, 2 * n, n, b, 2 * n, n, S, n, h->pit_acc, perm, st);
+  if (pw_sums) CUDA_TRY(h, cudaMemcpyAsync(pw_sums, h->pit_acc, (size_t)S * 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

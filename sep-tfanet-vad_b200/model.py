@@ -1,0 +1,204 @@
+"""Drop-in ``SeparationModel`` (reference: model/model.py:360-461) backed by libseptfa.so.
+
+Same constructor (``SeparationModel(**config["arch"]["args"])``), same ``state_dict`` keys and
+shapes (so the reference ``.pth`` checkpoints load with ``strict=True``), same
+``forward(x, inference_kw={})`` return tuple and the same side-effect attributes
+(``mask_per_speaker``, ``spectrum``, ``masks_b``, ``estimated_stfts``). The arithmetic runs in
+the hand-written CUDA kernels behind the C ABI of ``include/septfa.h``; this class only owns
+torch tensors (parameters, inputs, outputs, workspace) and passes raw device pointers plus the
+current CUDA stream. There is no CPU path: inputs must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import lib as _lib
+from . import synth as _synth
+
+_DEFAULTS = {  # model/model.py:362-366
+    'n_fftBins': 512, 'BN_dim': 256, 'H_dim': 512, 'layer': 8, 'stack': 3, 'kernel': 3,
+    'num_spk': 2, 'skip': False, 'dilated': True, 'casual': False, 'bool_drop': True,
+    'drop_value': 0.1, 'weight_norm': False, 'final_vad': True, 'noisy_phase': False,
+    'activity_input_bool': False, 'tf_attention': False, 'apply_recursive_ln': False,
+    'apply_residual_ln': False, 'final_vad_masked_speakers': False}
+
+
+def _attach(root: nn.Module, dotted: str, tensor: torch.Tensor, buffer: bool):
+    """Register ``tensor`` under a dotted state_dict key, creating bare container modules."""
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, nn.Module())
+        mod = mod._modules[p]
+    if buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+class _Handle:
+    """One septfa_handle per CUDA device, with its weights committed."""
+
+    def __init__(self, cfg: "_lib.Config", device_index: int):
+        self.lib = _lib.load()
+        self.ptr = C.c_void_p()
+        rc = self.lib.septfa_create(C.byref(self.ptr), C.byref(cfg), device_index)
+        if rc != 0:
+            msg = self.lib.septfa_last_error(None)
+            raise _lib.SeptfaError(f"septfa_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.version = -1
+        self.workspace = None
+        self.device_index = device_index
+
+    def keys(self):
+        n = self.lib.septfa_num_keys(self.ptr)
+        return [(self.lib.septfa_key_name(self.ptr, i).decode(), self.lib.septfa_key_numel(self.ptr, i)) for i in range(n)]
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.septfa_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class SeparationModel(nn.Module):
+    def __init__(self, **config):
+        super().__init__()
+        defaults = dict(_DEFAULTS)
+        defaults.update(config)
+        print(defaults)  # the reference prints the merged dict (model/model.py:371)
+        for key, value in defaults.items():
+            setattr(self, key, value)
+        self._args = defaults
+        self.n_fftBins_h = self.n_fftBins // 2 + 1
+        # unsupported-at-these-configs branches fail loudly
+        if not self.weight_norm or self.skip or self.casual or not self.dilated or self.final_vad_masked_speakers:
+            raise NotImplementedError(
+                "septfa_b200 implements the shipped configurations only: weight_norm=True, skip=False, "
+                "casual=False, dilated=True, final_vad_masked_speakers=False")
+        if (self.n_fftBins, self.BN_dim, self.H_dim, self.num_spk) != (512, 256, 512, 2):
+            raise NotImplementedError("septfa_b200 needs n_fftBins=512, BN_dim=256, H_dim=512, num_spk=2")
+        # parameters / buffers with the reference's names and shapes (random init like a fresh reference module)
+        seed = int(torch.initial_seed()) & 0x7FFFFFFF
+        for k, v in _synth.make_state_dict(defaults, seed).items():
+            _attach(self, k, v.clone(), buffer=k.endswith("window"))
+        self._handles = {}
+        self._weights_version = 0
+        #: which optional outputs forward() materialises (all on = the reference's behaviour)
+        self.materialize = {"estimated_stfts": True, "mask_per_speaker": True, "spectrum": True, "masks_b": True}
+        self.engine = _lib.ENGINE_TCGEN05_F16
+        self.last_launch_count = 0
+
+    # -- weights ---------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._weights_version += 1
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._weights_version += 1
+        return out
+
+    def refresh_weights(self):
+        """Call after mutating parameters in place (the CUDA side keeps packed copies)."""
+        self._weights_version += 1
+
+    def set_engine(self, engine):
+        self.engine = int(engine)
+
+    def _handle(self, device: torch.device) -> _Handle:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
+            h = _Handle(_lib.Config.from_args(self._args), idx)
+            self._handles[idx] = h
+        if h.version != self._weights_version:
+            sd = super().state_dict()
+            for name, numel in h.keys():
+                t = sd[name].detach().to("cpu", torch.float32).contiguous()
+                if t.numel() != numel:
+                    raise _lib.SeptfaError(f"size mismatch for {name}")
+                _lib.check(h.ptr, h.lib.septfa_set_tensor(h.ptr, name.encode(), C.c_void_p(t.data_ptr()), numel))
+            _lib.check(h.ptr, h.lib.septfa_commit_weights(h.ptr))
+            h.version = self._weights_version
+        _lib.check(h.ptr, h.lib.septfa_set_option(h.ptr, b"engine", self.engine))
+        return h
+
+    # -- forward ---------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, inference_kw={}):
+        """x - 2-speaker mixed signal, shape = [B, T]  (model/model.py:402-461)"""
+        assert x.ndim == 2, "input tensor must be 2 dimensions (B, T), but got dimensions of {}".format(x.ndim)
+        if not x.is_cuda:
+            raise RuntimeError("septfa_b200.SeparationModel runs on CUDA (sm_100a) only: move the input to a B200 "
+                               "(there is no CPU fallback)")
+        kw = _lib.InferKw.from_dict(inference_kw) if (inference_kw and self.final_vad) else None
+        x = x.detach().to(torch.float32).contiguous()
+        B, L = x.shape
+        T = _lib.num_frames(L)
+        dev = x.device
+        with torch.cuda.device(dev):
+            h = self._handle(dev)
+            need = h.lib.septfa_workspace_bytes(h.ptr, B, L)
+            if need == 0:
+                raise _lib.SeptfaError(f"unsupported input shape B={B}, L={L} (need L >= 257)")
+            if h.workspace is None or h.workspace.numel() < need:
+                h.workspace = None
+                h.workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+            out = torch.empty((B, self.num_spk, L), dtype=torch.float32, device=dev)
+            vad = torch.empty((B, self.num_spk, T), dtype=torch.float32, device=dev) if self.final_vad else None
+            m = self.materialize
+            est = torch.empty((B, self.num_spk, self.n_fftBins_h, T, 2), dtype=torch.float32, device=dev) \
+                if m["estimated_stfts"] else None
+            mask = torch.empty((B, self.num_spk, self.n_fftBins_h, T), dtype=torch.float32, device=dev) \
+                if m["mask_per_speaker"] else None
+            spec = torch.empty((B, self.n_fftBins_h, T), dtype=torch.float32, device=dev) if m["spectrum"] else None
+            logits = torch.empty((B, self.n_fftBins_h * self.num_spk, T), dtype=torch.float32, device=dev) \
+                if m["masks_b"] else None
+            p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            rc = h.lib.septfa_forward(h.ptr, p(x), B, L, C.byref(kw) if kw is not None else None, p(out), p(vad),
+                                      p(est), p(mask), p(spec), p(logits), p(h.workspace), h.workspace.numel(), stream)
+            _lib.check(h.ptr, rc)
+            self.last_launch_count = h.lib.septfa_last_launch_count(h.ptr)
+        self.spectrum = spec
+        self.masks_b = logits
+        self.mask_per_speaker = mask
+        self.estimated_stfts = torch.view_as_complex(est) if est is not None else None
+        if not self.final_vad:
+            output_vad = 0                                    # model/model.py:426-427
+        elif kw is not None and kw.return_smoothed_vad:
+            output_vad = vad.unsqueeze(2)                     # [B, 2, 1, T], model/model.py:449-457
+        else:
+            output_vad = vad
+        return out, output_vad, self.estimated_stfts
+
+    def forward_host(self, x_host: torch.Tensor, inference_kw={}, device=0):
+        """End-to-end call with HOST tensors: septfa_forward_host does the H2D copy, the forward and
+        the D2H copy of (out_separation, output_vad) through pinned staging buffers."""
+        assert x_host.ndim == 2 and not x_host.is_cuda
+        kw = _lib.InferKw.from_dict(inference_kw) if (inference_kw and self.final_vad) else None
+        x_host = x_host.detach().to(torch.float32).contiguous()
+        B, L = x_host.shape
+        T = _lib.num_frames(L)
+        dev = torch.device("cuda", device)
+        with torch.cuda.device(dev):
+            h = self._handle(dev)
+            out = torch.empty((B, self.num_spk, L), dtype=torch.float32)
+            vad = torch.empty((B, self.num_spk, T), dtype=torch.float32) if self.final_vad else None
+            rc = h.lib.septfa_forward_host(h.ptr, C.c_void_p(x_host.data_ptr()), B, L,
+                                           C.byref(kw) if kw is not None else None, C.c_void_p(out.data_ptr()),
+                                           C.c_void_p(vad.data_ptr()) if vad is not None else None)
+            _lib.check(h.ptr, rc)
+            self.last_launch_count = h.lib.septfa_last_launch_count(h.ptr)
+        if not self.final_vad:
+            return out, 0
+        if kw is not None and kw.return_smoothed_vad:
+            return out, vad.unsqueeze(2)
+        return out, vad

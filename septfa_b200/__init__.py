@@ -1,0 +1,12 @@
+"""Import alias: the package lives in ``sep-tfanet-vad_b200/`` (not a valid Python identifier),
+so ``import septfa_b200`` loads that directory as the package ``septfa_b200``."""
+import importlib.util as _ilu
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "sep-tfanet-vad_b200")
+_spec = _ilu.spec_from_file_location("septfa_b200", _os.path.join(_dir, "__init__.py"),
+                                     submodule_search_locations=[_dir])
+_mod = _ilu.module_from_spec(_spec)
+_sys.modules["septfa_b200"] = _mod
+_spec.loader.exec_module(_mod)
