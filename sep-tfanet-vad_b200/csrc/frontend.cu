@@ -28,9 +28,9 @@ __device__ __forceinline__ void fft512_smem(float2* buf, const float2* tw) {
     const int pos = k & (half - 1);
     const int i0 = ((k >> s) << (s + 1)) + pos;
     const int i1 = i0 + half;
+    __syncthreads();  // also orders the caller's writes of buf / tw before the first stage
     float2 w = tw[pos << (8 - s)];
     if (INVERSE) w.y = -w.y;
-    __syncthreads();
     const float2 a = buf[i0], b = buf[i1];
     const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
     buf[i0] = make_float2(a.x + t.x, a.y + t.y);
