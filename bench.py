@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Benchmark of the Sep-TFAnet-VAD inference forward pass (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU port of the reference path (oracle)
+
+A "step" is one forward pass over one batch of synthetic noisy two-speaker mixtures
+(BASELINE.json configs[1]: config_with_vad.json, 256 x 4 s per GPU, filter_signals_by_smo_vad).
+Metric: mixture-seconds processed per second, whole job (all N GPUs). Weak scaling: every rank
+runs the same per-GPU batch on its own shard of mixtures; there is no collective on the data
+path, torch.distributed only takes the MAX of the per-rank times.
+
+Prints ONE JSON line (rank 0) with the keys the driver contract asks for, plus:
+  roofline     - dominant kernel (tcgen05 dconv+res_out GEMM): algorithmic FLOP per launch divided by
+                 its CUDA-event duration, against the measured bf16 peak (MEASURED_PEAKS.json)
+  kernels      - per-kernel-class device time per step (CUDA events on the launch stream)
+  cpu_baseline - the numpy port of the reference path timed on this box's host cores (bounded sample)
+  e2e          - the same metric through SeparationModel.forward_host: pinned host buffers, H2D and D2H inside
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 16000
+MAC_PER_FRAME = 4899657                     # algorithmic MACs per STFT frame
+DCONV_MAC_PER_FRAME = 131072 + 1536         # res_out 512->256 + depthwise k3 (the dominant kernel's share)
+CONV1_MAC_PER_FRAME = 65536
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return 1400.0, 6650.0, "fallback"  # /opt/skills/guides/B200_PROFILING.md
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            load = [s for s in sm if s >= 0.5 * max(sm)] or sm
+            out = {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def cpu_reference_throughput(n_mix, length, repeats=1):
+    """The oracle (numpy port of the reference path, fp32, BLAS threads = all host cores) on a bounded
+    sample of the same workload. Returns (audio-seconds per second, seconds per pass)."""
+    import numpy as np
+    from oracle import septfa_oracle as O
+    from septfa_b200 import synth
+    args = synth.CONFIG_WITH_VAD
+    W = O.OracleWeights(synth.make_state_dict_numpy(args, 0), args, np.float32)
+    x = synth.make_mixtures(n_mix, length, 1234)
+    kw = dict(synth.DEFAULT_INFERENCE_KW, filter_signals_by_smo_vad=True)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.forward(x, W, dict(kw))
+        best = min(best, time.perf_counter() - t0)
+    return n_mix * length / FS / best, best
+
+
+def run_reference(a, rank, world):
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    n_mix = a.ref_sample
+    # warm-up + timed steps, each a bounded sample of the workload
+    for _ in range(a.warmup):
+        cpu_reference_throughput(1, a.length)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cpu_reference_throughput(n_mix, a.length)
+    dt = time.perf_counter() - t0
+    value = a.steps * n_mix * a.length / FS / dt
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "mixture-seconds processed per second (offline forward)", "value": value,
+        "unit": "audio-s/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"config_with_vad, {a.batch} x {a.length / FS:g} s mixtures per GPU, "
+                               "filter_signals_by_smo_vad", "sample": f"{n_mix} x {a.length / FS:g} s per step"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_mix} x {a.length / FS:g} s mixtures per step, {a.steps} steps, numpy fp32 "
+                                   "port of model/model.py:402-461 (oracle/septfa_oracle.py)"},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="mixtures per GPU per step")
+    ap.add_argument("--length", type=int, default=64000, help="samples per mixture (4 s @ 16 kHz)")
+    ap.add_argument("--ref-sample", type=int, default=8, help="mixtures per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="mixtures of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lean", action="store_true", help="skip the optional exports (est/mask/spectrum/logits)")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from septfa_b200 import synth
+    from septfa_b200.model import SeparationModel
+    from septfa_b200.shard import gather_max_time, shard_range
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    args = synth.CONFIG_WITH_VAD
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = SeparationModel(**args)
+    model.load_state_dict(synth.make_state_dict(args, 0), strict=True)
+    model.eval().to(dev)
+    if a.lean:
+        model.materialize.update(estimated_stfts=False, mask_per_speaker=False, spectrum=False, masks_b=False)
+    kw = dict(synth.DEFAULT_INFERENCE_KW, filter_signals_by_smo_vad=True)
+
+    # this rank's shard of the global batch (distinct mixtures per rank; 32 distinct ones tiled)
+    B, L = a.batch, a.length
+    g0, _ = shard_range(world * B, rank, world)
+    n_distinct = min(B, 32)
+    base = synth.make_mixtures(n_distinct, L, 1234, first_index=g0)
+    x_host = torch.from_numpy(np.tile(base, ((B + n_distinct - 1) // n_distinct, 1))[:B]).pin_memory()
+    x_dev = x_host.to(dev)
+    T = 1 + L // 256
+
+    def step():
+        return model(x_dev, kw)
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`): CUDA events on the launch stream, max over ranks
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_dev = gather_max_time(e0.elapsed_time(e1) * 1e-3)
+    clocks = sampler.stop() if sampler else None
+    launches = model.last_launch_count * a.steps
+
+    # ---- per-kernel-class timing (separate pass; events inside forward on the same stream)
+    model.set_profile(True)
+    for _ in range(a.steps):
+        step()
+    prof = model.read_profile(dev)
+    model.set_profile(False)
+    kernels = {k: {"ms_per_step": v[0] / a.steps, "launches_per_step": v[1] / a.steps} for k, v in prof.items()}
+
+    # ---- end to end through the public host API (pinned host buffers, H2D + D2H inside)
+    out_h = None
+    for _ in range(2):
+        out_h = model.forward_host(x_host, kw, device=local_rank)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        out_h = model.forward_host(x_host, kw, device=local_rank)
+    t_e2e = gather_max_time(time.perf_counter() - t0)
+    assert out_h[0].shape == (B, 2, L)
+
+    if rank == 0:
+        audio_s = world * B * L / FS * a.steps
+        peak_tf, peak_hbm, peak_src = measured_peaks()
+        M = B * T
+        d_ms, d_n = prof["dconv"]
+        dconv_ms = d_ms / max(d_n, 1)
+        flop_per_launch = 2.0 * DCONV_MAC_PER_FRAME * M
+        achieved = flop_per_launch / (dconv_ms * 1e-3) / 1e12 if dconv_ms > 0 else 0.0
+        c_ms, c_n = prof["conv1"]
+        conv1_tf = 2.0 * CONV1_MAC_PER_FRAME * M / (c_ms / max(c_n, 1) * 1e-3) / 1e12 if c_ms > 0 else 0.0
+        line = {
+            "metric": "mixture-seconds processed per second (offline forward)",
+            "value": audio_s / t_dev, "unit": "audio-s/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16xf16->f32 (tcgen05), f32 elsewhere", "data": "synthetic",
+            "config": {"workload": f"config_with_vad, {B} x {L / FS:g} s mixtures per GPU, filter_signals_by_smo_vad "
+                                   "(BASELINE.json configs[1])", "frames_per_step_per_gpu": M,
+                       "l2": "working set ~0.6 GB per step >> 126 MB L2 (no explicit flush)",
+                       "weights": "seeded random-init, reference layout", "exports": not a.lean},
+            "model_flops_utilization": 2.0 * MAC_PER_FRAME * M * world * a.steps / t_dev / 1e12 / (peak_tf * world),
+            "roofline": {"kernel": "k_tc_gemm<1> (depthwise conv prologue + res_out 512->256 tcgen05 GEMM)",
+                         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "ms_per_launch": dconv_ms, "flop_per_launch": flop_per_launch,
+                         "conv1_tflops": conv1_tf},
+            "kernels": kernels,
+            "e2e": {"value": audio_s / t_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
+                    "d2h_bytes_per_step": int(B * 2 * L * 4 + B * 2 * T * 4), "ms_per_step": 1e3 * t_e2e / a.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            v, secs = cpu_reference_throughput(a.cpu_sample, L)
+            line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{a.cpu_sample} x {L / FS:g} s mixtures, one pass ({secs:.1f} s), numpy "
+                                              "fp32 port of model/model.py:402-461 (oracle/septfa_oracle.py)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -101,7 +101,7 @@ int septfa_num_keys(const septfa_handle* h);
 const char* septfa_key_name(const septfa_handle* h, int i);
 int64_t septfa_key_numel(const septfa_handle* h, int i);
 
-/* name = "engine" (SEPTFA_ENGINE_*). */
+/* name = "engine" (SEPTFA_ENGINE_*) or "profile" (0/1). */
 int septfa_set_option(septfa_handle* h, const char* name, int value);
 int septfa_get_option(const septfa_handle* h, const char* name);
 
@@ -121,6 +121,21 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
 
 /* Number of GPU kernels launched by the last forward / online step on this handle. */
 int septfa_last_launch_count(const septfa_handle* h);
+
+/* Per-kernel-class device timing. With option "profile" = 1, forward records CUDA events on its
+ * launch stream around each class of kernels; septfa_profile_read waits for them and returns the
+ * accumulated milliseconds and interval counts per class (arrays of SEPTFA_PROF_NCAT). */
+#define SEPTFA_PROF_FRONTEND 0 /* memset + STFT/dB + activity gate (+ spectrum export) */
+#define SEPTFA_PROF_CONV1 1    /* tcgen05 GEMM 256->256 with GroupNorm prologue, PReLU/stats epilogue */
+#define SEPTFA_PROF_DCONV 2    /* tcgen05 GEMM 512->256 with depthwise-conv prologue */
+#define SEPTFA_PROF_GATE 3     /* TF-attention gates */
+#define SEPTFA_PROF_RESID 4    /* post-block GroupNorm residual kernels */
+#define SEPTFA_PROF_OUTCONV 5  /* output statistics + tcgen05 GEMM 256->514 */
+#define SEPTFA_PROF_VAD 6      /* VAD head + smoothing */
+#define SEPTFA_PROF_ISTFT 7    /* mask + inverse STFT overlap-add */
+#define SEPTFA_PROF_EXPORT 8   /* optional torch-layout exports */
+#define SEPTFA_PROF_NCAT 9
+int septfa_profile_read(septfa_handle* h, double* ms, int* launches, int n, int reset);
 
 /* ---- online mode: OnlineSaving.calc_online, one hop for S independent streams -------------
  * State kept on the device per stream: the last <= 2 s of already-emitted (permutation-fixed)

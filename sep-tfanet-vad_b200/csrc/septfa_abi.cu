@@ -61,6 +61,13 @@ struct septfa_handle {
   size_t hcap_x = 0, hcap_out = 0, hcap_vad = 0, hcap_ws = 0;
   // pit scratch
   double* pit_acc = nullptr; int pit_cap = 0;
+  // optional per-kernel-class profiling (CUDA events recorded on the launch stream)
+  int profile = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_cat;   // category of the interval that STARTS at event i
+  int ev_used = 0;
+  double prof_ms[SEPTFA_PROF_NCAT] = {0};
+  int prof_launches[SEPTFA_PROF_NCAT] = {0};
 };
 
 struct septfa_online {
@@ -237,6 +244,20 @@ Workspace carve(const septfa_handle* h, void* base, int B, int64_t L) {
   return w;
 }
 
+// Record an event that starts an interval of category `cat` (cat < 0: closing event).
+void prof_mark(septfa_handle* h, int cat, cudaStream_t st) {
+  if (!h->profile) return;
+  if (h->ev_used == (int)h->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+    h->ev_cat.push_back(-1);
+  }
+  cudaEventRecord(h->ev_pool[h->ev_used], st);
+  h->ev_cat[h->ev_used] = cat;
+  ++h->ev_used;
+}
+
 int check_forward_args(septfa_handle* h, int B, int64_t L) {
   if (!h) return SEPTFA_E_INVALID;
   if (!h->committed) return fail(h, SEPTFA_E_STATE, "weights not committed");
@@ -296,6 +317,7 @@ void septfa_destroy(septfa_handle* h) {
   cudaFree(h->hx_dev); cudaFree(h->hout_dev); cudaFree(h->hvad_dev); cudaFree(h->hws); cudaFree(h->pit_acc);
   cudaFreeHost(h->hx_pin); cudaFreeHost(h->hout_pin); cudaFreeHost(h->hvad_pin);
   if (h->hstream) cudaStreamDestroy(h->hstream);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -328,10 +350,15 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
     h->engine = value;
     return 0;
   }
+  if (std::strcmp(name, "profile") == 0) {
+    h->profile = value ? 1 : 0;
+    return 0;
+  }
   return fail(h, SEPTFA_E_INVALID, std::string("unknown option ") + name);
 }
 int septfa_get_option(const septfa_handle* h, const char* name) {
   if (h && name && std::strcmp(name, "engine") == 0) return h->engine;
+  if (h && name && std::strcmp(name, "profile") == 0) return h->profile;
   return SEPTFA_E_INVALID;
 }
 
@@ -498,6 +525,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   const auto& c = h->cfg;
   g_launch_count = 0;
 
+  prof_mark(h, SEPTFA_PROF_FRONTEND, st);
   CUDA_TRY(h, cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, st));
   launch_stft(x, B, L, T, h->win_fwd, h->twiddle, ws.S, ws.P, st);
   launch_activity_gate(ws.P, B, T, c.activity_input_bool, h->act_k, h->act_b, h->act_a, ws.w, ws.dcg, ws.st0, st);
@@ -514,13 +542,17 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     float* colsum = ws.colsum + (size_t)i * B * kC;
 
     Conv1Params c1{ws.w, norm, M, T, B, d.b1, d.a1, d.w1_img, d.w1_t, ws.p, st_p};
+    prof_mark(h, SEPTFA_PROF_CONV1, st);
     if (tc_conv1) launch_tc_conv1(c1, st); else launch_ref_conv1(c1, st);
 
+    prof_mark(h, SEPTFA_PROF_DCONV, st);
     DconvParams dc{ws.p, st_p, d.g1, d.be1, d.w2b, d.a2, d.dil, M, T, B, d.w3_img, d.w3_t, ws.racc, ws.rowsum, colsum, st_q};
     if (tc_dconv) launch_tc_dconv(dc, st); else launch_ref_dconv(dc, st);
 
+    prof_mark(h, SEPTFA_PROF_GATE, st);
     GateParams gp{st_q, tc_dconv ? d.s3_tc : d.s3_ref, d.c03, ws.rowsum, colsum, d.tf, M, T, B, ws.ra, ws.rb, ws.gf, ws.gt};
     launch_tf_gate(gp, st);
+    prof_mark(h, SEPTFA_PROF_RESID, st);
 
     ResidParams rp{};
     rp.w = ws.w; rp.norm = norm; rp.racc = ws.racc; rp.ra = ws.ra; rp.rb = ws.rb; rp.gf = ws.gf; rp.gt = ws.gt;
@@ -541,10 +573,12 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     }
   }
   // output layer: PReLU -> GroupNorm -> conv (model.py:322-325,357)
+  prof_mark(h, SEPTFA_PROF_OUTCONV, st);
   launch_out_stats(ws.w, norm, h->out_a, M, T, ws.st_o, st);
   OutConvParams oc{ws.w, norm, h->out_a, ws.st_o, h->out_g, h->out_be, M, T, B, h->out_bias, h->out_img, h->out_wt, ws.logits};
   if (tc_out) launch_tc_outconv(oc, st); else launch_ref_outconv(oc, st);
 
+  prof_mark(h, SEPTFA_PROF_VAD, st);
   const bool use_kw = kw != nullptr && c.final_vad;  // `if inference_kw and self.final_vad`, model.py:444
   const float* gate = nullptr;
   if (c.final_vad) {
@@ -561,10 +595,36 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     const float* vsrc = (use_kw && kw->return_smoothed_vad) ? ws.smooth : ws.prob;                      // model.py:456-457
     CUDA_TRY(h, cudaMemcpyAsync(out_vad, vsrc, (size_t)M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+  prof_mark(h, SEPTFA_PROF_ISTFT, st);
   launch_mask_istft(ws.S, ws.logits, gate, h->win_inv, h->twiddle, B, L, T, out_wav, st);
+  prof_mark(h, SEPTFA_PROF_EXPORT, st);
   launch_export(ws.S, ws.logits, gate, ws.w, ws.dcg, B, T, reinterpret_cast<float2*>(est_stft), mask, nullptr, logits_out, st);
+  prof_mark(h, -1, st);
   h->last_launches = g_launch_count;
   CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+int septfa_profile_read(septfa_handle* h, double* ms, int* launches, int n, int reset) {
+  if (!h || !ms || n < SEPTFA_PROF_NCAT) return SEPTFA_E_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->ev_used > 0) {
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_pool[h->ev_used - 1]));
+    for (int i = 0; i + 1 < h->ev_used; ++i) {
+      const int cat = h->ev_cat[i];
+      if (cat < 0) continue;
+      float t = 0.f;
+      CUDA_TRY(h, cudaEventElapsedTime(&t, h->ev_pool[i], h->ev_pool[i + 1]));
+      h->prof_ms[cat] += t;
+      h->prof_launches[cat] += 1;
+    }
+    h->ev_used = 0;
+  }
+  for (int i = 0; i < SEPTFA_PROF_NCAT; ++i) {
+    ms[i] = h->prof_ms[i];
+    if (launches) launches[i] = h->prof_launches[i];
+    if (reset) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+  }
   return 0;
 }
 
@@ -595,17 +655,25 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
     CUDA_TRY(h, cudaMalloc(&h->hws, nws));
     h->hcap_ws = nws;
   }
-  std::memcpy(h->hx_pin, x_host, nx);
-  CUDA_TRY(h, cudaMemcpyAsync(h->hx_dev, h->hx_pin, nx, cudaMemcpyHostToDevice, h->hstream));
+  // Page-locked caller buffers are copied directly; pageable ones go through the pinned staging buffers.
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const bool pin_x = is_pinned(x_host), pin_out = is_pinned(out_wav_host);
+  const bool pin_vad = out_vad_host != nullptr && is_pinned(out_vad_host);
+  if (!pin_x) std::memcpy(h->hx_pin, x_host, nx);
+  CUDA_TRY(h, cudaMemcpyAsync(h->hx_dev, pin_x ? x_host : h->hx_pin, nx, cudaMemcpyHostToDevice, h->hstream));
   if (int rc = septfa_forward(h, h->hx_dev, B, L, kw, h->hout_dev, h->hvad_dev, nullptr, nullptr, nullptr, nullptr, h->hws,
                               h->hcap_ws, h->hstream))
     return rc;
-  CUDA_TRY(h, cudaMemcpyAsync(h->hout_pin, h->hout_dev, nout, cudaMemcpyDeviceToHost, h->hstream));
+  CUDA_TRY(h, cudaMemcpyAsync(pin_out ? out_wav_host : h->hout_pin, h->hout_dev, nout, cudaMemcpyDeviceToHost, h->hstream));
   if (h->cfg.final_vad && out_vad_host)
-    CUDA_TRY(h, cudaMemcpyAsync(h->hvad_pin, h->hvad_dev, nvad, cudaMemcpyDeviceToHost, h->hstream));
+    CUDA_TRY(h, cudaMemcpyAsync(pin_vad ? out_vad_host : h->hvad_pin, h->hvad_dev, nvad, cudaMemcpyDeviceToHost, h->hstream));
   CUDA_TRY(h, cudaStreamSynchronize(h->hstream));
-  std::memcpy(out_wav_host, h->hout_pin, nout);
-  if (h->cfg.final_vad && out_vad_host) std::memcpy(out_vad_host, h->hvad_pin, nvad);
+  if (!pin_out) std::memcpy(out_wav_host, h->hout_pin, nout);
+  if (h->cfg.final_vad && out_vad_host && !pin_vad) std::memcpy(out_vad_host, h->hvad_pin, nvad);
   return 0;
 }
 

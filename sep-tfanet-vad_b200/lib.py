@@ -78,6 +78,7 @@ _PROTOS = {
     "septfa_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.POINTER(InferKw), C.c_void_p,
                                       C.c_void_p]),
     "septfa_last_launch_count": (C.c_int, [C.c_void_p]),
+    "septfa_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int, C.c_int]),
     "septfa_online_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "septfa_online_destroy": (None, [C.c_void_p]),
     "septfa_online_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -113,6 +114,9 @@ def check(handle, rc):
     if rc != 0:
         msg = load().septfa_last_error(handle)
         raise SeptfaError(f"septfa error {rc}: {msg.decode() if msg else ''}")
+
+
+PROF_NAMES = ("frontend", "conv1", "dconv", "gate", "resid", "outconv", "vad", "istft", "export")
 
 
 def num_frames(L):

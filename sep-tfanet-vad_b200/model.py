@@ -113,6 +113,19 @@ class SeparationModel(nn.Module):
     def set_engine(self, engine):
         self.engine = int(engine)
 
+    def set_profile(self, on: bool):
+        """Per-kernel-class CUDA-event timing inside forward (septfa_set_option "profile")."""
+        self._profile = bool(on)
+
+    def read_profile(self, device=None, reset=True):
+        """{class name: (milliseconds, intervals)} accumulated since the last reset."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = self._handle(dev)
+        ms = (C.c_double * 16)()
+        cnt = (C.c_int * 16)()
+        _lib.check(h.ptr, h.lib.septfa_profile_read(h.ptr, ms, cnt, 16, int(reset)))
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(_lib.PROF_NAMES)}
+
     def _handle(self, device: torch.device) -> _Handle:
         idx = device.index if device.index is not None else torch.cuda.current_device()
         h = self._handles.get(idx)
@@ -129,6 +142,7 @@ class SeparationModel(nn.Module):
             _lib.check(h.ptr, h.lib.septfa_commit_weights(h.ptr))
             h.version = self._weights_version
         _lib.check(h.ptr, h.lib.septfa_set_option(h.ptr, b"engine", self.engine))
+        _lib.check(h.ptr, h.lib.septfa_set_option(h.ptr, b"profile", int(getattr(self, "_profile", False))))
         return h
 
     # -- forward ---------------------------------------------------------------------------

@@ -1,0 +1,59 @@
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def load_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return g, json.loads(str(g["meta"]))
+
+
+def sisdr_db(est, ref):
+    """Minimum SI-SDR (dB) of est against ref over all leading axes (model/combined_loss.py:16-56, no eps)."""
+    est = np.asarray(est, dtype=np.float64).reshape(-1, est.shape[-1])
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1, ref.shape[-1])
+    keep = (ref ** 2).sum(-1) > 0
+    est, ref = est[keep], ref[keep]
+    a = (est * ref).sum(-1, keepdims=True) / (ref ** 2).sum(-1, keepdims=True)
+    noise = a * ref - est
+    return float((10 * np.log10(((a * ref) ** 2).sum(-1) / np.maximum((noise ** 2).sum(-1), 1e-300))).min())
+
+
+def build_cuda_model(args, weight_seed, engine=0):
+    import torch
+    from septfa_b200 import synth
+    from septfa_b200.model import SeparationModel
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = SeparationModel(**args)
+    m.load_state_dict(synth.make_state_dict(args, weight_seed), strict=True)
+    m.eval().to(torch.device("cuda", 0))
+    m.set_engine(engine)
+    return m
+
+
+@pytest.fixture(scope="session")
+def cuda_models():
+    """Cache of CUDA models keyed by (config name, weight seed)."""
+    cache = {}
+
+    def get(args, seed, engine=0):
+        key = (json.dumps(args, sort_keys=True), seed)
+        if key not in cache:
+            cache[key] = build_cuda_model(args, seed)
+        cache[key].set_engine(engine)
+        return cache[key]
+    return get

@@ -1,0 +1,145 @@
+"""CPU: host-side logic - the C ABI library loads and exports every symbol include/septfa.h
+declares, the drop-in module keeps the reference's state_dict layout, PIT / reorder / SI-SDR
+helpers, seeded synthetic inputs, the batch sharding plan (incl. a 2-rank gloo run)."""
+import contextlib
+import ctypes
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+from septfa_b200 import lib as L
+from septfa_b200 import synth
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "septfa.h")).read()
+    declared = set(re.findall(r"\b(septfa_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found"
+    assert os.path.exists(L.LIB_PATH), "libseptfa.so not built (python -m septfa_b200.build)"
+    so = ctypes.CDLL(L.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(so, name), f"{name} declared in septfa.h but not exported"
+    assert declared == set(L.EXPORTED_SYMBOLS), "ctypes prototypes out of sync with the header"
+    lib = L.load()
+    assert b"sm_100a" in lib.septfa_version()
+    assert lib.septfa_num_frames(64000) == 251 and lib.septfa_num_frames(48000) == 188
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from septfa_b200.model import SeparationModel
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = SeparationModel(**synth.CONFIG_WITH_VAD)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 4000))
+    # the C ABI refuses too: no device -> error code, never a silent CPU path
+    lib = L.load()
+    h = ctypes.c_void_p()
+    cfg = L.Config.from_args(synth.CONFIG_WITH_VAD)
+    assert lib.septfa_create(ctypes.byref(h), ctypes.byref(cfg), 0) != 0
+    assert b"CUDA" in lib.septfa_last_error(None)
+
+
+@pytest.mark.parametrize("name,cfg", [("with_vad", synth.CONFIG_WITH_VAD), ("without_vad", synth.CONFIG_WITHOUT_VAD)])
+def test_state_dict_layout_equals_reference(name, cfg):
+    """Keys, order and shapes recorded from the reference's own SeparationModel (make_golden env)."""
+    from septfa_b200.model import SeparationModel
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))[name]
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        m = SeparationModel(**cfg)
+    assert "n_fftBins" in out.getvalue()  # the reference prints the merged config (model/model.py:371)
+    mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert list(mine.keys()) == list(ref.keys())
+    assert mine == ref
+    m.load_state_dict(synth.make_state_dict(cfg, 11), strict=True)
+    bad = synth.make_state_dict(cfg, 11)
+    bad.pop("TCN.LN.weight")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+
+
+def test_unsupported_configs_fail_loudly():
+    from septfa_b200.model import SeparationModel
+    for bad in ({"casual": True}, {"skip": True}, {"weight_norm": False}, {"dilated": False}, {"BN_dim": 128}):
+        with contextlib.redirect_stdout(io.StringIO()), pytest.raises(NotImplementedError):
+            SeparationModel(**dict(synth.CONFIG_WITH_VAD, **bad))
+
+
+def test_infer_kw_semantics():
+    assert L.InferKw.from_dict({}) is None
+    with pytest.raises(KeyError):  # missing keys raise like model/model.py:445-456
+        L.InferKw.from_dict({"filter_signals_by_smo_vad": True})
+    kw = L.InferKw.from_dict(dict(synth.DEFAULT_INFERENCE_KW, threshold_activated_vad=0.3))
+    assert abs(kw.threshold_activated_vad - 0.3) < 1e-7 and kw.length_smoothing_filter == 3
+
+
+def test_pit_host_helpers_match_reference_semantics():
+    from septfa_b200.pit import PITLossWrapper, calc_sisdr, reorder_source_mse
+    torch.manual_seed(0)
+    tgt = torch.randn(3, 2, 500)
+    est = tgt[:, [1, 0]] + 0.01 * torch.randn(3, 2, 500)
+    w = PITLossWrapper(torch.nn.L1Loss(), pit_from="pw_pt", per_stream=True)
+    loss, idx = w(est, tgt, return_incides=True)
+    assert idx.tolist() == [[1, 0]] * 3
+    assert torch.allclose(reorder_source_mse(est, idx), est[:, [1, 0]])
+    # reference quirk: nn.L1Loss reduces over the batch -> one joint decision (model/pit_wrapper.py:173-176)
+    mixed_est = torch.cat([tgt[:1], tgt[1:, [1, 0]]])
+    _, joint = PITLossWrapper(torch.nn.L1Loss(), pit_from="pw_pt")(mixed_est, tgt, return_incides=True)
+    assert joint.tolist() == [[1, 0]] * 3
+    _, per = PITLossWrapper(torch.nn.L1Loss(), pit_from="pw_pt", per_stream=True)(mixed_est, tgt, return_incides=True)
+    assert per.tolist() == [[0, 1], [1, 0], [1, 0]]
+    # ties -> identity
+    z = torch.zeros(1, 2, 10)
+    assert PITLossWrapper(torch.nn.L1Loss(), pit_from="pw_pt")(z, z, return_incides=True)[1].tolist() == [[0, 1]]
+    v = calc_sisdr(torch.tensor([2.5, 0.0, 2.0, 8.0]), torch.tensor([3.0, -0.5, 2.0, 7.0]), zero_mean=False)
+    assert abs(v.item() - 18.4030) < 1e-3
+
+
+def test_synth_is_deterministic_and_normalised():
+    a = synth.make_mixtures(2, 5000, 77)
+    b = synth.make_mixtures(2, 5000, 77)
+    assert np.array_equal(a, b) and a.dtype == np.float32
+    assert abs(a.max() - 0.9) < 1e-6 and abs(a.min() + 0.9) < 1e-6  # only_inference.py:81
+    sd = synth.make_state_dict_numpy(synth.CONFIG_WITH_VAD, 5)
+    assert len(sd) == 719 and sum(v.size for k, v in sd.items() if "window" not in k) == 5005347
+
+
+def test_shard_plan():
+    from septfa_b200.shard import shard_range
+    for n, w in ((8192, 8), (10, 4), (3, 8), (256, 1)):
+        parts = [shard_range(n, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_sharding_and_metric_gather(tmp_path):
+    """world_size-2 gloo run of the sharding/gather host logic (the data path has no collective)."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from septfa_b200.shard import shard_range, gather_max_time, gather_counts\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "a, b = shard_range(11, r, w)\n"
+        "tot = gather_counts(b - a)\n"
+        "t = gather_max_time(0.5 + r)\n"
+        "assert tot == 11 and abs(t - 1.5) < 1e-9, (tot, t)\n"
+        "if r == 0: print('OK', tot, t)\n"
+        "dist.destroy_process_group()\n")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                       capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "OK 11 1.5" in r.stdout
