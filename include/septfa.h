@@ -101,7 +101,8 @@ int septfa_num_keys(const septfa_handle* h);
 const char* septfa_key_name(const septfa_handle* h, int i);
 int64_t septfa_key_numel(const septfa_handle* h, int i);
 
-/* name = "engine" (SEPTFA_ENGINE_*) or "profile" (0/1). */
+/* name = "engine" (SEPTFA_ENGINE_*), "profile" (0/1), or "host_chunks" (0 = automatic, 1..8: number of
+ * batch chunks septfa_forward_host pipelines over its copy-in / compute / copy-out streams). */
 int septfa_set_option(septfa_handle* h, const char* name, int value);
 int septfa_get_option(const septfa_handle* h, const char* name);
 
@@ -113,9 +114,11 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
                    float* out_wav, float* out_vad, void* est_stft, float* mask, float* spectrum,
                    float* logits, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Same, from/to HOST buffers: copies x host->device, runs forward, copies out_wav/out_vad back
- * (pinned staging owned by the handle) and waits for completion. This is the call a caller
- * without device memory of its own makes (only_inference.py:90-91 semantics). */
+/* Same, from/to HOST buffers: copies x host->device, runs forward, copies out_wav/out_vad back and
+ * waits for completion. Page-locked caller buffers are used directly, pageable ones go through
+ * pinned staging owned by the handle. The batch is processed in chunks so that copies overlap the
+ * kernels (utterances are independent). This is the call a caller without device memory of its
+ * own makes (only_inference.py:90-91 semantics). */
 int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L, const septfa_infer_kw* kw,
                         float* out_wav_host, float* out_vad_host);
 

@@ -3,80 +3,98 @@
 // Reference: model/model.py:173-179 (VAD), :423-457 (masks, noisy phase, inference gating),
 // :460 (InverseSpectrogram -> torch.istft).
 #include "kernels.h"
+#include "fft512.cuh"
 
 namespace septfa {
 
-template <bool INVERSE>
-__device__ __forceinline__ void fft512_smem_be(float2* buf, const float2* tw) {
-  const int k = threadIdx.x;
-#pragma unroll
-  for (int s = 0; s < 9; ++s) {
-    const int half = 1 << s;
-    const int pos = k & (half - 1);
-    const int i0 = ((k >> s) << (s + 1)) + pos;
-    const int i1 = i0 + half;
-    __syncthreads();  // also orders the caller's writes of buf / tw before the first stage
-    float2 w = tw[pos << (8 - s)];
-    if (INVERSE) w.y = -w.y;
-    const float2 a = buf[i0], b = buf[i1];
-    const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
-    buf[i0] = make_float2(a.x + t.x, a.y + t.y);
-    buf[i1] = make_float2(a.x - t.x, a.y - t.y);
-  }
-  __syncthreads();
-}
-
 // ------------------------------------------------------------------------------------------
-// VAD.common.conv1_1 (257 -> 4, k5, pad 2) + PReLU on the mask logits of each speaker, plus the
-// statistics of GroupNorm(1,4) over the [4,T] plane. One CTA per frame, warp = (speaker, channel).
-__global__ void __launch_bounds__(256) k_vad_conv(VadParams p) {
-  __shared__ float vals[8];
-  const int row = blockIdx.x, b = row / p.T, t = row - b * p.T;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = warp >> 2, j = warp & 3;
-  float acc = 0.f;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const int tt = t + k - 2;
-    if (tt < 0 || tt >= p.T) continue;
-    const float* lr = p.logits + (int64_t)(row + k - 2) * kLogitStride + s * kBins;
-    const float* wr = p.w1t + (k * 4 + j) * kBins;
-    for (int f = lane; f < kBins; f += 32) acc = fmaf(__ldg(wr + f), __ldg(lr + f), acc);
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    const float v = prelu(acc + p.b1[j], p.slope);
-    p.c4[(((int64_t)(b * 2 + s)) * p.T + t) * 4 + j] = v;
-    vals[warp] = v;
-  }
+// VAD.common.conv1_1 (257 -> 4, k5, pad 2) as per-row partial products: every logits row is read
+// once and dotted with the 20 (tap, channel) weight vectors of each speaker;
+//   part[row][s][k*4+j] = sum_f w[j][f][k] * logit[row][s*257 + f]
+// the taps are combined by k_vad_final. One warp per frame, weights staged in shared memory.
+constexpr int kVadRowsPerCta = 16;
+constexpr int kVadWPitch = 264;
+
+__global__ void __launch_bounds__(256) k_vad_partial(const float* __restrict__ logits, int M,
+                                                     const float* __restrict__ w1t, float* __restrict__ part) {
+  __shared__ float w[20][kVadWPitch];
+  for (int i = threadIdx.x; i < 20 * kBins; i += 256) w[i / kBins][i % kBins] = __ldg(w1t + i);
   __syncthreads();
-  if (threadIdx.x < 2) {
-    double sm = 0.0, ssm = 0.0;
-    for (int i = 0; i < 4; ++i) {
-      const double v = vals[threadIdx.x * 4 + i];
-      sm += v;
-      ssm += v * v;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < kVadRowsPerCta; r += 8) {
+    const int row = blockIdx.x * kVadRowsPerCta + r;
+    if (row >= M) break;
+    const float* lr = logits + (int64_t)row * kLogitStride;
+    float a0[20], a1[20];
+#pragma unroll
+    for (int i = 0; i < 20; ++i) a0[i] = a1[i] = 0.f;
+    for (int f = lane; f < kBins; f += 32) {
+      const float x0 = __ldg(lr + f), x1 = __ldg(lr + kBins + f);
+#pragma unroll
+      for (int i = 0; i < 20; ++i) {
+        const float wv = w[i][f];
+        a0[i] = fmaf(wv, x0, a0[i]);
+        a1[i] = fmaf(wv, x1, a1[i]);
+      }
     }
-    atomicAdd(&p.st_v[b * 2 + threadIdx.x].s, sm);
-    atomicAdd(&p.st_v[b * 2 + threadIdx.x].ss, ssm);
+    float o0 = 0.f, o1 = 0.f;  // lane i < 20 keeps speaker 0 / value i, lane i >= 20 ... speaker 1 via o1
+#pragma unroll
+    for (int i = 0; i < 20; ++i) {
+      const float s0 = warp_sum(a0[i]), s1 = warp_sum(a1[i]);
+      if (lane == i) { o0 = s0; o1 = s1; }
+    }
+    if (lane < 20) {
+      part[(int64_t)row * 40 + lane] = o0;
+      part[(int64_t)row * 40 + 20 + lane] = o1;
+    }
   }
 }
 
-// GroupNorm(1,4) -> output_layer_vad (4 -> 1, k3, pad 1) -> sigmoid; then the inference-only
-// threshold (>=) and [1,0,1] neighbour-OR smoothing with edge copy (model.py:449-451).
-// One CTA per (utterance, speaker).
+// Tap combination + PReLU + GroupNorm(1,4) over the [4,T] plane -> output_layer_vad (4 -> 1, k3, pad 1)
+// -> sigmoid; then the inference-only threshold (>=) and [1,0,1] neighbour-OR smoothing with edge copy
+// (model.py:173-179, 449-451). One CTA owns one (utterance, speaker): its statistics need no atomics.
 __global__ void __launch_bounds__(256) k_vad_final(VadParams p) {
-  const int bs = blockIdx.x;
-  const float2 mr = stat_mean_rstd(p.st_v + bs, 1.0 / (4.0 * p.T), 1e-8f);
-  const float* c4 = p.c4 + (int64_t)bs * p.T * 4;
+  __shared__ double red[2][8];
+  __shared__ float2 s_mr;
+  const int bs = blockIdx.x, b = bs >> 1, s = bs & 1;
+  float* c4 = p.c4 + (int64_t)bs * p.T * 4;
   float* prob = p.prob + (int64_t)bs * p.T;
+  double sum = 0.0, sumsq = 0.0;
+  for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+    float c[4] = {p.b1[0], p.b1[1], p.b1[2], p.b1[3]};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int tt = t + k - 2;
+      if (tt < 0 || tt >= p.T) continue;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.part + ((int64_t)b * p.T + tt) * 40 + s * 20 + k * 4));
+      c[0] += v.x; c[1] += v.y; c[2] += v.z; c[3] += v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      c[j] = prelu(c[j], p.slope);
+      sum += c[j];
+      sumsq += (double)c[j] * c[j];
+    }
+    *reinterpret_cast<float4*>(c4 + (int64_t)t * 4) = make_float4(c[0], c[1], c[2], c[3]);
+  }
+  sum = warp_sum(sum);
+  sumsq = warp_sum(sumsq);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sum; red[1][threadIdx.x >> 5] = sumsq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Stat2 st{0.0, 0.0};
+    for (int i = 0; i < 8; ++i) { st.s += red[0][i]; st.ss += red[1][i]; }
+    s_mr = stat_mean_rstd(&st, 1.0 / (4.0 * p.T), 1e-8f);
+  }
+  __syncthreads();
+  const float2 mr = s_mr;
   for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
     float acc = p.b2;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int tt = t + k - 1;
       if (tt < 0 || tt >= p.T) continue;
-      const float4 c = __ldg(reinterpret_cast<const float4*>(c4 + (int64_t)tt * 4));
+      const float4 c = *reinterpret_cast<const float4*>(c4 + (int64_t)tt * 4);  // written by this CTA above
       acc += p.w2[0 * 3 + k] * (((c.x - mr.x) * mr.y) * p.g[0] + p.be[0]);
       acc += p.w2[1 * 3 + k] * (((c.y - mr.x) * mr.y) * p.g[1] + p.be[1]);
       acc += p.w2[2 * 3 + k] * (((c.z - mr.x) * mr.y) * p.g[2] + p.be[2]);
@@ -100,63 +118,82 @@ __global__ void __launch_bounds__(256) k_vad_final(VadParams p) {
 }
 
 void launch_vad(const VadParams& p, cudaStream_t st) {
-  k_vad_conv<<<p.M, 256, 0, st>>>(p);
+  k_vad_partial<<<(p.M + kVadRowsPerCta - 1) / kVadRowsPerCta, 256, 0, st>>>(p.logits, p.M, p.w1t, p.part);
   k_vad_final<<<p.B * 2, 256, 0, st>>>(p);
   g_launch_count += 2;
 }
 
 // ------------------------------------------------------------------------------------------
-// Mask application + inverse STFT + overlap-add, one CTA per 256-sample output block of one
-// (utterance, speaker): out[256 j + n] = (w[256+n] fr_j[256+n] + w[n] fr_{j+1}[n]) / env.
-// fr_t = irfft_512(S[t] * sigmoid(logit[s,:,t]) * gate[s,t]) (model.py:429-437,452-455,460).
+// Mask application + inverse STFT + overlap-add. One CTA = 8 consecutive 256-sample output blocks of
+// one utterance, BOTH speakers: the two Hermitian spectra share one complex FFT (Z = E0 + i E1 ->
+// z = e0 + i e1), and every frame is transformed once per CTA.
+//   E_s[f] = S[t,f] * sigmoid(logit[s,f,t]) * gate[s,t]                    (model.py:429-437,452-455)
+//   out[256 j + n] = (w[256+n] fr_j[256+n] + w[n] fr_{j+1}[n]) / (w[256+n]^2 + w[n]^2)        (:460)
+constexpr int kIstftBlocks = 8;
+
 __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S, const float* __restrict__ logits,
                                                     const float* __restrict__ gate, const float* __restrict__ window,
                                                     const float2* __restrict__ twiddle, int64_t L, int T,
                                                     float* __restrict__ out) {
   __shared__ float2 buf[kNfft];
   __shared__ float2 tw[256];
-  const int j = blockIdx.x, s = blockIdx.y, b = blockIdx.z;
-  const int n = threadIdx.x;
-  if ((int64_t)j * kHop >= L) return;
+  const int n = threadIdx.x, b = blockIdx.y;
+  const int j0 = blockIdx.x * kIstftBlocks;
   tw[n] = __ldg(twiddle + n);
-  float acc = 0.f, env = 0.f;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int t = j + h;
-    if (t >= T) break;
+  const float w_lo = __ldg(window + n), w_hi = __ldg(window + kHop + n);
+  float* out0 = out + ((int64_t)b * 2) * L;
+  float* out1 = out0 + L;
+  float2 prev = make_float2(0.f, 0.f);  // second half (x w) of the previous frame: (speaker 0, speaker 1)
+  const int t_last = min(j0 + kIstftBlocks, T - 1);
+  for (int t = j0; t <= t_last; ++t) {
     const int64_t row = (int64_t)b * T + t;
-    const float g = gate != nullptr ? __ldg(gate + ((int64_t)b * 2 + s) * T + t) : 1.f;
-    __syncthreads();  // previous iteration's reads of buf are done
-    // Hermitian-extended spectrum in bit-reversed order; thread n fills bins n and 512-n (n>=1), 0 and 256.
-    {
-      const int f = n;  // 0..255
-      float2 e = make_float2(0.f, 0.f);
-      if (f >= 1) {
-        const float2 sv = __ldg(S + row * kBins + f);
-        const float m = sigmoidf_acc(__ldg(logits + row * kLogitStride + s * kBins + f)) * g;
-        e = make_float2(sv.x * m, sv.y * m);
-      }
-      buf[__brev((unsigned)f) >> 23] = e;
-      if (f >= 1) buf[__brev((unsigned)(kNfft - f)) >> 23] = make_float2(e.x, -e.y);
-      if (f == 0) {
-        const float2 sv = __ldg(S + row * kBins + 256);
-        const float m = sigmoidf_acc(__ldg(logits + row * kLogitStride + s * kBins + 256)) * g;
-        buf[__brev(256u) >> 23] = make_float2(sv.x * m, 0.f);  // imaginary part of Nyquist is ignored by irfft
+    float g0 = 1.f, g1 = 1.f;
+    if (gate != nullptr) {
+      g0 = __ldg(gate + ((int64_t)b * 2) * T + t);
+      g1 = __ldg(gate + ((int64_t)b * 2 + 1) * T + t);
+    }
+    const float* lr = logits + row * kLogitStride;
+    __syncthreads();  // the previous frame's reads of buf are done
+    if (n >= 1) {
+      const float2 sv = __ldg(S + row * kBins + n);
+      const float m0 = sigmoidf_acc(__ldg(lr + n)) * g0, m1 = sigmoidf_acc(__ldg(lr + kBins + n)) * g1;
+      const float a0 = sv.x * m0, b0 = sv.y * m0, a1 = sv.x * m1, b1 = sv.y * m1;
+      buf[__brev((unsigned)n) >> 23] = make_float2(a0 - b1, b0 + a1);                 // E0[f] + i E1[f]
+      buf[__brev((unsigned)(kNfft - n)) >> 23] = make_float2(a0 + b1, a1 - b0);       // conj(E0[f]) + i conj(E1[f])
+    } else {
+      const float2 sv = __ldg(S + row * kBins + 256);
+      const float m0 = sigmoidf_acc(__ldg(lr + 256)) * g0, m1 = sigmoidf_acc(__ldg(lr + kBins + 256)) * g1;
+      buf[0] = make_float2(0.f, 0.f);                                                  // DC bin is zero
+      buf[__brev(256u) >> 23] = make_float2(sv.x * m0, sv.x * m1);  // irfft ignores the imaginary part of Nyquist
+    }
+    fft512_smem<true>(buf, tw);
+    const float sc = 1.f / (float)kNfft;
+    const float2 lo = buf[n], hi = buf[kHop + n];
+    const float2 first = make_float2(lo.x * sc * w_lo, lo.y * sc * w_lo);
+    if (t > j0) {
+      const int64_t o = (int64_t)(t - 1) * kHop + n;
+      if (o < L) {
+        const float env = w_hi * w_hi + w_lo * w_lo;
+        out0[o] = (prev.x + first.x) / env;
+        out1[o] = (prev.y + first.y) / env;
       }
     }
-    fft512_smem_be<true>(buf, tw);
-    const int idx = (h == 0) ? (kHop + n) : n;
-    const float wv = __ldg(window + idx);
-    acc += buf[idx].x * (1.f / (float)kNfft) * wv;
-    env += wv * wv;
+    prev = make_float2(hi.x * sc * w_hi, hi.y * sc * w_hi);
   }
-  const int64_t o = (int64_t)j * kHop + n;
-  if (o < L) out[((int64_t)b * 2 + s) * L + o] = acc / env;
+  // the last frame of the utterance has no successor: its second half is the ragged tail
+  if (t_last == T - 1 && T - 1 < j0 + kIstftBlocks) {
+    const int64_t o = (int64_t)(T - 1) * kHop + n;
+    if (o < L) {
+      const float env = w_hi * w_hi;
+      out0[o] = prev.x / env;
+      out1[o] = prev.y / env;
+    }
+  }
 }
 
 void launch_mask_istft(const float2* S, const float* logits, const float* gate, const float* window,
                        const float2* twiddle, int B, int64_t L, int T, float* out, cudaStream_t st) {
-  dim3 grid(T, 2, B);
+  dim3 grid((T + kIstftBlocks - 1) / kIstftBlocks, B);
   k_mask_istft<<<grid, 256, 0, st>>>(S, logits, gate, window, twiddle, L, T, out);
   ++g_launch_count;
 }

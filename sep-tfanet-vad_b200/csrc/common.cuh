@@ -57,4 +57,58 @@ __device__ __forceinline__ void block_stat_atomic(float s, float ss, Stat2* dst,
   __syncthreads();
 }
 
+// Running GroupNorm statistics of one thread over the utterance segments of its tile. Slots 0 and 1
+// (the tile's first two utterances) live in registers; further segments (only when T is smaller
+// than the tile) fall back to shared float atomics. Shared float atomics are CAS loops (ATOMS.CAST.SPIN)
+// and collapse under same-address contention, so they stay off the common path: flush_warp() reduces
+// over the warp with shuffles and issues one atomic per warp and value.
+struct SegStat2 {
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+  template <int N>
+  __device__ __forceinline__ void add(int sg, const float (&v)[N], float* sm) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { s += v[i]; q = fmaf(v[i], v[i], q); }
+    if (sg == 0) { s0 += s; q0 += q; }
+    else if (sg == 1) { s1 += s; q1 += q; }
+    else { atomicAdd(sm + 2 * sg, s); atomicAdd(sm + 2 * sg + 1, q); }
+  }
+  // Must be called by all 32 lanes of the warp: shuffle-reduce, then lane 0 stores the warp's partials
+  // into its own slot (slots[warp_slot*4 ..]); seg_stats_commit() adds the slots in a fixed order.
+  __device__ __forceinline__ void flush_warp(float* slots, int warp_slot) {
+    s0 = warp_sum(s0); q0 = warp_sum(q0);
+    s1 = warp_sum(s1); q1 = warp_sum(q1);
+    if ((threadIdx.x & 31) == 0) {
+      slots[warp_slot * 4 + 0] = s0; slots[warp_slot * 4 + 1] = q0;
+      slots[warp_slot * 4 + 2] = s1; slots[warp_slot * 4 + 3] = q1;
+    }
+  }
+};
+
+// After a block barrier: thread i < nseg adds the tile's statistics of segment i to the utterance's
+// double accumulators. Slots are summed in warp order, so a tile's contribution is bit-reproducible;
+// only the order of the (double) global atomics varies between runs.
+__device__ __forceinline__ void seg_stats_commit(const float* slots, int nslots, const float* seg_acc, int nseg,
+                                                 Stat2* dst) {
+  for (int i = threadIdx.x; i < nseg; i += blockDim.x) {
+    float s = seg_acc[2 * i], q = seg_acc[2 * i + 1];
+    if (i < 2)
+      for (int w = 0; w < nslots; ++w) { s += slots[w * 4 + 2 * i]; q += slots[w * 4 + 2 * i + 1]; }
+    atomicAdd(&dst[i].s, (double)s);
+    atomicAdd(&dst[i].ss, (double)q);
+  }
+}
+
+// Row -> utterance segment of a tile without an integer division on the common path.
+struct SegMap {
+  int e1, e2, T, b_first;  // e1 / e2: first global row of the tile's 2nd / 3rd utterance
+  __device__ __forceinline__ SegMap(int r0, int T_) : T(T_) {
+    b_first = r0 / T_;
+    e1 = (b_first + 1) * T_;
+    e2 = e1 + T_;
+  }
+  __device__ __forceinline__ int seg(int row) const { return row < e1 ? 0 : (row < e2 ? 1 : row / T - b_first); }
+  __device__ __forceinline__ int frame(int row, int sg) const { return row - (b_first + sg) * T; }
+};
+
 }  // namespace septfa

@@ -1,8 +1,9 @@
-// Front-end kernels: STFT (frame, window, 512-point shared-memory radix-2 FFT), power-dB,
-// activity gate and the statistics of the TCN input norm.
+// Front-end kernel: STFT (frame, window, 512-point shared-memory FFT), power-dB, activity gate and
+// the statistics of the TCN input norm, fused: the dB spectrogram never goes to HBM.
 // Reference: model/model.py:408-419 (Spectrogram/InputSpec -> torch.stft, AmplitudeToDB,
 // activity_input Conv2d 3x3 + PReLU) and :333 (TCN.LN statistics).
 #include "kernels.h"
+#include "fft512.cuh"
 
 namespace septfa {
 
@@ -16,108 +17,113 @@ void make_twiddles(float2* h) {
   }
 }
 
-// In-place 512-point complex FFT over shared memory, decimation in time; the caller has stored
-// the input in bit-reversed order. 256 threads, one butterfly per thread per stage.
-// INVERSE uses conjugated twiddles (unnormalised inverse).
-template <bool INVERSE>
-__device__ __forceinline__ void fft512_smem(float2* buf, const float2* tw) {
-  const int k = threadIdx.x;
-#pragma unroll
-  for (int s = 0; s < 9; ++s) {
-    const int half = 1 << s;
-    const int pos = k & (half - 1);
-    const int i0 = ((k >> s) << (s + 1)) + pos;
-    const int i1 = i0 + half;
-    __syncthreads();  // also orders the caller's writes of buf / tw before the first stage
-    float2 w = tw[pos << (8 - s)];
-    if (INVERSE) w.y = -w.y;
-    const float2 a = buf[i0], b = buf[i1];
-    const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
-    buf[i0] = make_float2(a.x + t.x, a.y + t.y);
-    buf[i1] = make_float2(a.x - t.x, a.y - t.y);
-  }
-  __syncthreads();
-}
+constexpr int kFrontFrames = 14;              // frames produced per CTA
+constexpr int kFrontRows = kFrontFrames + 2;  // + one halo frame each side for the 3x3 gate
+constexpr int kPPitch = kBins + 3;            // dB row: [0] = bin -1 (zero pad), [1..257] = bins, [258] = bin 257 (zero pad)
 
-// One CTA per STFT frame. torch.stft(center=True, pad_mode='reflect', onesided), no normalisation,
-// DC bin zeroed (model.py:24,410). S[row, f] complex, P[row, f] = 10 log10(max(|S|^2, 1e-10)).
-__global__ void __launch_bounds__(256) k_stft(const float* __restrict__ x, int64_t L, int T,
-                                              const float* __restrict__ window,
-                                              const float2* __restrict__ twiddle,
-                                              float2* __restrict__ S, float* __restrict__ P) {
+struct GateK { float k[9]; float bias, slope; int enabled; };
+
+// One CTA = 14 consecutive frames of one utterance. Two real frames share one complex FFT
+// (z = a + i b; A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i).
+// torch.stft(center=True, pad_mode='reflect', onesided), no normalisation, DC bin zeroed (model.py:24,410);
+// P = 10 log10(max(|S|^2, 1e-10)); spectrum *= PReLU(Conv2d 3x3 (zero pad 1) over the (257, T) plane),
+// rows 1..256 feed the TCN (model.py:411-421).
+__global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, int64_t L, int T,
+                                                  const float* __restrict__ window, const float2* __restrict__ twiddle,
+                                                  GateK gk, float2* __restrict__ S, float* __restrict__ z0,
+                                                  float* __restrict__ dc_gated, Stat2* __restrict__ st0) {
   __shared__ float2 buf[kNfft];
   __shared__ float2 tw[256];
-  const int row = blockIdx.x;
-  const int b = row / T, t = row - b * T;
-  const float* xb = x + (int64_t)b * L;
-  tw[threadIdx.x] = __ldg(twiddle + threadIdx.x);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int n = threadIdx.x + h * 256;
-    int64_t i = (int64_t)t * kHop + n - kNfft / 2;
-    if (i < 0) i = -i;
-    if (i >= L) i = 2 * (L - 1) - i;
-    const float v = __ldg(xb + i) * __ldg(window + n);
-    buf[__brev((unsigned)n) >> 23] = make_float2(v, 0.f);
-  }
-  fft512_smem<false>(buf, tw);
-  float2* Sr = S + (int64_t)row * kBins;
-  float* Pr = P + (int64_t)row * kBins;
-  for (int f = threadIdx.x; f < kBins; f += 256) {
-    float2 v = buf[f];
-    if (f == 0) v = make_float2(0.f, 0.f);
-    Sr[f] = v;
-    Pr[f] = 10.f * log10f(fmaxf(v.x * v.x + v.y * v.y, 1e-10f));
-  }
-}
-
-// One CTA per frame: spectrum *= PReLU(Conv2d 3x3 (zero pad 1) over the (257, T) plane), rows
-// 1..256 go to the TCN (model.py:414-421); accumulates the TCN.LN statistics.
-__global__ void __launch_bounds__(256) k_activity_gate(const float* __restrict__ P, int T, int enabled,
-                                                       float k00, float k01, float k02, float k10, float k11,
-                                                       float k12, float k20, float k21, float k22, float bias,
-                                                       float slope, float* __restrict__ z0,
-                                                       float* __restrict__ dc_gated, Stat2* __restrict__ st0) {
-  __shared__ float rows[3][kBins + 2];
+  __shared__ float win[kNfft];
+  __shared__ float P[kFrontRows][kPPitch];
   __shared__ float red[64];
-  const int row = blockIdx.x;
-  const int b = row / T, t = row - b * T;
-  for (int i = threadIdx.x; i < 3 * (kBins + 2); i += 256) {
-    const int j = i / (kBins + 2), f = i - j * (kBins + 2) - 1;  // f in [-1, 257]
-    const int tt = t + j - 1;
-    float v = 0.f;
-    if (tt >= 0 && tt < T && f >= 0 && f < kBins) v = __ldg(P + (int64_t)(row + j - 1) * kBins + f);
-    rows[j][f + 1] = v;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y, t0 = blockIdx.x * kFrontFrames;
+  const float* xb = x + (int64_t)b * L;
+  tw[tid] = __ldg(twiddle + tid);
+  win[tid] = __ldg(window + tid);
+  win[tid + 256] = __ldg(window + tid + 256);
+  for (int i = tid; i < kFrontRows * kPPitch; i += 256) (&P[0][0])[i] = 0.f;  // zero padding of the gate conv
+  __syncthreads();
+
+  for (int pair = 0; pair < kFrontRows / 2; ++pair) {
+    const int la = 2 * pair;  // local row of frame a (rows 0 and 15 are halo rows)
+    const int ta = t0 - 1 + la, tb = ta + 1;
+    const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
+    if (!va && !vb) continue;  // uniform: both frames outside the utterance -> rows stay zero
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = tid + h * 256;
+      float a = 0.f, c = 0.f;
+      if (va) {
+        int64_t i = (int64_t)ta * kHop + n - kNfft / 2;
+        if (i < 0) i = -i;
+        if (i >= L) i = 2 * (L - 1) - i;
+        a = __ldg(xb + i) * win[n];
+      }
+      if (vb) {
+        int64_t i = (int64_t)tb * kHop + n - kNfft / 2;
+        if (i < 0) i = -i;
+        if (i >= L) i = 2 * (L - 1) - i;
+        c = __ldg(xb + i) * win[n];
+      }
+      buf[__brev((unsigned)n) >> 23] = make_float2(a, c);
+    }
+    fft512_smem<false>(buf, tw);
+    const bool wa = va && la >= 1 && la <= kFrontFrames;  // frames this CTA owns (not halo)
+    const bool wb = vb && (la + 1) <= kFrontFrames;
+    for (int f = tid; f < kBins; f += 256) {
+      float2 A = make_float2(0.f, 0.f), Bc = A;
+      if (f > 0) {
+        const float2 zk = buf[f], zn = buf[(kNfft - f) & (kNfft - 1)];
+        A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        Bc = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+      }
+      if (va) P[la][f + 1] = 10.f * log10f(fmaxf(A.x * A.x + A.y * A.y, 1e-10f));
+      if (vb) P[la + 1][f + 1] = 10.f * log10f(fmaxf(Bc.x * Bc.x + Bc.y * Bc.y, 1e-10f));
+      if (wa) S[((int64_t)b * T + ta) * kBins + f] = A;
+      if (wb) S[((int64_t)b * T + tb) * kBins + f] = Bc;
+    }
+    __syncthreads();  // buf is rewritten by the next pair
   }
   __syncthreads();
-  // kernel index [i][j]: i over frequency, j over time (input plane is [257, T])
-  auto gate = [&](int f) {
-    const float c = rows[1][f + 1];
-    if (!enabled) return c;
-    float acc = k00 * rows[0][f] + k01 * rows[1][f] + k02 * rows[2][f];
-    acc += k10 * rows[0][f + 1] + k11 * rows[1][f + 1] + k12 * rows[2][f + 1];
-    acc += k20 * rows[0][f + 2] + k21 * rows[1][f + 2] + k22 * rows[2][f + 2];
-    acc += bias;
-    return c * prelu(acc, slope);
-  };
-  const float z = gate(threadIdx.x + 1);
-  z0[(int64_t)row * kC + threadIdx.x] = z;
-  if (threadIdx.x == 0) dc_gated[row] = gate(0);
-  block_stat_atomic(z, z * z, st0 + b, red);
+
+  // activity gate; kernel index [i][j]: i over frequency, j over time (the input plane is [257, T])
+  float s = 0.f, ss = 0.f;
+  for (int lf = 1; lf <= kFrontFrames; ++lf) {
+    const int t = t0 + lf - 1;
+    if (t >= T) break;
+    const int64_t row = (int64_t)b * T + t;
+    auto gate = [&](int f) {
+      const float c = P[lf][f + 1];
+      if (!gk.enabled) return c;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc += gk.k[i * 3 + j] * P[lf - 1 + j][f + i];
+      acc += gk.bias;
+      return c * prelu(acc, gk.slope);
+    };
+    const float z = gate(tid + 1);
+    z0[row * kC + tid] = z;
+    if (tid == 0) dc_gated[row] = gate(0);
+    s += z;
+    ss += z * z;
+  }
+  block_stat_atomic(s, ss, st0 + b, red);
 }
 
-void launch_stft(const float* x, int B, int64_t L, int T, const float* window, const float2* twiddle, float2* S, float* P,
-                 cudaStream_t st) {
-  k_stft<<<B * T, 256, 0, st>>>(x, L, T, window, twiddle, S, P);
-  ++g_launch_count;
-}
-
-void launch_activity_gate(const float* P, int B, int T, int enabled, const float* k, float bias, float slope,
-                          float* z0, float* dc_gated, Stat2* st0, cudaStream_t st) {
-  // Conv2d weight [1,1,3,3]: k[i*3+j], i = frequency tap, j = time tap; the kernel's kIJ multiplies
-  // rows[J][f+I] (rows[J] holds time tap J), i.e. P[f+I-1][t+J-1].
-  k_activity_gate<<<B * T, 256, 0, st>>>(P, T, enabled, k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], k[8], bias,
-                                         slope, z0, dc_gated, st0);
+void launch_frontend(const float* x, int B, int64_t L, int T, const float* window, const float2* twiddle, int enabled,
+                     const float* k3x3, float bias, float slope, float2* S, float* z0, float* dc_gated, Stat2* st0,
+                     cudaStream_t st) {
+  GateK gk;
+  for (int i = 0; i < 9; ++i) gk.k[i] = k3x3[i];  // Conv2d weight [1,1,3,3]: k[i*3+j], i = frequency tap, j = time tap
+  gk.bias = bias;
+  gk.slope = slope;
+  gk.enabled = enabled;
+  dim3 grid((T + kFrontFrames - 1) / kFrontFrames, B);
+  k_frontend<<<grid, 256, 0, st>>>(x, L, T, window, twiddle, gk, S, z0, dc_gated, st0);
   ++g_launch_count;
 }
 

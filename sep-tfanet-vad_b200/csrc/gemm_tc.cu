@@ -11,6 +11,7 @@
 //   warp 9    : allocates TMEM, issues tcgen05.mma (one elected thread), tcgen05.commit -> mbarriers
 // Reference semantics: model/model.py:130-149 (DepthConv1d), :322-325,357 (TCN.output).
 #include <cstdio>
+#include <cstdlib>
 #include "kernels.h"
 
 namespace septfa {
@@ -22,6 +23,7 @@ constexpr int kAChunkBytes = kTileM * 128;  // one K-chunk (64 halves = 128 B) o
 constexpr int kStages = 2;
 constexpr int kThreads = 320;
 constexpr int kAuxBytes = 4096;
+constexpr int kDconvWBytes = 512 * 16 + 512 * 4;  // MODE 1: folded depthwise taps staged in shared memory
 constexpr int kStgPitch = 36;               // floats per staged row (32 + 4 pad, 16 B aligned)
 
 struct TcParams {
@@ -32,12 +34,13 @@ struct TcParams {
   // MODE 2 prologue
   float slope_o; const Stat2* st_o; const float* g_o; const float* b_o;
   // MODE 1 prologue
-  const Stat2* st_p; const float* g1; const float* be1; const float4* w2b; float slope2; int dil; Stat2* st_q;
+  const Stat2* st_p; const float* g1; const float* be1; const float4* w2b; const float4* w2f; const float* c2f;
+  float slope2; int dil; Stat2* st_q;
   // epilogue
   const float* bias; float slope;
   float* out; int out_stride;
   Stat2* st_out;
-  float* rowsum; float* colsum;
+  float* rowsum; double* colsum;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -156,23 +159,6 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int c8) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
 }
 
-struct LaneStat {  // per-lane running (sum, sumsq) with utterance-segment tracking
-  float s = 0.f, ss = 0.f;
-  int seg = -1;
-  __device__ __forceinline__ void add(int sg, float v, float* sm) {
-    if (sg != seg) { flush(sm); seg = sg; }
-    s += v;
-    ss += v * v;
-  }
-  __device__ __forceinline__ void flush(float* sm) {
-    if (seg >= 0 && (s != 0.f || ss != 0.f)) {
-      atomicAdd(sm + 2 * seg, s);
-      atomicAdd(sm + 2 * seg + 1, ss);
-    }
-    s = ss = 0.f;
-  }
-};
-
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   constexpr int NT = (MODE == 2) ? 192 : 256;
@@ -183,7 +169,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   constexpr uint32_t IDESC = make_idesc_f16(kTileM, NT);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for the 128B swizzle; plain pointer arithmetic keeps the shared address space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE);
   uint64_t* full_a = bars;          // [kStages] producers -> MMA
   uint64_t* full_w = bars + 2;      // [kStages] bulk copy -> MMA
@@ -194,11 +181,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   float2* tab_b = tab_a + kMaxSegs;
   float* seg_acc = reinterpret_cast<float*>(tab_b + kMaxSegs);
   float* rs_x = seg_acc + 2 * kMaxSegs;  // [128] row-sum exchange between the two column halves
+  float* slots = rs_x + kTileM;          // [8 warps][4] per-warp statistics partials
+  float4* w2f_s = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + kAuxBytes);  // MODE 1: [512] folded taps
+  float* c2f_s = reinterpret_cast<float*>(w2f_s + kH);                                       // MODE 1: [512]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * kTileM;
   const int nrows = min(kTileM, p.M - r0);
-  const int b_first = r0 / p.T;
+  const SegMap smap(r0, p.T);
+  const int b_first = smap.b_first;
   const int nseg = (r0 + nrows - 1) / p.T - b_first + 1;
   const __half* w_img = p.w_img + (size_t)blockIdx.y * NCH * (WCH / 2);
 
@@ -224,6 +215,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
       }
     }
     for (int i = threadIdx.x; i < 2 * nseg; i += kThreads) seg_acc[i] = 0.f;
+    if (MODE == 1) {
+      // staged as [chunk j][output o][lane chunk c8] so that the 8 lane groups of a warp read consecutive words
+      for (int i = threadIdx.x; i < kH; i += kThreads) {
+        const int jj = i >> 6, cc = (i >> 3) & 7, oo = i & 7, d = (jj * 8 + oo) * 8 + cc;
+        w2f_s[d] = __ldg(p.w2f + i);
+        c2f_s[d] = __ldg(p.c2f + i);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -262,8 +261,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
     __syncwarp();
   } else {
     // ------------------------------------------------------------ A-operand producers (warps 0-7)
+    // lane -> (row group rg = lane/8, 16-byte chunk c8 = lane%8); each warp covers 4 rows per step.
     const int c8 = lane & 7, rg = lane >> 3;
-    LaneStat qstat;
+    SegStat2 qstat;
     for (int j = 0; j < NCH; ++j) {
       const int s = j % kStages, u = j / kStages;
       if (u > 0) mbar_wait(empty + s, (u - 1) & 1, 400 + j);
@@ -272,11 +272,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
         const int kc = j * 64 + c8 * 8;
         const bool has_norm = p.norm.gamma != nullptr;
         float ga[8], be[8], go[8], bo[8];
-        if (has_norm) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { ga[i] = __ldg(p.norm.gamma + kc + i); be[i] = __ldg(p.norm.beta + kc + i); }
-        }
         if (MODE == 2) {
+          if (has_norm) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ga[i] = __ldg(p.norm.gamma + kc + i); be[i] = __ldg(p.norm.beta + kc + i); }
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) { go[i] = __ldg(p.g_o + kc + i); bo[i] = __ldg(p.b_o + kc + i); }
         }
@@ -297,13 +297,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
           const int rl = it * 32 + warp * 4 + rg;
           float y[8] = {x0[it].x, x0[it].y, x0[it].z, x0[it].w, x1[it].x, x1[it].y, x1[it].z, x1[it].w};
           if (rl < nrows) {
-            const int sg = (r0 + rl) / p.T - b_first;
+            const int sg = smap.seg(r0 + rl);
             const float2 mr = tab_a[sg];
-            if (has_norm) {
+            if (MODE == 0) {
+              // gamma / beta of the stream norm live in the weight image and the bias: A = (x - mean) * rstd
+              const float nb = -mr.x * mr.y;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) y[i] = ((y[i] - mr.x) * mr.y) * ga[i] + be[i];
-            }
-            if (MODE == 2) {
+              for (int i = 0; i < 8; ++i) y[i] = fmaf(y[i], mr.y, nb);
+            } else {
+              if (has_norm) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = ((y[i] - mr.x) * mr.y) * ga[i] + be[i];
+              }
               const float2 mo = tab_b[sg];
 #pragma unroll
               for (int i = 0; i < 8; ++i) y[i] = ((prelu(y[i], p.slope_o) - mo.x) * mo.y) * go[i] + bo[i];
@@ -314,64 +319,81 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
           *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
         }
       } else {
-        // q channels 64j + 8*c8 .. +7  <-  in-channels g0 .. g0+3 (out-channel o reads in-channel o/2)
+        // q channels 64j + 8*c8 .. +7  <-  in-channels g0 .. g0+3 (out-channel o reads in-channel o/2).
+        // GroupNorm reg1 is folded into the taps (w2f = w * gamma, c2f = b2 + beta * sum(w)):
+        //   q = PReLU(c2f + rstd * (sum_k w2f[k] p[t+(k-1)d] - mean * sum_k w2f[k]))      (all taps inside the utterance)
         const int g0 = j * 32 + c8 * 4;
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.g1 + g0));
-        const float4 be = __ldg(reinterpret_cast<const float4*>(p.be1 + g0));
-        float4 wb[8];
+        const float4* wf = w2f_s + j * 64 + c8;   // folded taps of this lane's 8 output channels: wf[o * 8]
+        const float* cf = c2f_s + j * 64 + c8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) wb[i] = __ldg(p.w2b + 2 * g0 + i);
-        float4 xm[4], xc[4], xp[4];
-        int okm[4], okp[4];
+        for (int half = 0; half < 2; ++half) {   // two row steps at a time: 6 x 16 B loads in flight per thread
+          float4 xm[2], xc[2], xp[2];
+          int flg[2];                              // segment | tap (t-d) valid << 8 | tap (t+d) valid << 9
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rl = it * 32 + warp * 4 + rg;
-          xm[it] = xc[it] = xp[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          okm[it] = okp[it] = 0;
-          if (rl < nrows) {
-            const int row = r0 + rl;
-            const int t = row - (row / p.T) * p.T;
-            const float* src = p.in + (int64_t)row * kC + g0;
-            xc[it] = __ldg(reinterpret_cast<const float4*>(src));
-            if (t - p.dil >= 0) { okm[it] = 1; xm[it] = __ldg(reinterpret_cast<const float4*>(src - (int64_t)p.dil * kC)); }
-            if (t + p.dil < p.T) { okp[it] = 1; xp[it] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)p.dil * kC)); }
-          }
-        }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rl = it * 32 + warp * 4 + rg;
-          float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (rl < nrows) {
-            const int sg = (r0 + rl) / p.T - b_first;
-            const float2 mr = tab_a[sg];
-            const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
-            const float vm[4] = {xm[it].x, xm[it].y, xm[it].z, xm[it].w};
-            const float vc[4] = {xc[it].x, xc[it].y, xc[it].z, xc[it].w};
-            const float vp[4] = {xp[it].x, xp[it].y, xp[it].z, xp[it].w};
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              // GroupNorm reg1 on load; taps outside the utterance are zero padding of the *normalised* signal
-              const float hm = okm[it] ? ((vm[g] - mr.x) * mr.y) * gam[g] + bet[g] : 0.f;
-              const float hc = ((vc[g] - mr.x) * mr.y) * gam[g] + bet[g];
-              const float hp = okp[it] ? ((vp[g] - mr.x) * mr.y) * gam[g] + bet[g] : 0.f;
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float4 w = wb[2 * g + e];
-                const float v = prelu(w.w + w.x * hm + w.y * hc + w.z * hp, p.slope2);
-                q[2 * g + e] = v;
-                qstat.add(sg, v, seg_acc);
-              }
+          for (int i2 = 0; i2 < 2; ++i2) {
+            const int rl = (half * 2 + i2) * 32 + warp * 4 + rg;
+            xm[i2] = xc[i2] = xp[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            flg[i2] = 0;
+            if (rl < nrows) {
+              const int row = r0 + rl;
+              const int sg = smap.seg(row);
+              const int t = smap.frame(row, sg);
+              const float* src = p.in + (int64_t)row * kC + g0;
+              xc[i2] = __ldg(reinterpret_cast<const float4*>(src));
+              int f = sg;
+              if (t - p.dil >= 0) { f |= 256; xm[i2] = __ldg(reinterpret_cast<const float4*>(src - (int64_t)p.dil * kC)); }
+              if (t + p.dil < p.T) { f |= 512; xp[i2] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)p.dil * kC)); }
+              flg[i2] = f;
             }
           }
-          const uint4 pk = make_uint4(pack_half2(q[0], q[1]), pack_half2(q[2], q[3]), pack_half2(q[4], q[5]),
-                                      pack_half2(q[6], q[7]));
-          *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
+#pragma unroll
+          for (int i2 = 0; i2 < 2; ++i2) {
+            const int rl = (half * 2 + i2) * 32 + warp * 4 + rg;
+            float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (rl < nrows) {
+              const int sg = flg[i2] & 255;
+              const bool okm = flg[i2] & 256, okp = flg[i2] & 512;
+              const float2 mr = tab_a[sg];
+              const float vm[4] = {xm[i2].x, xm[i2].y, xm[i2].z, xm[i2].w};
+              const float vc[4] = {xc[i2].x, xc[i2].y, xc[i2].z, xc[i2].w};
+              const float vp[4] = {xp[i2].x, xp[i2].y, xp[i2].z, xp[i2].w};
+              if (okm && okp) {
+                const float nmu = -mr.x;
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                  const float4 w = wf[o * 8];
+                  const float conv = fmaf(w.z, vp[o >> 1], fmaf(w.y, vc[o >> 1], w.x * vm[o >> 1]));
+                  q[o] = prelu(fmaf(mr.y, fmaf(nmu, w.w, conv), cf[o * 8]), p.slope2);
+                }
+              } else {
+                // frames within `dil` of an utterance edge: taps outside are zero padding of the *normalised* signal
+                const float4 ga = __ldg(reinterpret_cast<const float4*>(p.g1 + g0));
+                const float4 be = __ldg(reinterpret_cast<const float4*>(p.be1 + g0));
+                const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const float hm = okm ? ((vm[g] - mr.x) * mr.y) * gam[g] + bet[g] : 0.f;
+                  const float hc = ((vc[g] - mr.x) * mr.y) * gam[g] + bet[g];
+                  const float hp = okp ? ((vp[g] - mr.x) * mr.y) * gam[g] + bet[g] : 0.f;
+#pragma unroll
+                  for (int e = 0; e < 2; ++e) {
+                    const float4 w = __ldg(p.w2b + 2 * (g0 + g) + e);
+                    q[2 * g + e] = prelu(w.w + w.x * hm + w.y * hc + w.z * hp, p.slope2);
+                  }
+                }
+              }
+              qstat.add(sg, q, seg_acc);
+            }
+            const uint4 pk = make_uint4(pack_half2(q[0], q[1]), pack_half2(q[2], q[3]), pack_half2(q[4], q[5]),
+                                        pack_half2(q[6], q[7]));
+            *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
+          }
         }
       }
       fence_proxy_async();
       mbar_arrive(full_a + s);
     }
-    if (MODE == 1) qstat.flush(seg_acc);
+    if (MODE == 1) qstat.flush_warp(slots, warp);
 
     // ------------------------------------------------------------ epilogue (warps 0-7)
     // warp w reads TMEM lanes 32*(w%4).. (rows) and columns (w/4)*NT/2 .. in chunks of 32.
@@ -381,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
     float* stg = reinterpret_cast<float*>(smem) + warp * (32 * kStgPitch);  // aliases the (now idle) stage buffers
     const int my_rl = lq * 32 + lane;       // the row this thread owns in TMEM
     float rowacc = 0.f;
-    LaneStat ostat;
+    SegStat2 ostat;
     constexpr int NCC = NT / 64;            // 32-column chunks per column half
     for (int cc = 0; cc < NCC; ++cc) {
       const int col0 = ch * (NT / 2) + cc * 32;
@@ -401,8 +423,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
       const int gcol = (MODE == 2 ? (int)blockIdx.y * NT : 0) + col0 + c4;
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (MODE != 1) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
-      float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-      int cseg = -1;
+      float4 cs0 = make_float4(0.f, 0.f, 0.f, 0.f), cs1 = cs0;   // column sums of the tile's 1st / 2nd utterance
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int i = it * 4 + (lane >> 3);
@@ -410,51 +431,48 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
         if (rl < nrows) {
           float4 o = *reinterpret_cast<const float4*>(stg + i * kStgPitch + c4);
           const int row = r0 + rl;
-          const int sg = row / p.T - b_first;
+          const int sg = smap.seg(row);
           if (MODE == 0) {
             o.x = prelu(o.x + bias4.x, p.slope); o.y = prelu(o.y + bias4.y, p.slope);
             o.z = prelu(o.z + bias4.z, p.slope); o.w = prelu(o.w + bias4.w, p.slope);
-            ostat.add(sg, o.x, seg_acc); ostat.add(sg, o.y, seg_acc);
-            ostat.add(sg, o.z, seg_acc); ostat.add(sg, o.w, seg_acc);
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+            ostat.add(sg, ov, seg_acc);
           } else if (MODE == 2) {
             o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
           } else {
-            if (sg != cseg) {
-              if (cseg >= 0) {
-                float* dst = p.colsum + (size_t)(b_first + cseg) * kC + col0 + c4;
-                atomicAdd(dst, csum.x); atomicAdd(dst + 1, csum.y); atomicAdd(dst + 2, csum.z); atomicAdd(dst + 3, csum.w);
-              }
-              csum = make_float4(0.f, 0.f, 0.f, 0.f);
-              cseg = sg;
+            if (sg == 0) { cs0.x += o.x; cs0.y += o.y; cs0.z += o.z; cs0.w += o.w; }
+            else if (sg == 1) { cs1.x += o.x; cs1.y += o.y; cs1.z += o.z; cs1.w += o.w; }
+            else {  // only when T < 128
+              double* dst = p.colsum + (size_t)(b_first + sg) * kC + col0 + c4;
+              atomicAdd(dst, (double)o.x); atomicAdd(dst + 1, (double)o.y);
+              atomicAdd(dst + 2, (double)o.z); atomicAdd(dst + 3, (double)o.w);
             }
-            csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w;
           }
           *reinterpret_cast<float4*>(p.out + (int64_t)row * p.out_stride + gcol) = o;
         }
       }
       if (MODE == 1) {
-        // column sums: combine the 4 row groups of the warp when they all belong to one utterance
-        const int seg0 = __shfl_sync(0xffffffffu, cseg, 0);
-        const bool uniform = __all_sync(0xffffffffu, cseg == seg0);
-        if (uniform) {
-          if (seg0 >= 0) {
+        // column sums: fold the 4 row groups of the warp, then one global atomic per column and utterance
 #pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-              csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
-              csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
-            }
-            if (lane < 8) {
-              float* dst = p.colsum + (size_t)(b_first + seg0) * kC + col0 + c4;
-              atomicAdd(dst, csum.x); atomicAdd(dst + 1, csum.y); atomicAdd(dst + 2, csum.z); atomicAdd(dst + 3, csum.w);
-            }
+        for (int o = 8; o <= 16; o <<= 1) {
+          cs0.x += __shfl_xor_sync(0xffffffffu, cs0.x, o); cs0.y += __shfl_xor_sync(0xffffffffu, cs0.y, o);
+          cs0.z += __shfl_xor_sync(0xffffffffu, cs0.z, o); cs0.w += __shfl_xor_sync(0xffffffffu, cs0.w, o);
+          cs1.x += __shfl_xor_sync(0xffffffffu, cs1.x, o); cs1.y += __shfl_xor_sync(0xffffffffu, cs1.y, o);
+          cs1.z += __shfl_xor_sync(0xffffffffu, cs1.z, o); cs1.w += __shfl_xor_sync(0xffffffffu, cs1.w, o);
+        }
+        if (lane < 8) {
+          double* dst = p.colsum + (size_t)b_first * kC + col0 + c4;
+          atomicAdd(dst, (double)cs0.x); atomicAdd(dst + 1, (double)cs0.y);
+          atomicAdd(dst + 2, (double)cs0.z); atomicAdd(dst + 3, (double)cs0.w);
+          if (nseg > 1) {
+            dst += kC;
+            atomicAdd(dst, (double)cs1.x); atomicAdd(dst + 1, (double)cs1.y);
+            atomicAdd(dst + 2, (double)cs1.z); atomicAdd(dst + 3, (double)cs1.w);
           }
-        } else if (cseg >= 0) {
-          float* dst = p.colsum + (size_t)(b_first + cseg) * kC + col0 + c4;
-          atomicAdd(dst, csum.x); atomicAdd(dst + 1, csum.y); atomicAdd(dst + 2, csum.z); atomicAdd(dst + 3, csum.w);
         }
       }
     }
-    if (MODE == 0) ostat.flush(seg_acc);
+    if (MODE == 0) ostat.flush_warp(slots, warp);
     if (MODE == 1) {
       // row sums: the two column halves (warps w and w+4) own the same rows
       if (ch == 1) rs_x[my_rl] = rowacc;
@@ -467,18 +485,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem_base, 256);
   Stat2* sdst = (MODE == 0) ? p.st_out : (MODE == 1 ? p.st_q : nullptr);
-  if (sdst != nullptr && blockIdx.y == 0) {
-    for (int i = threadIdx.x; i < nseg; i += kThreads) {
-      atomicAdd(&sdst[b_first + i].s, (double)seg_acc[2 * i]);
-      atomicAdd(&sdst[b_first + i].ss, (double)seg_acc[2 * i + 1]);
-    }
-  }
+  if (sdst != nullptr && blockIdx.y == 0) seg_stats_commit(slots, 8, seg_acc, nseg, sdst + b_first);
 }
 
 template <int MODE>
 void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
   constexpr int NT = (MODE == 2) ? 192 : 256;
-  constexpr int smem = kStages * (kAChunkBytes + NT * 128) + kAuxBytes + 1024;
+  constexpr int smem = kStages * (kAChunkBytes + NT * 128) + kAuxBytes + 1024 + (MODE == 1 ? kDconvWBytes : 0);
   dim3 grid((p.M + kTileM - 1) / kTileM, ntiles_n);
   k_tc_gemm<MODE><<<grid, kThreads, smem, st>>>(p);
   ++g_launch_count;
@@ -488,14 +501,29 @@ void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
 
 cudaError_t tc_gemm_setup() {
   cudaError_t e;
+  // two CTAs per SM need (almost) the whole shared-memory carveout
+  cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_tc_gemm<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   e = cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024);
+                           kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024 + kDconvWBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_tc_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            kStages * (kAChunkBytes + 192 * 128) + kAuxBytes + 1024);
+  if (e == cudaSuccess && getenv("SEPTFA_DEBUG")) {
+    int o0 = 0, o1 = 0, o2 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, k_tc_gemm<0>, kThreads, kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_tc_gemm<1>, kThreads,
+                                                  kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024 + kDconvWBytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_tc_gemm<2>, kThreads, kStages * (kAChunkBytes + 192 * 128) + kAuxBytes + 1024);
+    int smem_sm = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    fprintf(stderr, "septfa: k_tc_gemm occupancy (CTAs/SM): conv1 %d, dconv %d, outconv %d (smem/SM %d B)\n", o0, o1, o2, smem_sm);
+  }
   return e;
 }
 
@@ -503,7 +531,7 @@ void launch_tc_conv1(const Conv1Params& c, cudaStream_t st) {
   TcParams p{};
   p.M = c.M; p.T = c.T; p.B = c.B;
   p.w_img = c.w_img; p.in = c.w_in; p.norm = c.norm;
-  p.bias = c.bias; p.slope = c.slope;
+  p.bias = c.bias_f; p.slope = c.slope;
   p.out = c.p_out; p.out_stride = kC; p.st_out = c.st_p;
   launch_mode<0>(p, 1, st);
 }
@@ -512,7 +540,8 @@ void launch_tc_dconv(const DconvParams& c, cudaStream_t st) {
   TcParams p{};
   p.M = c.M; p.T = c.T; p.B = c.B;
   p.w_img = c.w_img; p.in = c.p_in;
-  p.st_p = c.st_p; p.g1 = c.g1; p.be1 = c.be1; p.w2b = c.w2b; p.slope2 = c.slope2; p.dil = c.dil; p.st_q = c.st_q;
+  p.st_p = c.st_p; p.g1 = c.g1; p.be1 = c.be1; p.w2b = c.w2b; p.w2f = c.w2f; p.c2f = c.c2f;
+  p.slope2 = c.slope2; p.dil = c.dil; p.st_q = c.st_q;
   p.out = c.racc; p.out_stride = kC; p.rowsum = c.rowsum; p.colsum = c.colsum;
   launch_mode<1>(p, 1, st);
 }

@@ -25,7 +25,8 @@ struct Conv1Params {
   int M, T, B;
   const float* bias;   // [256]
   float slope;
-  const __half* w_img; // tcgen05 image: 4 K-chunks x [256 rows x 128 B], 128B-swizzled K-major
+  const __half* w_img; // tcgen05 image of W1*diag(gamma_in): 4 K-chunks x [256 rows x 128 B], 128B-swizzled K-major
+  const float* bias_f; // [256] b1 + W1 beta_in (the stream norm's affine folded into the weights; tcgen05 engine)
   const float* w_t;    // fp32 [256 k][256 n]
   float* p_out;        // [M,256]
   Stat2* st_p;         // [B]
@@ -39,6 +40,8 @@ struct DconvParams {
   const float* g1;     // reg1 gamma/beta [256]
   const float* be1;
   const float4* w2b;   // [512] {w[o][0], w[o][1], w[o][2], b2[o]}
+  const float4* w2f;   // [512] reg1 folded in: {w[o][k]*g1[o/2] (k=0..2), their sum}
+  const float* c2f;    // [512] b2[o] + be1[o/2] * sum_k w[o][k]
   float slope2;
   int dil;
   int M, T, B;
@@ -46,7 +49,7 @@ struct DconvParams {
   const float* w_t;    // fp32 [512 k][256 n] (gamma2-folded)
   float* racc;         // [M,256]
   float* rowsum;       // [M]
-  float* colsum;       // [B,256] (pre-zeroed, accumulated with atomics)
+  double* colsum;      // [B,256] (pre-zeroed, accumulated with double atomics)
   Stat2* st_q;         // [B]
 };
 
@@ -78,7 +81,7 @@ struct GateParams {
   const float* s3;     // [256] sum_o W3g[c,o]
   const float* c03;    // [256] sum_o W3[c,o]*beta2[o] + b3[c]
   const float* rowsum; // [M]
-  const float* colsum; // [B,256]
+  const double* colsum; // [B,256]
   TfParams tf;
   int M, T, B;
   float* ra;           // [B]
@@ -105,10 +108,9 @@ struct ResidParams {
 // ---- launchers ---------------------------------------------------------------------------
 // frontend.cu
 void make_twiddles(float2* host256);
-void launch_stft(const float* x, int B, int64_t L, int T, const float* window, const float2* twiddle, float2* S, float* P,
-                 cudaStream_t st);
-void launch_activity_gate(const float* P, int B, int T, int enabled, const float* k3x3, float bias, float slope,
-                          float* z0, float* dc_gated, Stat2* st0, cudaStream_t st);
+void launch_frontend(const float* x, int B, int64_t L, int T, const float* window, const float2* twiddle, int enabled,
+                     const float* k3x3, float bias, float slope, float2* S, float* z0, float* dc_gated, Stat2* st0,
+                     cudaStream_t st);
 // tcn.cu
 void launch_ref_conv1(const Conv1Params& p, cudaStream_t st);
 void launch_ref_dconv(const DconvParams& p, cudaStream_t st);
@@ -129,8 +131,8 @@ struct VadParams {
   const float* w1t;      // [5 k][4 j][257 f] folded conv1_1 weights
   float b1[4]; float slope; float g[4]; float be[4];
   float w2[12]; float b2;  // output_layer_vad [4 j][3 k]
+  float* part;           // [M, 2, 20] per-row partial products of conv1_1 (scratch)
   float* c4;             // [B*2*T, 4] scratch
-  Stat2* st_v;           // [B*2]
   float* prob;           // [B,2,T]
   float* smooth;         // [B,2,T]
   float thr;

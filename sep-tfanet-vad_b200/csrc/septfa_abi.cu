@@ -1,6 +1,7 @@
 // C ABI of libseptfa.so (include/septfa.h): handle, weight folding / packing, workspace carving,
 // the forward pass orchestration and the online (sliding-window) step.
 // Reference: model/model.py:360-461 (SeparationModel), model/online_class_unknown_targets.py:72-105.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -23,8 +24,8 @@ struct KeySpec {
 };
 
 struct DevBlock {
-  const __half* w1_img; const float* w1_t; const float* b1; float a1; const float* g1; const float* be1;
-  const float4* w2b; float a2; int dil;
+  const __half* w1_img; const float* w1_t; const float* b1; const float* b1f; float a1; const float* g1; const float* be1;
+  const float4* w2b; const float4* w2f; const float* c2f; float a2; int dil;
   const __half* w3_img; const float* w3_t; const float* s3_tc; const float* s3_ref; const float* c03;
   TfParams tf;
   const float* lf_g; const float* lf_b; const float* ls_g; const float* ls_b;  // recursive
@@ -55,7 +56,9 @@ struct septfa_handle {
   const float* win_fwd = nullptr; const float* win_inv = nullptr; const float2* twiddle = nullptr;
   int last_launches = 0;
   // forward_host resources
-  cudaStream_t hstream = nullptr;
+  cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
+  cudaEvent_t hev_in[8] = {}, hev_done[8] = {};
+  int host_chunks = 0;  // 0 = automatic
   float* hx_dev = nullptr; float* hout_dev = nullptr; float* hvad_dev = nullptr; void* hws = nullptr;
   float* hx_pin = nullptr; float* hout_pin = nullptr; float* hvad_pin = nullptr;
   size_t hcap_x = 0, hcap_out = 0, hcap_vad = 0, hcap_ws = 0;
@@ -83,6 +86,7 @@ struct septfa_online {
 namespace {
 
 constexpr int kFs = 16000, kWinLen = 48000, kHopLen = 16000, kTailCap = 32000;
+constexpr int kHostChunksMax = 8;
 
 int fail(septfa_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
@@ -202,10 +206,10 @@ std::vector<__half> pack_image(const std::vector<double>& w, int nvalid, int kdi
 const std::vector<float>& T_(septfa_handle* h, const std::string& k) { return h->host.at(k); }
 
 struct Workspace {
-  float2* S; float* P; float* w; float* dcg; float* p; float* racc; float* rowsum; float* gt; float* logits;
+  float2* S; float* part; float* w; float* dcg; float* p; float* racc; float* rowsum; float* gt; float* logits;
   float* ra; float* rb; float* gf; float* c4; float* prob; float* smooth;
   uint8_t* zero_begin; size_t zero_bytes;
-  Stat2* st0; Stat2* st_blk; Stat2* st_o; Stat2* st_vad; float* colsum;
+  Stat2* st0; Stat2* st_blk; Stat2* st_o; Stat2* st_vad; double* colsum;
   size_t total;
 };
 
@@ -219,7 +223,7 @@ Workspace carve(const septfa_handle* h, void* base, int B, int64_t L) {
     return p;
   };
   w.S = (float2*)take(M * kBins * sizeof(float2));
-  w.P = (float*)take(M * kBins * sizeof(float));
+  w.part = (float*)take(M * 40 * sizeof(float));
   w.w = (float*)take(M * kC * sizeof(float));
   w.dcg = (float*)take(M * sizeof(float));
   w.p = (float*)take(M * kC * sizeof(float));
@@ -238,7 +242,7 @@ Workspace carve(const septfa_handle* h, void* base, int B, int64_t L) {
   w.st_blk = (Stat2*)take((size_t)h->nblk * 4 * B * sizeof(Stat2));
   w.st_o = (Stat2*)take(B * sizeof(Stat2));
   w.st_vad = (Stat2*)take((size_t)B * 2 * sizeof(Stat2));
-  w.colsum = (float*)take((size_t)h->nblk * B * kC * sizeof(float));
+  w.colsum = (double*)take((size_t)h->nblk * B * kC * sizeof(double));
   w.zero_bytes = (reinterpret_cast<uint8_t*>(base) + off) - w.zero_begin;
   w.total = off;
   return w;
@@ -316,7 +320,10 @@ void septfa_destroy(septfa_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   cudaFree(h->hx_dev); cudaFree(h->hout_dev); cudaFree(h->hvad_dev); cudaFree(h->hws); cudaFree(h->pit_acc);
   cudaFreeHost(h->hx_pin); cudaFreeHost(h->hout_pin); cudaFreeHost(h->hvad_pin);
-  if (h->hstream) cudaStreamDestroy(h->hstream);
+  if (h->hstream) {
+    cudaStreamDestroy(h->hstream); cudaStreamDestroy(h->hstream_in); cudaStreamDestroy(h->hstream_out);
+    for (int i = 0; i < kHostChunksMax; ++i) { cudaEventDestroy(h->hev_in[i]); cudaEventDestroy(h->hev_done[i]); }
+  }
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
@@ -352,6 +359,11 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "profile") == 0) {
     h->profile = value ? 1 : 0;
+    return 0;
+  }
+  if (std::strcmp(name, "host_chunks") == 0) {
+    if (value < 0 || value > kHostChunksMax) return fail(h, SEPTFA_E_INVALID, "host_chunks must be 0..8");
+    h->host_chunks = value;
     return 0;
   }
   return fail(h, SEPTFA_E_INVALID, std::string("unknown option ") + name);
@@ -395,8 +407,28 @@ int septfa_commit_weights(septfa_handle* h) {
       std::vector<float> wt((size_t)kC * kC);
       for (int n = 0; n < kC; ++n)
         for (int k = 0; k < kC; ++k) wt[(size_t)k * kC + n] = (float)w[(size_t)n * kC + k];
-      if (upload(h, pack_image(w, kC, kC, 1, 256), &d.w1_img) || upload(h, wt, &d.w1_t) ||
-          upload(h, T_(h, p + ".conv1d.bias"), &d.b1))
+      // tcgen05 engine: the affine (gamma, beta) of the norm that produces this block's input is folded into
+      // the weights / bias, so the A operand is the plain standardised stream (x - mean) * rstd.
+      const std::vector<float>* gin = nullptr; const std::vector<float>* bin = nullptr;
+      if (i == 0) { gin = &T_(h, "TCN.LN.weight"); bin = &T_(h, "TCN.LN.bias"); }
+      else if (c.apply_recursive_ln) {
+        gin = &T_(h, "TCN.ln_second_modules." + std::to_string(i - 1) + ".weight");
+        bin = &T_(h, "TCN.ln_second_modules." + std::to_string(i - 1) + ".bias");
+      }
+      std::vector<double> wf(w);
+      std::vector<float> b1f(T_(h, p + ".conv1d.bias"));
+      if (gin) {
+        for (int n = 0; n < kC; ++n) {
+          double acc = 0.0;
+          for (int k = 0; k < kC; ++k) {
+            acc += w[(size_t)n * kC + k] * (double)(*bin)[k];
+            wf[(size_t)n * kC + k] = w[(size_t)n * kC + k] * (double)(*gin)[k];
+          }
+          b1f[n] = (float)((double)b1f[n] + acc);
+        }
+      }
+      if (upload(h, pack_image(wf, kC, kC, 1, 256), &d.w1_img) || upload(h, wt, &d.w1_t) ||
+          upload(h, T_(h, p + ".conv1d.bias"), &d.b1) || upload(h, b1f, &d.b1f))
         return SEPTFA_E_CUDA;
       d.a1 = T_(h, p + ".nonlinearity1.weight")[0];
       if (upload(h, T_(h, p + ".reg1.weight"), &d.g1) || upload(h, T_(h, p + ".reg1.bias"), &d.be1)) return SEPTFA_E_CUDA;
@@ -405,9 +437,18 @@ int septfa_commit_weights(septfa_handle* h) {
     {
       const auto w = fold_wn(T_(h, p + ".dconv1d.weight_g"), T_(h, p + ".dconv1d.weight_v"), kH);
       const auto& b2 = T_(h, p + ".dconv1d.bias");
-      std::vector<float4> w2b(kH);
-      for (int o = 0; o < kH; ++o) w2b[o] = make_float4((float)w[o * 3], (float)w[o * 3 + 1], (float)w[o * 3 + 2], b2[o]);
-      if (upload(h, w2b, &d.w2b)) return SEPTFA_E_CUDA;
+      const auto& g1v = T_(h, p + ".reg1.weight");
+      const auto& be1v = T_(h, p + ".reg1.bias");
+      std::vector<float4> w2b(kH), w2f(kH);
+      std::vector<float> c2f(kH);
+      for (int o = 0; o < kH; ++o) {
+        w2b[o] = make_float4((float)w[o * 3], (float)w[o * 3 + 1], (float)w[o * 3 + 2], b2[o]);
+        const double g = g1v[o / 2], be = be1v[o / 2];
+        const double f0 = w[o * 3] * g, f1 = w[o * 3 + 1] * g, f2 = w[o * 3 + 2] * g;
+        w2f[o] = make_float4((float)f0, (float)f1, (float)f2, (float)(f0 + f1 + f2));
+        c2f[o] = (float)((double)b2[o] + be * (w[o * 3] + w[o * 3 + 1] + w[o * 3 + 2]));
+      }
+      if (upload(h, w2b, &d.w2b) || upload(h, w2f, &d.w2f) || upload(h, c2f, &d.c2f)) return SEPTFA_E_CUDA;
       d.a2 = T_(h, p + ".nonlinearity2.weight")[0];
     }
     // res_out 512 -> 256 with GroupNorm reg2 folded in:  r = rstd2 * (W3g q - mu2 * s3) + c03
@@ -527,8 +568,8 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
 
   prof_mark(h, SEPTFA_PROF_FRONTEND, st);
   CUDA_TRY(h, cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, st));
-  launch_stft(x, B, L, T, h->win_fwd, h->twiddle, ws.S, ws.P, st);
-  launch_activity_gate(ws.P, B, T, c.activity_input_bool, h->act_k, h->act_b, h->act_a, ws.w, ws.dcg, ws.st0, st);
+  launch_frontend(x, B, L, T, h->win_fwd, h->twiddle, c.activity_input_bool, h->act_k, h->act_b, h->act_a, ws.S, ws.w,
+                  ws.dcg, ws.st0, st);
   if (spectrum) launch_export(ws.S, ws.logits, nullptr, ws.w, ws.dcg, B, T, nullptr, nullptr, spectrum, nullptr, st);
 
   const double inv_n = 1.0 / ((double)kC * T);
@@ -539,14 +580,14 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     Stat2* st_q = ws.st_blk + (size_t)(i * 4 + 1) * B;
     Stat2* st_v = ws.st_blk + (size_t)(i * 4 + 2) * B;
     Stat2* st_w = ws.st_blk + (size_t)(i * 4 + 3) * B;
-    float* colsum = ws.colsum + (size_t)i * B * kC;
+    double* colsum = ws.colsum + (size_t)i * B * kC;
 
-    Conv1Params c1{ws.w, norm, M, T, B, d.b1, d.a1, d.w1_img, d.w1_t, ws.p, st_p};
+    Conv1Params c1{ws.w, norm, M, T, B, d.b1, d.a1, d.w1_img, d.b1f, d.w1_t, ws.p, st_p};
     prof_mark(h, SEPTFA_PROF_CONV1, st);
     if (tc_conv1) launch_tc_conv1(c1, st); else launch_ref_conv1(c1, st);
 
     prof_mark(h, SEPTFA_PROF_DCONV, st);
-    DconvParams dc{ws.p, st_p, d.g1, d.be1, d.w2b, d.a2, d.dil, M, T, B, d.w3_img, d.w3_t, ws.racc, ws.rowsum, colsum, st_q};
+    DconvParams dc{ws.p, st_p, d.g1, d.be1, d.w2b, d.w2f, d.c2f, d.a2, d.dil, M, T, B, d.w3_img, d.w3_t, ws.racc, ws.rowsum, colsum, st_q};
     if (tc_dconv) launch_tc_dconv(dc, st); else launch_ref_dconv(dc, st);
 
     prof_mark(h, SEPTFA_PROF_GATE, st);
@@ -587,7 +628,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     std::memcpy(vp.b1, h->vad_b1, sizeof(vp.b1)); vp.slope = h->vad_a;
     std::memcpy(vp.g, h->vad_g, sizeof(vp.g)); std::memcpy(vp.be, h->vad_be, sizeof(vp.be));
     std::memcpy(vp.w2, h->vad_w2, sizeof(vp.w2)); vp.b2 = h->vad_b2;
-    vp.c4 = ws.c4; vp.st_v = ws.st_vad; vp.prob = ws.prob; vp.smooth = ws.smooth;
+    vp.part = ws.part; vp.c4 = ws.c4; vp.prob = ws.prob; vp.smooth = ws.smooth;
     vp.thr = use_kw ? kw->threshold_activated_vad : 0.f;
     vp.do_smooth = use_kw ? 1 : 0;
     launch_vad(vp, st);
@@ -633,10 +674,23 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
   if (int rc = check_forward_args(h, B, L)) return rc;
   if (!x_host || !out_wav_host) return fail(h, SEPTFA_E_INVALID, "null host buffer");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  if (!h->hstream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+  if (!h->hstream) {
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->hstream_in, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->hstream_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kHostChunksMax; ++i) {
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->hev_in[i], cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->hev_done[i], cudaEventDisableTiming));
+    }
+  }
   const int64_t T = septfa_num_frames(L);
+  // Independent utterances: the batch is cut into chunks so that the H2D copy of chunk c+1 and the D2H copy
+  // of chunk c-1 overlap the kernels of chunk c (three streams, events between them).
+  int nchunk = h->host_chunks > 0 ? h->host_chunks : (B >= 128 ? 4 : (B >= 32 ? 2 : 1));
+  nchunk = std::min(std::min(nchunk, kHostChunksMax), B);
+  const int Bc = (B + nchunk - 1) / nchunk;
   const size_t nx = (size_t)B * L * sizeof(float), nout = nx * 2, nvad = (size_t)B * 2 * T * sizeof(float);
-  const size_t nws = septfa_workspace_bytes(h, B, L);
+  const size_t nws = septfa_workspace_bytes(h, Bc, L);
   auto grow = [&](float** dev, float** pin, size_t* cap, size_t need) -> cudaError_t {
     if (*cap >= need) return cudaSuccess;
     cudaFree(*dev); cudaFreeHost(*pin);
@@ -662,18 +716,35 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
     return at.type == cudaMemoryTypeHost;
   };
   const bool pin_x = is_pinned(x_host), pin_out = is_pinned(out_wav_host);
-  const bool pin_vad = out_vad_host != nullptr && is_pinned(out_vad_host);
+  const bool want_vad = h->cfg.final_vad && out_vad_host != nullptr;
+  const bool pin_vad = want_vad && is_pinned(out_vad_host);
   if (!pin_x) std::memcpy(h->hx_pin, x_host, nx);
-  CUDA_TRY(h, cudaMemcpyAsync(h->hx_dev, pin_x ? x_host : h->hx_pin, nx, cudaMemcpyHostToDevice, h->hstream));
-  if (int rc = septfa_forward(h, h->hx_dev, B, L, kw, h->hout_dev, h->hvad_dev, nullptr, nullptr, nullptr, nullptr, h->hws,
-                              h->hcap_ws, h->hstream))
-    return rc;
-  CUDA_TRY(h, cudaMemcpyAsync(pin_out ? out_wav_host : h->hout_pin, h->hout_dev, nout, cudaMemcpyDeviceToHost, h->hstream));
-  if (h->cfg.final_vad && out_vad_host)
-    CUDA_TRY(h, cudaMemcpyAsync(pin_vad ? out_vad_host : h->hvad_pin, h->hvad_dev, nvad, cudaMemcpyDeviceToHost, h->hstream));
+  const float* xsrc = pin_x ? x_host : h->hx_pin;
+  float* odst = pin_out ? out_wav_host : h->hout_pin;
+  float* vdst = pin_vad ? out_vad_host : h->hvad_pin;
+  int launches = 0;
+  for (int c = 0; c < nchunk; ++c) {
+    const int b0 = c * Bc, bn = std::min(Bc, B - b0);
+    if (bn <= 0) break;
+    const size_t xo = (size_t)b0 * L, oo = (size_t)b0 * 2 * L, vo = (size_t)b0 * 2 * T;
+    CUDA_TRY(h, cudaMemcpyAsync(h->hx_dev + xo, xsrc + xo, (size_t)bn * L * sizeof(float), cudaMemcpyHostToDevice, h->hstream_in));
+    CUDA_TRY(h, cudaEventRecord(h->hev_in[c], h->hstream_in));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->hstream, h->hev_in[c], 0));
+    if (int rc = septfa_forward(h, h->hx_dev + xo, bn, L, kw, h->hout_dev + oo, h->hvad_dev + vo, nullptr, nullptr, nullptr,
+                                nullptr, h->hws, h->hcap_ws, h->hstream))
+      return rc;
+    launches += h->last_launches;
+    CUDA_TRY(h, cudaEventRecord(h->hev_done[c], h->hstream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->hstream_out, h->hev_done[c], 0));
+    CUDA_TRY(h, cudaMemcpyAsync(odst + oo, h->hout_dev + oo, (size_t)bn * 2 * L * sizeof(float), cudaMemcpyDeviceToHost, h->hstream_out));
+    if (want_vad)
+      CUDA_TRY(h, cudaMemcpyAsync(vdst + vo, h->hvad_dev + vo, (size_t)bn * 2 * T * sizeof(float), cudaMemcpyDeviceToHost, h->hstream_out));
+  }
+  h->last_launches = launches;
+  CUDA_TRY(h, cudaStreamSynchronize(h->hstream_out));
   CUDA_TRY(h, cudaStreamSynchronize(h->hstream));
   if (!pin_out) std::memcpy(out_wav_host, h->hout_pin, nout);
-  if (h->cfg.final_vad && out_vad_host && !pin_vad) std::memcpy(out_vad_host, h->hvad_pin, nvad);
+  if (want_vad && !pin_vad) std::memcpy(out_vad_host, h->hvad_pin, nvad);
   return 0;
 }
 

@@ -13,24 +13,6 @@ __device__ __forceinline__ void fill_seg_table(float2* tab, const Stat2* st, dou
   for (int i = threadIdx.x; i < nseg; i += blockDim.x) tab[i] = stat_mean_rstd(st + b_first + i, inv_n, eps);
 }
 
-// Per-lane running statistics with segment tracking; flushed to shared float accumulators.
-struct SegAcc {
-  float s = 0.f, ss = 0.f;
-  int seg = -1;
-  __device__ __forceinline__ void add(int sg, float v, float* sm /*[nseg][2]*/) {
-    if (sg != seg) { flush(sm); seg = sg; }
-    s += v;
-    ss += v * v;
-  }
-  __device__ __forceinline__ void flush(float* sm) {
-    if (seg >= 0 && (s != 0.f || ss != 0.f)) {
-      atomicAdd(sm + 2 * seg, s);
-      atomicAdd(sm + 2 * seg + 1, ss);
-    }
-    s = ss = 0.f;
-  }
-};
-
 constexpr int kRowsPerCta = 64;  // element-wise kernels: 8 warps x 8 rows, lane = 8 channels
 
 struct RowCtx {
@@ -67,6 +49,7 @@ __global__ void __launch_bounds__(256) k_resid(ResidParams p) {
   __shared__ float2 tab_y[kMaxSegs];   // stream norm
   __shared__ float2 tab_v[kMaxSegs];   // stats of v (MODE 1)
   __shared__ float acc_sm[kMaxSegs * 2];
+  __shared__ float slots[8 * 4];
   const RowCtx c = row_ctx(p.M, p.T);
   const bool has_norm = p.norm.gamma != nullptr;
   if (has_norm) fill_seg_table(tab_y, p.norm.st, p.norm.inv_n, p.norm.eps, c.b_first, c.nseg);
@@ -78,10 +61,11 @@ __global__ void __launch_bounds__(256) k_resid(ResidParams p) {
   float gy[8], by[8], ga[8], ba[8];
   if (has_norm) { ld8(p.norm.gamma + c0, gy); ld8(p.norm.beta + c0, by); }
   if (MODE == 1 && p.mode != LN_NONE) { ld8(p.g_a + c0, ga); ld8(p.b_a + c0, ba); }
-  SegAcc acc;
+  SegStat2 acc;
+  const SegMap smap(c.r0, p.T);
   for (int i = warp; i < c.nrows; i += 8) {
     const int row = c.r0 + i;
-    const int b = row / p.T, sg = b - c.b_first;
+    const int sg = smap.seg(row), b = c.b_first + sg;
     float w[8], ra8[8], rb[8], gf[8], y[8], v[8];
     ld8_plain(p.w + (int64_t)row * kC + c0, w);
     ld8(p.racc + (int64_t)row * kC + c0, ra8);
@@ -96,8 +80,7 @@ __global__ void __launch_bounds__(256) k_resid(ResidParams p) {
       v[j] = (p.mode == LN_RECURSIVE) ? y[j] + r : r;
     }
     if (MODE == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc.add(sg, v[j], acc_sm);
+      acc.add(sg, v, acc_sm);
     } else {
       float o[8];
       if (p.mode == LN_NONE) {
@@ -109,21 +92,13 @@ __global__ void __launch_bounds__(256) k_resid(ResidParams p) {
         for (int j = 0; j < 8; ++j) o[j] = y[j] + (((v[j] - mv.x) * mv.y) * ga[j] + ba[j]);
       }
       st8(p.w + (int64_t)row * kC + c0, o);
-      if (p.mode == LN_RECURSIVE) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc.add(sg, o[j], acc_sm);
-      }
+      if (p.mode == LN_RECURSIVE) acc.add(sg, o, acc_sm);
     }
   }
-  acc.flush(acc_sm);
+  acc.flush_warp(slots, warp);
   __syncthreads();
   Stat2* dst = (MODE == 0) ? p.st_v : p.st_w;
-  if (dst != nullptr && (MODE == 0 || p.mode == LN_RECURSIVE)) {
-    for (int i = threadIdx.x; i < c.nseg; i += blockDim.x) {
-      atomicAdd(&dst[c.b_first + i].s, (double)acc_sm[2 * i]);
-      atomicAdd(&dst[c.b_first + i].ss, (double)acc_sm[2 * i + 1]);
-    }
-  }
+  if (dst != nullptr && (MODE == 0 || p.mode == LN_RECURSIVE)) seg_stats_commit(slots, 8, acc_sm, c.nseg, dst + c.b_first);
 }
 
 void launch_resid_stats(const ResidParams& p, cudaStream_t st) {
@@ -140,6 +115,7 @@ __global__ void __launch_bounds__(256) k_out_stats(const float* __restrict__ w, 
                                                    int T, Stat2* __restrict__ st_o) {
   __shared__ float2 tab_y[kMaxSegs];
   __shared__ float acc_sm[kMaxSegs * 2];
+  __shared__ float slots[8 * 4];
   const RowCtx c = row_ctx(M, T);
   const bool has_norm = norm.gamma != nullptr;
   if (has_norm) fill_seg_table(tab_y, norm.st, norm.inv_n, norm.eps, c.b_first, c.nseg);
@@ -148,25 +124,21 @@ __global__ void __launch_bounds__(256) k_out_stats(const float* __restrict__ w, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c0 = lane * 8;
   float gy[8], by[8];
   if (has_norm) { ld8(norm.gamma + c0, gy); ld8(norm.beta + c0, by); }
-  SegAcc acc;
+  SegStat2 acc;
+  const SegMap smap(c.r0, T);
   for (int i = warp; i < c.nrows; i += 8) {
     const int row = c.r0 + i;
-    const int sg = row / T - c.b_first;
-    float wv[8];
+    const int sg = smap.seg(row);
+    float wv[8], z[8];
     ld8(w + (int64_t)row * kC + c0, wv);
     const float2 my = has_norm ? tab_y[sg] : make_float2(0.f, 1.f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float y = has_norm ? ((wv[j] - my.x) * my.y) * gy[j] + by[j] : wv[j];
-      acc.add(sg, prelu(y, slope), acc_sm);
-    }
+    for (int j = 0; j < 8; ++j) z[j] = prelu(has_norm ? ((wv[j] - my.x) * my.y) * gy[j] + by[j] : wv[j], slope);
+    acc.add(sg, z, acc_sm);
   }
-  acc.flush(acc_sm);
+  acc.flush_warp(slots, warp);
   __syncthreads();
-  for (int i = threadIdx.x; i < c.nseg; i += blockDim.x) {
-    atomicAdd(&st_o[c.b_first + i].s, (double)acc_sm[2 * i]);
-    atomicAdd(&st_o[c.b_first + i].ss, (double)acc_sm[2 * i + 1]);
-  }
+  seg_stats_commit(slots, 8, acc_sm, c.nseg, st_o + c.b_first);
 }
 
 void launch_out_stats(const float* w, StreamNorm norm, float slope, int M, int T, Stat2* st_o, cudaStream_t st) {
@@ -214,7 +186,7 @@ __global__ void __launch_bounds__(256) k_tf_gate(GateParams p) {
   // thread = channel
   const float rbv = __ldg(p.c03 + tid) - ra * mu * __ldg(p.s3 + tid);
   p.rb[b * kC + tid] = rbv;
-  m_f[tid] = ra * (__ldg(p.colsum + b * kC + tid) / (float)p.T) + rbv;
+  m_f[tid] = ra * (float)(__ldg(p.colsum + b * kC + tid) / (double)p.T) + rbv;
   float s = warp_sum(rbv);
   if ((tid & 31) == 0) red[tid >> 5] = s;
   __syncthreads();
@@ -291,7 +263,7 @@ __global__ void __launch_bounds__(256) k_ref_dconv(DconvParams p) {
 #pragma unroll 8
   for (int k = 0; k < kH; ++k) acc = fmaf(q[k], __ldg(p.w_t + k * kC + c), acc);
   p.racc[(int64_t)row * kC + c] = acc;
-  atomicAdd(p.colsum + b * kC + c, acc);
+  atomicAdd(p.colsum + b * kC + c, (double)acc);
   float rs = warp_sum(acc);
   if ((c & 31) == 0) red[c >> 5] = rs;
   __syncthreads();

@@ -193,7 +193,7 @@ class SeparationModel(nn.Module):
             output_vad = vad
         return out, output_vad, self.estimated_stfts
 
-    def forward_host(self, x_host: torch.Tensor, inference_kw={}, device=0):
+    def forward_host(self, x_host: torch.Tensor, inference_kw={}, device=0, pin_outputs=True):
         """End-to-end call with HOST tensors: septfa_forward_host does the H2D copy, the forward and
         the D2H copy of (out_separation, output_vad) through pinned staging buffers."""
         assert x_host.ndim == 2 and not x_host.is_cuda
@@ -204,8 +204,10 @@ class SeparationModel(nn.Module):
         dev = torch.device("cuda", device)
         with torch.cuda.device(dev):
             h = self._handle(dev)
-            out = torch.empty((B, self.num_spk, L), dtype=torch.float32)
-            vad = torch.empty((B, self.num_spk, T), dtype=torch.float32) if self.final_vad else None
+            # page-locked result buffers (copied into directly by the library); pass pin_outputs=False for pageable
+            pin = bool(pin_outputs)
+            out = torch.empty((B, self.num_spk, L), dtype=torch.float32, pin_memory=pin)
+            vad = torch.empty((B, self.num_spk, T), dtype=torch.float32, pin_memory=pin) if self.final_vad else None
             rc = h.lib.septfa_forward_host(h.ptr, C.c_void_p(x_host.data_ptr()), B, L,
                                            C.byref(kw) if kw is not None else None, C.c_void_p(out.data_ptr()),
                                            C.c_void_p(vad.data_ptr()) if vad is not None else None)
