@@ -33,10 +33,13 @@ __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + exp
 
 // mean / rstd of one utterance from its double accumulators (biased variance, GroupNorm(1,C)).
 __device__ __forceinline__ float2 stat_mean_rstd(const Stat2* st, double inv_n, float eps) {
-  double m = st->s * inv_n;
+  // mean and the E[x^2] - mean^2 cancellation in double (three cheap DFMA-class ops); the reciprocal square
+  // root in float (IEEE sqrt + divide) - a double sqrt/divide is a ~200-instruction software routine that every
+  // CTA would wait on before touching its tile.
+  const double m = st->s * inv_n;
   double var = st->ss * inv_n - m * m;
   if (var < 0.0) var = 0.0;
-  return make_float2((float)m, (float)(1.0 / sqrt(var + (double)eps)));
+  return make_float2((float)m, 1.0f / sqrtf((float)var + eps));
 }
 
 // Block-wide reduction of (s, ss) for blocks whose rows all belong to ONE utterance, followed by

@@ -13,7 +13,7 @@ __device__ __forceinline__ void fill_seg_table(float2* tab, const Stat2* st, dou
   for (int i = threadIdx.x; i < nseg; i += blockDim.x) tab[i] = stat_mean_rstd(st + b_first + i, inv_n, eps);
 }
 
-constexpr int kRowsPerCta = 64;  // element-wise kernels: 8 warps x 8 rows, lane = 8 channels
+constexpr int kRowsPerCta = 128;  // rows per CTA of the element-wise kernels
 
 struct RowCtx {
   int r0, nrows, b_first, nseg;
@@ -43,7 +43,10 @@ __device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
 }
 
 // MODE: 0 = statistics of v only; 1 = apply (w <- y + GN(v)), plus statistics of the new stream
-// when the ln mode is recursive.
+// when the ln mode is recursive.  Per element (coefficients cached per utterance in registers):
+//   y = w * Ay + By            Ay = rstd_y * gamma_y, By = beta_y - mean_y * Ay      (stream norm)
+//   r*g = gt[row] * (racc * G1 + G2)      G1 = ra * gf, G2 = rb * gf             (TF-attention gates)
+//   v = y + r*g (recursive) | r*g (residual);  out = y + v * Av + Bv   (Av, Bv: ln_first / ln_modules)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_resid(ResidParams p) {
   __shared__ float2 tab_y[kMaxSegs];   // stream norm
@@ -52,47 +55,84 @@ __global__ void __launch_bounds__(256) k_resid(ResidParams p) {
   __shared__ float slots[8 * 4];
   const RowCtx c = row_ctx(p.M, p.T);
   const bool has_norm = p.norm.gamma != nullptr;
+  const bool use_v_norm = MODE == 1 && p.mode != LN_NONE;
   if (has_norm) fill_seg_table(tab_y, p.norm.st, p.norm.inv_n, p.norm.eps, c.b_first, c.nseg);
-  if (MODE == 1 && p.mode != LN_NONE) fill_seg_table(tab_v, p.st_v, 1.0 / (256.0 * p.T), 1e-5f, c.b_first, c.nseg);
+  if (use_v_norm) fill_seg_table(tab_v, p.st_v, 1.0 / (256.0 * p.T), 1e-5f, c.b_first, c.nseg);
   for (int i = threadIdx.x; i < c.nseg * 2; i += blockDim.x) acc_sm[i] = 0.f;
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c0 = lane * 8;
-  float gy[8], by[8], ga[8], ba[8];
-  if (has_norm) { ld8(p.norm.gamma + c0, gy); ld8(p.norm.beta + c0, by); }
-  if (MODE == 1 && p.mode != LN_NONE) { ld8(p.g_a + c0, ga); ld8(p.b_a + c0, ba); }
+  // a warp covers half a row (lane = 4 channels); warps (2k, 2k+1) walk the same rows
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = ((warp & 1) * 32 + lane) * 4;
+  float4 Ay, By, G1, G2, Av, Bv;
+  Av = Bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur = -1;
   SegStat2 acc;
   const SegMap smap(c.r0, p.T);
-  for (int i = warp; i < c.nrows; i += 8) {
-    const int row = c.r0 + i;
-    const int sg = smap.seg(row), b = c.b_first + sg;
-    float w[8], ra8[8], rb[8], gf[8], y[8], v[8];
-    ld8_plain(p.w + (int64_t)row * kC + c0, w);
-    ld8(p.racc + (int64_t)row * kC + c0, ra8);
-    ld8(p.rb + b * kC + c0, rb);
-    ld8(p.gf + b * kC + c0, gf);
-    const float ra = __ldg(p.ra + b), gt = __ldg(p.gt + row);
-    const float2 my = has_norm ? tab_y[sg] : make_float2(0.f, 1.f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      y[j] = has_norm ? ((w[j] - my.x) * my.y) * gy[j] + by[j] : w[j];
-      const float r = (ra8[j] * ra + rb[j]) * (gf[j] * gt);
-      v[j] = (p.mode == LN_RECURSIVE) ? y[j] + r : r;
-    }
-    if (MODE == 0) {
-      acc.add(sg, v, acc_sm);
+  auto ld4 = [](const float* q) { return __ldg(reinterpret_cast<const float4*>(q)); };
+  auto load_coeffs = [&](int sg) {
+    const int b = c.b_first + sg;
+    if (has_norm) {
+      const float2 my = tab_y[sg];
+      const float4 g = ld4(p.norm.gamma + c0), be = ld4(p.norm.beta + c0);
+      Ay = make_float4(my.y * g.x, my.y * g.y, my.y * g.z, my.y * g.w);
+      By = make_float4(be.x - my.x * Ay.x, be.y - my.x * Ay.y, be.z - my.x * Ay.z, be.w - my.x * Ay.w);
     } else {
-      float o[8];
-      if (p.mode == LN_NONE) {
+      Ay = make_float4(1.f, 1.f, 1.f, 1.f);
+      By = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float ra = __ldg(p.ra + b);
+    const float4 rb = ld4(p.rb + b * kC + c0), gf = ld4(p.gf + b * kC + c0);
+    G1 = make_float4(ra * gf.x, ra * gf.y, ra * gf.z, ra * gf.w);
+    G2 = make_float4(rb.x * gf.x, rb.y * gf.y, rb.z * gf.z, rb.w * gf.w);
+    if (use_v_norm) {
+      const float2 mv = tab_v[sg];
+      const float4 g = ld4(p.g_a + c0), be = ld4(p.b_a + c0);
+      Av = make_float4(mv.y * g.x, mv.y * g.y, mv.y * g.z, mv.y * g.w);
+      Bv = make_float4(be.x - mv.x * Av.x, be.y - mv.x * Av.y, be.z - mv.x * Av.z, be.w - mv.x * Av.w);
+    }
+    cur = sg;
+  };
+  constexpr int RS = 4;  // rows per warp step: 8 x 16 B loads in flight per lane
+  for (int i = (warp >> 1) * RS; i < c.nrows; i += 4 * RS) {
+    float4 w[RS], ra4[RS];
+    float gt[RS];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = y[j] + v[j];
-      } else {
-        const float2 mv = tab_v[sg];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = y[j] + (((v[j] - mv.x) * mv.y) * ga[j] + ba[j]);
+    for (int k = 0; k < RS; ++k) {
+      if (i + k < c.nrows) {
+        const int row = c.r0 + i + k;
+        w[k] = *reinterpret_cast<const float4*>(p.w + (int64_t)row * kC + c0);  // coherent: rewritten in place
+        ra4[k] = ld4(p.racc + (int64_t)row * kC + c0);
+        gt[k] = __ldg(p.gt + row);
       }
-      st8(p.w + (int64_t)row * kC + c0, o);
-      if (p.mode == LN_RECURSIVE) acc.add(sg, o, acc_sm);
+    }
+#pragma unroll
+    for (int k = 0; k < RS; ++k) {
+      if (i + k < c.nrows) {
+        const int row = c.r0 + i + k;
+        const int sg = smap.seg(row);
+        if (sg != cur) load_coeffs(sg);
+        const float wv[4] = {w[k].x, w[k].y, w[k].z, w[k].w}, rv[4] = {ra4[k].x, ra4[k].y, ra4[k].z, ra4[k].w};
+        const float ay[4] = {Ay.x, Ay.y, Ay.z, Ay.w}, by[4] = {By.x, By.y, By.z, By.w};
+        const float g1[4] = {G1.x, G1.y, G1.z, G1.w}, g2[4] = {G2.x, G2.y, G2.z, G2.w};
+        float v[4], y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          y[j] = fmaf(wv[j], ay[j], by[j]);
+          const float r = gt[k] * fmaf(rv[j], g1[j], g2[j]);
+          v[j] = (p.mode == LN_RECURSIVE) ? y[j] + r : r;
+        }
+        if (MODE == 0) {
+          acc.add(sg, v, acc_sm);
+        } else {
+          const float av[4] = {Av.x, Av.y, Av.z, Av.w}, bv[4] = {Bv.x, Bv.y, Bv.z, Bv.w};
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = (p.mode == LN_NONE) ? y[j] + v[j] : y[j] + fmaf(v[j], av[j], bv[j]);
+          *reinterpret_cast<float4*>(p.w + (int64_t)row * kC + c0) = make_float4(o[0], o[1], o[2], o[3]);
+          if (p.mode == LN_RECURSIVE) acc.add(sg, o, acc_sm);
+        }
+      }
     }
   }
   acc.flush_warp(slots, warp);

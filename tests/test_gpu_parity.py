@@ -153,20 +153,27 @@ def test_engines_agree(cuda_models):
 
 
 def test_batch_invariance_and_determinism(cuda_models):
-    """Utterances are independent: item b of a batch equals the same item run alone (tiles straddle
-    utterances in the batched run), and repeated runs are reproducible to the atomics' rounding."""
+    """Utterances are independent: item b of a batch equals the same item run alone up to the fp16
+    operand noise (tiles straddle utterances differently, so the statistics' partial sums - and with
+    them some fp16 roundings - differ). Repeated runs of the SAME call are bit-identical whenever an
+    utterance spans at least one 128-frame tile (L >= 2 s): per-tile statistics are reduced in a fixed
+    order and accumulated in double. Shorter inputs (several utterances per tile) use shared-memory
+    float atomics for the 3rd+ utterance of a tile and reproduce only to the fp16 noise level."""
     args = synth.CONFIG_WITH_VAD
     m = cuda_models(args, 32, 0)
-    x = torch.from_numpy(synth.make_mixtures(5, 9000, 555)).cuda()
     kw = dict(synth.DEFAULT_INFERENCE_KW)
+    x = torch.from_numpy(synth.make_mixtures(5, 40000, 555)).cuda()   # T = 157
     ob, vb, _ = m(x, kw)
     ob2, vb2, _ = m(x, kw)
-    # per-tile statistics are reduced in a fixed order and accumulated in double: reruns are bit-identical
-    assert (ob - ob2).abs().max().item() == 0.0 and (vb - vb2).abs().max().item() == 0.0, ((ob - ob2).abs().max().item(), (vb - vb2).abs().max().item())
+    assert torch.equal(ob, ob2) and torch.equal(vb, vb2)
     for b in (0, 3, 4):
         o1, v1, _ = m(x[b:b + 1].contiguous(), kw)
         assert (o1[0] - ob[b]).abs().max().item() < 5e-4, (o1[0] - ob[b]).abs().max().item()
         assert (v1[0] - vb[b]).abs().max().item() < 1e-3, (v1[0] - vb[b]).abs().max().item()
+    xs = torch.from_numpy(synth.make_mixtures(5, 9000, 556)).cuda()    # T = 36: five utterances share a tile
+    os1, vs1, _ = m(xs, kw)
+    os2, vs2, _ = m(xs, kw)
+    assert (os1 - os2).abs().max().item() < 5e-4 and (vs1 - vs2).abs().max().item() < 1e-3
 
 
 def test_forward_host_equals_forward(cuda_models):
