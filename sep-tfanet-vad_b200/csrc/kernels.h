@@ -51,6 +51,7 @@ struct DconvParams {
   float* rowsum;       // [M]
   double* colsum;      // [B,256] (pre-zeroed, accumulated with double atomics)
   Stat2* st_q;         // [B]
+  long long* dbg;      // optional timeline buffer (bring-up only), nullptr otherwise
 };
 
 // TCN.output (model/model.py:322-325,357): logits = Wo GN(PReLU(y)) + bo, N = 514 padded to 576.
@@ -124,6 +125,9 @@ void launch_tc_conv1(const Conv1Params& p, cudaStream_t st);
 void launch_tc_dconv(const DconvParams& p, cudaStream_t st);
 void launch_tc_outconv(const OutConvParams& p, cudaStream_t st);
 cudaError_t tc_gemm_setup();  // opt-in shared memory attributes; call once per device
+// gemm_persist.cu
+cudaError_t dconv_persist_setup();
+void launch_dconv_persist(const DconvParams& p, cudaStream_t st);
 // backend.cu
 struct VadParams {
   const float* logits;   // [M,576]

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -59,9 +60,10 @@ struct septfa_handle {
   cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
   cudaEvent_t hev_in[8] = {}, hev_done[8] = {};
   int host_chunks = 0;  // 0 = automatic
-  float* hx_dev = nullptr; float* hout_dev = nullptr; float* hvad_dev = nullptr; void* hws = nullptr;
+  int dconv_persistent = 0;  // 1: persistent warp-specialised dconv+res_out kernel (experimental), 0: one tile per CTA
+  float* hx_dev = nullptr; float* hout_dev = nullptr; float* hvad_dev = nullptr; void* hws = nullptr; void* hws_b = nullptr;
   float* hx_pin = nullptr; float* hout_pin = nullptr; float* hvad_pin = nullptr;
-  size_t hcap_x = 0, hcap_out = 0, hcap_vad = 0, hcap_ws = 0;
+  size_t hcap_x = 0, hcap_out = 0, hcap_vad = 0, hcap_ws = 0, hcap_ws_b = 0;
   // pit scratch
   double* pit_acc = nullptr; int pit_cap = 0;
   // optional per-kernel-class profiling (CUDA events recorded on the launch stream)
@@ -273,6 +275,8 @@ int check_forward_args(septfa_handle* h, int B, int64_t L) {
 
 }  // namespace
 
+long long* septfa_dbg_ptr = nullptr;
+
 extern "C" {
 
 const char* septfa_version(void) { return "septfa-b200 0.1 (sm_100a)"; }
@@ -309,6 +313,7 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
   build_keys(h);
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, "cudaSetDevice failed"); }
   cudaError_t e = tc_gemm_setup();
+  if (e == cudaSuccess) e = dconv_persist_setup();
   if (e != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, std::string("tc_gemm_setup: ") + cudaGetErrorString(e)); }
   *out = h;
   return 0;
@@ -318,7 +323,7 @@ void septfa_destroy(septfa_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
-  cudaFree(h->hx_dev); cudaFree(h->hout_dev); cudaFree(h->hvad_dev); cudaFree(h->hws); cudaFree(h->pit_acc);
+  cudaFree(h->hx_dev); cudaFree(h->hout_dev); cudaFree(h->hvad_dev); cudaFree(h->hws); cudaFree(h->hws_b); cudaFree(h->pit_acc);
   cudaFreeHost(h->hx_pin); cudaFreeHost(h->hout_pin); cudaFreeHost(h->hvad_pin);
   if (h->hstream) {
     cudaStreamDestroy(h->hstream); cudaStreamDestroy(h->hstream_in); cudaStreamDestroy(h->hstream_out);
@@ -359,6 +364,10 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "profile") == 0) {
     h->profile = value ? 1 : 0;
+    return 0;
+  }
+  if (std::strcmp(name, "dconv_persistent") == 0) {
+    h->dconv_persistent = value ? 1 : 0;
     return 0;
   }
   if (std::strcmp(name, "host_chunks") == 0) {
@@ -587,8 +596,16 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     if (tc_conv1) launch_tc_conv1(c1, st); else launch_ref_conv1(c1, st);
 
     prof_mark(h, SEPTFA_PROF_DCONV, st);
-    DconvParams dc{ws.p, st_p, d.g1, d.be1, d.w2b, d.w2f, d.c2f, d.a2, d.dil, M, T, B, d.w3_img, d.w3_t, ws.racc, ws.rowsum, colsum, st_q};
-    if (tc_dconv) launch_tc_dconv(dc, st); else launch_ref_dconv(dc, st);
+    DconvParams dc{ws.p, st_p, d.g1, d.be1, d.w2b, d.w2f, d.c2f, d.a2, d.dil, M, T, B, d.w3_img, d.w3_t, ws.racc, ws.rowsum, colsum, st_q,
+                   nullptr};
+    long long*& s_dbg = septfa_dbg_ptr;   // bring-up timeline (SEPTFA_TIMELINE=1): block 5 of the persistent dconv kernel
+    if (i == 5 && getenv("SEPTFA_TIMELINE")) {
+      if (!s_dbg) { cudaMalloc(reinterpret_cast<void**>(&s_dbg), 8 * 256 * sizeof(long long)); }
+      cudaMemsetAsync(s_dbg, 0, 8 * 256 * sizeof(long long), st);
+      dc.dbg = s_dbg;
+    }
+    if (tc_dconv) { if (h->dconv_persistent) launch_dconv_persist(dc, st); else launch_tc_dconv(dc, st); }
+    else launch_ref_dconv(dc, st);
 
     prof_mark(h, SEPTFA_PROF_GATE, st);
     GateParams gp{st_q, tc_dconv ? d.s3_tc : d.s3_ref, d.c03, ws.rowsum, colsum, d.tf, M, T, B, ws.ra, ws.rb, ws.gf, ws.gt};
@@ -641,6 +658,24 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   prof_mark(h, SEPTFA_PROF_EXPORT, st);
   launch_export(ws.S, ws.logits, gate, ws.w, ws.dcg, B, T, reinterpret_cast<float2*>(est_stft), mask, nullptr, logits_out, st);
   prof_mark(h, -1, st);
+  if (getenv("SEPTFA_TIMELINE")) {
+    long long* dptr = nullptr;
+    // the static buffer lives in the block loop above; re-fetch it through a second static handle
+    dptr = septfa_dbg_ptr;
+    if (dptr) {
+      std::vector<long long> hbuf(8 * 256);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hbuf.data(), dptr, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long t0 = 0;
+      for (long long v : hbuf) if (v && (!t0 || v < t0)) t0 = v;
+      const char* names[8] = {"rawload", "wload", "mma_ready", "tr_start", "tr_end", "mma_wready", "tr_rawready", "epi"};
+      for (int r = 0; r < 8; ++r) {
+        fprintf(stderr, "TL %s:", names[r]);
+        for (int i2 = 0; i2 < 40; ++i2) if (hbuf[r * 256 + i2]) fprintf(stderr, " %lld", hbuf[r * 256 + i2] - t0);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   h->last_launches = g_launch_count;
   CUDA_TRY(h, cudaGetLastError());
   return 0;
@@ -684,8 +719,9 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
     }
   }
   const int64_t T = septfa_num_frames(L);
-  // Independent utterances: the batch is cut into chunks so that the H2D copy of chunk c+1 and the D2H copy
-  // of chunk c-1 overlap the kernels of chunk c (three streams, events between them).
+  // Independent utterances: the batch is cut into chunks that alternate between two stream "lanes". Each lane
+  // runs copy-in -> kernels -> copy-out in order on its own stream and workspace; the two lanes overlap each
+  // other's copies with kernels and keep the SMs filled while one lane's (smaller) grids drain.
   int nchunk = h->host_chunks > 0 ? h->host_chunks : (B >= 128 ? 4 : (B >= 32 ? 2 : 1));
   nchunk = std::min(std::min(nchunk, kHostChunksMax), B);
   const int Bc = (B + nchunk - 1) / nchunk;
@@ -709,6 +745,11 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
     CUDA_TRY(h, cudaMalloc(&h->hws, nws));
     h->hcap_ws = nws;
   }
+  if (nchunk > 1 && h->hcap_ws_b < nws) {
+    cudaFree(h->hws_b); h->hws_b = nullptr; h->hcap_ws_b = 0;
+    CUDA_TRY(h, cudaMalloc(&h->hws_b, nws));
+    h->hcap_ws_b = nws;
+  }
   // Page-locked caller buffers are copied directly; pageable ones go through the pinned staging buffers.
   auto is_pinned = [](const void* p) {
     cudaPointerAttributes at{};
@@ -726,23 +767,23 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
   for (int c = 0; c < nchunk; ++c) {
     const int b0 = c * Bc, bn = std::min(Bc, B - b0);
     if (bn <= 0) break;
+    const int lane = c & 1;
+    cudaStream_t ls = lane ? h->hstream_in : h->hstream;
+    void* lws = lane ? h->hws_b : h->hws;
+    const size_t lcap = lane ? h->hcap_ws_b : h->hcap_ws;
     const size_t xo = (size_t)b0 * L, oo = (size_t)b0 * 2 * L, vo = (size_t)b0 * 2 * T;
-    CUDA_TRY(h, cudaMemcpyAsync(h->hx_dev + xo, xsrc + xo, (size_t)bn * L * sizeof(float), cudaMemcpyHostToDevice, h->hstream_in));
-    CUDA_TRY(h, cudaEventRecord(h->hev_in[c], h->hstream_in));
-    CUDA_TRY(h, cudaStreamWaitEvent(h->hstream, h->hev_in[c], 0));
+    CUDA_TRY(h, cudaMemcpyAsync(h->hx_dev + xo, xsrc + xo, (size_t)bn * L * sizeof(float), cudaMemcpyHostToDevice, ls));
     if (int rc = septfa_forward(h, h->hx_dev + xo, bn, L, kw, h->hout_dev + oo, h->hvad_dev + vo, nullptr, nullptr, nullptr,
-                                nullptr, h->hws, h->hcap_ws, h->hstream))
+                                nullptr, lws, lcap, ls))
       return rc;
     launches += h->last_launches;
-    CUDA_TRY(h, cudaEventRecord(h->hev_done[c], h->hstream));
-    CUDA_TRY(h, cudaStreamWaitEvent(h->hstream_out, h->hev_done[c], 0));
-    CUDA_TRY(h, cudaMemcpyAsync(odst + oo, h->hout_dev + oo, (size_t)bn * 2 * L * sizeof(float), cudaMemcpyDeviceToHost, h->hstream_out));
+    CUDA_TRY(h, cudaMemcpyAsync(odst + oo, h->hout_dev + oo, (size_t)bn * 2 * L * sizeof(float), cudaMemcpyDeviceToHost, ls));
     if (want_vad)
-      CUDA_TRY(h, cudaMemcpyAsync(vdst + vo, h->hvad_dev + vo, (size_t)bn * 2 * T * sizeof(float), cudaMemcpyDeviceToHost, h->hstream_out));
+      CUDA_TRY(h, cudaMemcpyAsync(vdst + vo, h->hvad_dev + vo, (size_t)bn * 2 * T * sizeof(float), cudaMemcpyDeviceToHost, ls));
   }
   h->last_launches = launches;
-  CUDA_TRY(h, cudaStreamSynchronize(h->hstream_out));
   CUDA_TRY(h, cudaStreamSynchronize(h->hstream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->hstream_in));
   if (!pin_out) std::memcpy(out_wav_host, h->hout_pin, nout);
   if (want_vad && !pin_vad) std::memcpy(out_vad_host, h->hvad_pin, nvad);
   return 0;

@@ -48,7 +48,7 @@ __device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
 //   r*g = gt[row] * (racc * G1 + G2)      G1 = ra * gf, G2 = rb * gf             (TF-attention gates)
 //   v = y + r*g (recursive) | r*g (residual);  out = y + v * Av + Bv   (Av, Bv: ln_first / ln_modules)
 template <int MODE>
-__global__ void __launch_bounds__(256) k_resid(ResidParams p) {
+__global__ void __launch_bounds__(256, 4) k_resid(ResidParams p) {
   __shared__ float2 tab_y[kMaxSegs];   // stream norm
   __shared__ float2 tab_v[kMaxSegs];   // stats of v (MODE 1)
   __shared__ float acc_sm[kMaxSegs * 2];
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) k_resid(ResidParams p) {
     }
     cur = sg;
   };
-  constexpr int RS = 4;  // rows per warp step: 8 x 16 B loads in flight per lane
+  constexpr int RS = 2;  // rows per warp step: 4 x 16 B loads in flight per lane, 32 warps per SM
   for (int i = (warp >> 1) * RS; i < c.nrows; i += 4 * RS) {
     float4 w[RS], ra4[RS];
     float gt[RS];

@@ -113,6 +113,12 @@ class SeparationModel(nn.Module):
     def set_engine(self, engine):
         self.engine = int(engine)
 
+    def set_option(self, name, value):
+        """Forwarded to septfa_set_option (e.g. "dconv_persistent", "host_chunks")."""
+        if not hasattr(self, "_options"):
+            self._options = {}
+        self._options[name] = int(value)
+
     def set_profile(self, on: bool):
         """Per-kernel-class CUDA-event timing inside forward (septfa_set_option "profile")."""
         self._profile = bool(on)
@@ -143,6 +149,8 @@ class SeparationModel(nn.Module):
             h.version = self._weights_version
         _lib.check(h.ptr, h.lib.septfa_set_option(h.ptr, b"engine", self.engine))
         _lib.check(h.ptr, h.lib.septfa_set_option(h.ptr, b"profile", int(getattr(self, "_profile", False))))
+        for name, value in getattr(self, "_options", {}).items():
+            _lib.check(h.ptr, h.lib.septfa_set_option(h.ptr, name.encode(), int(value)))
         return h
 
     # -- forward ---------------------------------------------------------------------------
