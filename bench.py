@@ -154,6 +154,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8, help="mixtures of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="skip the optional exports (est/mask/spectrum/logits)")
+    ap.add_argument("--online-streams", type=int, default=1024, help="concurrent streams of the online leg (0 = skip)")
+    ap.add_argument("--online-hops", type=int, default=12)
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -239,6 +241,43 @@ def main():
     t_e2e = gather_max_time(time.perf_counter() - t0)
     assert out_h[0].shape == (B, 2, L)
 
+    # ---- online mode (BASELINE.json configs[2]): S concurrent streams, one hop-step = forward on the current 3 s
+    # windows + per-stream L1-PIT + reorder + append; latency per hop-step from CUDA events, windows resident
+    online = None
+    if a.online_streams > 0 and rank == 0:
+        import ctypes as C
+        from septfa_b200 import lib as _lib
+        S = a.online_streams
+        h = model._handle(dev)
+        st = C.c_void_p()
+        _lib.check(h.ptr, h.lib.septfa_online_create(h.ptr, S, C.byref(st)))
+        ws = torch.empty(h.lib.septfa_online_workspace_bytes(st), dtype=torch.uint8, device=dev)
+        win = torch.from_numpy(np.tile(synth.make_mixtures(16, 48000, 4321), ((S + 15) // 16, 1))[:S]).to(dev)
+        emitted = torch.empty((S, 2, 16000), dtype=torch.float32, device=dev)
+        perm = torch.empty((S, 2), dtype=torch.int32, device=dev)
+        ikw = _lib.InferKw.from_dict(kw)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        times = []
+        for i in range(a.online_hops + 3):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            _lib.check(h.ptr, h.lib.septfa_online_step(st, C.c_void_p(win.data_ptr()), C.byref(ikw), C.c_void_p(emitted.data_ptr()),
+                                                       C.c_void_p(perm.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), stream))
+            s1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                times.append(s0.elapsed_time(s1))
+        h.lib.septfa_online_destroy(st)
+        del ws
+        times.sort()
+        p50 = times[len(times) // 2]
+        p99 = times[min(len(times) - 1, int(0.99 * len(times)))]
+        online = {"streams": S, "hops_timed": len(times), "p50_ms_per_hop_step": p50, "p99_ms_per_hop_step": p99,
+                  "p50_ms_per_frame": p50 / 62.5, "p99_ms_per_frame": p99 / 62.5,
+                  "audio_s_per_s": S * 1.0 / (p50 * 1e-3),
+                  "note": "hop-step = forward on S x 3 s windows (T=188) + per-stream L1-PIT + reorder + emit 1 s; "
+                          "ms per frame = hop-step / 62.5 frames per hop (the reference has no per-frame entry point)"}
+
     if rank == 0:
         audio_s = world * B * L / FS * a.steps
         peak_tf, peak_hbm, peak_src = measured_peaks()
@@ -270,6 +309,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if online is not None:
+            line["online"] = online
         if world == 1 and not a.no_cpu_baseline:
             v, secs = cpu_reference_throughput(a.cpu_sample, L)
             line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",

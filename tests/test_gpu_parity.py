@@ -255,3 +255,42 @@ def test_full_size_batch_properties(cuda_models):
     assert np.abs(vad[137].cpu().numpy() - g["kw0_vad"][0]).max() < 1e-3
     # periodic batch -> identical results for identical utterances (up to the order of atomic sums)
     assert (out[0] - out[8]).abs().max().item() < 5e-4, (out[0] - out[8]).abs().max().item()
+
+
+def test_online_many_streams_equals_per_stream_runs(cuda_models):
+    """S streams as one batch == each stream driven on its own (per-stream permutation decisions)."""
+    from septfa_b200.online import OnlineSaving
+    args = synth.CONFIG_WITH_VAD
+    m = cuda_models(args, 41, 0)
+    kw = dict(synth.DEFAULT_INFERENCE_KW, filter_signals_by_smo_vad=True)
+    x = torch.from_numpy(synth.make_mixtures(6, 80000, 700)).cuda()   # 5 s -> 3 hops
+    o = OnlineSaving(m, "/tmp/septfa_online_test2")
+    o.num_save_samples = 0
+    batch = o.calc_online(x, "n", 0, dict(kw))
+    perms_batch = o.last_perms.cpu().numpy()
+    assert batch.shape == (6, 2, 48000) and perms_batch.shape == (3, 6, 2)
+    for s in (0, 5):
+        single = o.calc_online(x[s:s + 1].contiguous(), "n", 0, dict(kw))
+        # same permutation decisions, waveforms equal up to the fp16 batch-placement noise
+        assert np.array_equal(o.last_perms.cpu().numpy()[:, 0], perms_batch[:, s])
+        assert (single[0] - batch[s]).abs().max().item() < 5e-4
+
+
+def test_known_targets_driver_runs(cuda_models):
+    """OnlineSaving (known targets): intended behaviour of model/online_class_known_targets.py:85-154."""
+    from septfa_b200.online import OnlineSavingKnownTargets
+    from septfa_b200.pit import PITLossWrapper, calc_sisdr
+
+    def neg_sisdr(est, tgt):  # pairwise-point loss for PIT: mean over batch like the reference's loss functions
+        return -calc_sisdr(est, tgt).mean()
+    m = cuda_models(synth.CONFIG_WITH_VAD, 41, 0)
+    x = torch.from_numpy(synth.make_mixtures(1, 70000, 800)).cuda()
+    tgt = torch.stack([x * 0.6, x * 0.4], dim=1)
+    crit = PITLossWrapper(neg_sisdr, pit_from="pw_pt")
+    drv = OnlineSavingKnownTargets(m, "/tmp/septfa_online_test3", crit, criterion_similarity=PITLossWrapper(torch.nn.L1Loss(), pit_from="pw_pt"))
+    drv.num_save_samples = 0
+    sig = drv.calc_online(x, tgt, "n", 0, {})
+    # left-padded by 2 s (:92-93), then padded by the *remainder* (102000 - 48000) % 16000 = 6000 (:94-97, a quirk of
+    # the reference: it pads by the remainder, not up to the next hop) -> 108000 -> floor(60000 / 16000) + 1 = 4 hops
+    assert sig.shape == (1, 2, 4 * 16000)
+    assert len(drv.online_sisdr) == 1 and len(drv.reference_sisdr) == 1 and np.isfinite(drv.online_sisdr[0])
