@@ -100,6 +100,11 @@ def cpu_reference_throughput(n_mix, length, repeats=1):
     import numpy as np
     from oracle import septfa_oracle as O
     from septfa_b200 import synth
+    try:  # torchrun exports OMP_NUM_THREADS=1: give the BLAS behind numpy all host cores explicitly
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(os.cpu_count())
+    except Exception:  # noqa: BLE001
+        pass
     args = synth.CONFIG_WITH_VAD
     W = O.OracleWeights(synth.make_state_dict_numpy(args, 0), args, np.float32)
     x = synth.make_mixtures(n_mix, length, 1234)
@@ -158,6 +163,11 @@ def main():
     ap.add_argument("--online-hops", type=int, default=12)
     a = ap.parse_args()
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout and would precede the JSON line
+    if a.impl == "reference":
+        for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[v] = str(os.cpu_count())  # torchrun forces OMP_NUM_THREADS=1
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -2,15 +2,18 @@
 //   q = PReLU(depthwise dilated k3 conv(GroupNorm reg1(p)))      (model/model.py:136/142)
 //   racc = (W3 diag(gamma2)) q                                    (model/model.py:144, reg2 folded)
 // One CTA per SM loops over 128-frame tiles. Global-memory latency is taken off the compute warps:
-//   warps 4,15   raw loaders: cp.async (16 B per lane-op) of the fp32 p tile (+/-4 halo rows) into a 4-stage
-//                             shared-memory ring, completion on mbarriers (cp.async.mbarrier.arrive.noinc)
+//   warp  4      raw loader : one 2-D TMA tensor load (cp.async.bulk.tensor) per K-chunk of the fp32 p tile
+//                             (136 rows incl. +/-4 halo x 32 channels, out-of-range rows zero-filled) into a
+//                             4-stage shared-memory ring, mbarrier complete_tx
 //   warp 14      W loader   : cp.async.bulk of the pre-swizzled fp16 weight image, 2 stages
 //   warps 6-13   transform  : raw ring -> GroupNorm/depthwise/PReLU -> fp16 -> 128B-swizzled A operand stage,
 //                             statistics of q
 //   warp  5      MMA        : tcgen05.mma 128x256x16 (fp16 x fp16 -> fp32) into a DOUBLE-BUFFERED TMEM accumulator
-//   warps 0-3    epilogue   : tcgen05.ld -> smem staging -> coalesced stores of the raw accumulators, row sums,
-//                             per-utterance column sums; overlaps the next tile's loads / transform / MMA
+//   warps 0-3    epilogue   : tcgen05.ld -> 128B-swizzled smem staging -> 2-D TMA tensor stores of the raw
+//                             accumulators, row sums, per-utterance column sums; overlaps the next tile
 #include <cstdlib>
+#include <cuda.h>            // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
+#include <cudaTypedefs.h>
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -29,16 +32,14 @@ constexpr int kAStage = kTileM * 128;          // 16 KB: 128 rows x 64 halves
 constexpr int kWStage = 256 * 128;             // 32 KB: 256 rows x 64 halves
 constexpr int kOpStages = 2;
 constexpr int kNCH = 8;                        // K = 512 = 8 chunks of 64
-constexpr int kStgPitch = 36;
-constexpr int kThreadsP = 512;                 // 16 warps
-constexpr int kDconvW = 512 * 16 + 512 * 4;
+constexpr int kThreadsP = 480;                 // 15 warps
+constexpr int kStgBytes = 32 * 128;               // one [32 rows x 32 cols] fp32 box, 128B-swizzled
 
 constexpr int kOffA = 0;
 constexpr int kOffW = kOffA + kOpStages * kAStage;
 constexpr int kOffRaw = kOffW + kOpStages * kWStage;
 constexpr int kOffStg = kOffRaw + kRawStages * kRawBytes;
-constexpr int kOffWts = kOffStg + 4 * 32 * kStgPitch * 4;
-constexpr int kOffAux = kOffWts + kDconvW;
+constexpr int kOffAux = kOffStg + 4 * 2 * kStgBytes;   // 4 epilogue warps x 2 staging buffers
 constexpr int kAuxBytesP = 4096;
 constexpr int kSmemP = kOffAux + kAuxBytesP + 1024;
 
@@ -46,9 +47,31 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Frames within `dil` of an utterance edge: taps outside the utterance are zero padding of the *normalised* signal
+// (model/model.py:111-114 zero-pads the GroupNorm output). Rare (2*dil of T frames): kept out of line.
+__device__ __forceinline__ void edge_rows(const DconvParams& p, int g0, bool okm, bool okp, float2 mr, const float (&vm)[4],
+                                       const float (&vc)[4], const float (&vp)[4], float (&q)[8]) {
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(p.g1 + g0));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(p.be1 + g0));
+  const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float hm = okm ? ((vm[c] - mr.x) * mr.y) * gam[c] + bet[c] : 0.f;
+    const float hc = ((vc[c] - mr.x) * mr.y) * gam[c] + bet[c];
+    const float hp = okp ? ((vp[c] - mr.x) * mr.y) * gam[c] + bet[c] : 0.f;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float4 w = __ldg(p.w2b + 2 * (g0 + c) + e);
+      q[2 * c + e] = prelu(w.w + w.x * hm + w.y * hc + w.z * hp, p.slope2);
+    }
+  }
+}
+
 #define TL(role, idx) do { if (p.dbg != nullptr && blockIdx.x == 1 && lane == 0 && (idx) < 256) p.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(kThreadsP, 1) k_dconv_persist(DconvParams p, int ntiles) {
+__global__ void __launch_bounds__(kThreadsP, 1) k_dconv_persist(DconvParams p, int ntiles,
+                                                                const __grid_constant__ CUtensorMap tm_p,
+                                                                const __grid_constant__ CUtensorMap tm_racc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffAux);
@@ -63,13 +86,11 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_dconv_persist(DconvParams p, i
   float2* tab_a = reinterpret_cast<float2*>(bars + 20);          // [kMaxSegs] mean/rstd of p per segment
   float* seg_acc = reinterpret_cast<float*>(tab_a + kMaxSegs);   // [2*kMaxSegs] slow-path statistics
   float* slots = seg_acc + 2 * kMaxSegs;                         // [8][4]
-  float4* w2f_s = reinterpret_cast<float4*>(smem + kOffWts);
-  float* c2f_s = reinterpret_cast<float*>(w2f_s + kH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full + s, 64); mbar_init(raw_empty + s, 8); }
+    for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, 8); }
     for (int s = 0; s < kOpStages; ++s) {
       mbar_init(a_full + s, 8);
       mbar_init(w_full + s, 1);
@@ -80,42 +101,32 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_dconv_persist(DconvParams p, i
     fence_mbar_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 512);
-  for (int i = threadIdx.x; i < kH; i += kThreadsP) {
-    const int jj = i >> 6, cc = (i >> 3) & 7, oo = i & 7, d = (jj * 8 + oo) * 8 + cc;  // [chunk][output][lane group]
-    w2f_s[d] = __ldg(p.w2f + i);
-    c2f_s[d] = __ldg(p.c2f + i);
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int nmine = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
 
-  if (warp == 4 || warp == 15) {
-    // ------------------------------------------------------------ raw loaders: cp.async 16 B per lane-op, completion on
-    // the stage's mbarrier via cp.async.mbarrier.arrive.noinc (64 arrivals = 2 warps x 32 lanes per phase)
-    const int lid = (warp == 4 ? 0 : 32) + lane;   // 0..63
-    for (int k = 0; k < nmine; ++k) {
-      const int r0 = ((int)blockIdx.x + k * (int)gridDim.x) * kTileM;
-      const int lo = max(r0 - kHalo, 0), hi = min(r0 + kTileM + kHalo, p.M);  // valid global rows [lo, hi)
-      for (int j = 0; j < kNCH; ++j) {
-        const int g = k * kNCH + j, s = g % kRawStages, u = g / kRawStages;
-        if (u > 0) mbar_wait(raw_empty + s, (u - 1) & 1, 100 + j);
-        const uint32_t dst = smem_u32(smem + kOffRaw + s * kRawBytes);
-        const float* src = p.p_in + j * 32;
-        // op index i -> (raw row i / 8, 16-byte piece i % 8); 8 consecutive lanes fetch one 128 B row slice
-        for (int i = lid; i < kRawRows * 8; i += 64) {
-          const int rr = i >> 3, piece = i & 7;
-          const int row = r0 - kHalo + rr;
-          if (row >= lo && row < hi)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + rr * 128 + piece * 16),
-                         "l"(src + (int64_t)row * kC + piece * 4)
-                         : "memory");
+  if (warp == 4) {
+    // ------------------------------------------------------------ raw loader (one elected lane, 2-D TMA loads)
+    if (lane == 0) {
+      for (int k = 0; k < nmine; ++k) {
+        const int r0 = ((int)blockIdx.x + k * (int)gridDim.x) * kTileM;
+        for (int j = 0; j < kNCH; ++j) {
+          const int g = k * kNCH + j, s = g % kRawStages, u = g / kRawStages;
+          if (u > 0) mbar_wait(raw_empty + s, (u - 1) & 1, 100 + j);
+          mbar_expect_tx(raw_full + s, kRawBytes);
+          // box = 32 channels x 136 rows at (channel 32 j, row r0 - 4); rows < 0 or >= M arrive as zeros
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                  smem_u32(smem + kOffRaw + s * kRawBytes)),
+              "l"(reinterpret_cast<uint64_t>(&tm_p)), "r"(j * 32), "r"(r0 - kHalo), "r"(smem_u32(raw_full + s))
+              : "memory");
+          TL(0, g);
         }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(raw_full + s)) : "memory");
-        if (warp == 4) TL(0, g);
       }
     }
+    __syncwarp();
   } else if (warp == 14) {
     // ------------------------------------------------------------ weight loader
     if (lane == 0) {
@@ -180,54 +191,62 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_dconv_persist(DconvParams p, i
         if (tw == 0) TL(3, g);
         const uint8_t* raw = smem + kOffRaw + rs * kRawBytes;
         uint8_t* a_tile = smem + kOffA + as * kAStage;
-        const float4* wf = w2f_s + j * 64 + c8;
-        const float* cf = c2f_s + j * 64 + c8;
         const int g0 = j * 32 + c8 * 4;
+        // folded taps of this lane's 8 output channels, once per chunk (L1-resident, 10 KB per block)
+        float4 wf[8];
+        float cf[8];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rl = it * 32 + tw * 4 + rg;
-          float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (rl < nrows) {
+        for (int o = 0; o < 8; ++o) wf[o] = __ldg(p.w2f + 2 * g0 + o);
+        {
+          const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.c2f + 2 * g0));
+          const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.c2f + 2 * g0 + 4));
+          cf[0] = c0.x; cf[1] = c0.y; cf[2] = c0.z; cf[3] = c0.w; cf[4] = c1.x; cf[5] = c1.y; cf[6] = c1.z; cf[7] = c1.w;
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          // two row steps in flight: independent LDS / FMA chains for the scheduler to interleave
+          float4 xm[2], xc[2], xp[2];
+          int flg[2];
+#pragma unroll
+          for (int i2 = 0; i2 < 2; ++i2) {
+            const int rl = (half * 2 + i2) * 32 + tw * 4 + rg;
             const int row = r0 + rl;
             const int sg = smap.seg(row);
             const int t = smap.frame(row, sg);
-            const bool okm = t - p.dil >= 0, okp = t + p.dil < p.T;
-            const float2 mr = tab_a[sg];
-            const float4 xc = *reinterpret_cast<const float4*>(raw + (rl + kHalo) * 128 + c8 * 16);
-            float4 xm = make_float4(0.f, 0.f, 0.f, 0.f), xp = xm;
-            if (okm) xm = *reinterpret_cast<const float4*>(raw + (rl + kHalo - p.dil) * 128 + c8 * 16);
-            if (okp) xp = *reinterpret_cast<const float4*>(raw + (rl + kHalo + p.dil) * 128 + c8 * 16);
-            const float vm[4] = {xm.x, xm.y, xm.z, xm.w}, vc[4] = {xc.x, xc.y, xc.z, xc.w}, vp[4] = {xp.x, xp.y, xp.z, xp.w};
-            if (okm && okp) {
-              const float nmu = -mr.x;
-#pragma unroll
-              for (int o = 0; o < 8; ++o) {
-                const float4 w = wf[o * 8];
-                const float conv = fmaf(w.z, vp[o >> 1], fmaf(w.y, vc[o >> 1], w.x * vm[o >> 1]));
-                q[o] = prelu(fmaf(mr.y, fmaf(nmu, w.w, conv), cf[o * 8]), p.slope2);
-              }
-            } else {
-              // frames within `dil` of an utterance edge: taps outside are zero padding of the *normalised* signal
-              const float4 ga = __ldg(reinterpret_cast<const float4*>(p.g1 + g0));
-              const float4 be = __ldg(reinterpret_cast<const float4*>(p.be1 + g0));
-              const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float hm = okm ? ((vm[c] - mr.x) * mr.y) * gam[c] + bet[c] : 0.f;
-                const float hc = ((vc[c] - mr.x) * mr.y) * gam[c] + bet[c];
-                const float hp = okp ? ((vp[c] - mr.x) * mr.y) * gam[c] + bet[c] : 0.f;
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const float4 w = __ldg(p.w2b + 2 * (g0 + c) + e);
-                  q[2 * c + e] = prelu(w.w + w.x * hm + w.y * hc + w.z * hp, p.slope2);
-                }
-              }
-            }
-            qstat.add(sg, q, seg_acc);
+            flg[i2] = sg | (t - p.dil >= 0 ? 256 : 0) | (t + p.dil < p.T ? 512 : 0) | (rl < nrows ? 1024 : 0);
+            const uint8_t* base = raw + (rl + kHalo) * 128 + c8 * 16;
+            xc[i2] = *reinterpret_cast<const float4*>(base);
+            xm[i2] = *reinterpret_cast<const float4*>(base - p.dil * 128);
+            xp[i2] = *reinterpret_cast<const float4*>(base + p.dil * 128);
           }
-          const uint4 pk = make_uint4(pack_half2(q[0], q[1]), pack_half2(q[2], q[3]), pack_half2(q[4], q[5]),
-                                      pack_half2(q[6], q[7]));
-          *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
+#pragma unroll
+          for (int i2 = 0; i2 < 2; ++i2) {
+            const int rl = (half * 2 + i2) * 32 + tw * 4 + rg;
+            const int sg = flg[i2] & 255;
+            const bool okm = flg[i2] & 256, okp = flg[i2] & 512, valid = flg[i2] & 1024;
+            const float2 mr = tab_a[valid ? sg : 0];
+            const float vm[4] = {xm[i2].x, xm[i2].y, xm[i2].z, xm[i2].w};
+            const float vc[4] = {xc[i2].x, xc[i2].y, xc[i2].z, xc[i2].w};
+            const float vp[4] = {xp[i2].x, xp[i2].y, xp[i2].z, xp[i2].w};
+            float q[8];
+            const float nmu = -mr.x;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+              const float4 w = wf[o];
+              const float conv = fmaf(w.z, vp[o >> 1], fmaf(w.y, vc[o >> 1], w.x * vm[o >> 1]));
+              q[o] = prelu(fmaf(mr.y, fmaf(nmu, w.w, conv), cf[o]), p.slope2);
+            }
+            if (valid && !(okm && okp)) edge_rows(p, g0, okm, okp, mr, vm, vc, vp, q);
+            if (valid) {
+              qstat.add(sg, q, seg_acc);
+            } else {
+#pragma unroll
+              for (int o = 0; o < 8; ++o) q[o] = 0.f;
+            }
+            const uint4 pk = make_uint4(pack_half2(q[0], q[1]), pack_half2(q[2], q[3]), pack_half2(q[4], q[5]),
+                                        pack_half2(q[6], q[7]));
+            *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -251,34 +270,28 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_dconv_persist(DconvParams p, i
     }
   } else if (warp < 4) {
     // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp)
-    float* stg = reinterpret_cast<float*>(smem + kOffStg) + warp * (32 * kStgPitch);
+    uint8_t* stg_base = smem + kOffStg + warp * (2 * kStgBytes);   // two 4 KB boxes, 1024-byte aligned
+    int sbuf = 0;
     for (int k = 0; k < nmine; ++k) {
       const int r0 = ((int)blockIdx.x + k * (int)gridDim.x) * kTileM;
       const int nrows = min(kTileM, p.M - r0);
       const SegMap smap(r0, p.T);
       const int nseg = (r0 + nrows - 1) / p.T - smap.b_first + 1;
       const int ab = k & 1, au = k >> 1;
+      // warp-uniform row masks of this warp's 32 rows: valid / 2nd utterance of the tile / 3rd+ utterance (T < 128 only)
+      uint32_t m_valid, m_seg1, m_slow;
+      {
+        const int rl = warp * 32 + lane;
+        const int sg = rl < nrows ? smap.seg(r0 + rl) : -1;
+        m_valid = __ballot_sync(0xffffffffu, sg >= 0);
+        m_seg1 = __ballot_sync(0xffffffffu, sg == 1);
+        m_slow = __ballot_sync(0xffffffffu, sg >= 2);
+      }
       mbar_wait(acc_full + ab, au & 1, 500);
       tc_fence_after();
       if (warp == 0) TL(7, 2 * k);
       const int my_rl = warp * 32 + lane;
       float rowacc = 0.f;
-      // this lane copies out rows i = it*4 + lane/8 (it = 0..7) of the warp's 32 rows, 4 columns each:
-      // per-tile bit masks replace the per-row segment lookups inside the column loop
-      const int c4 = (lane & 7) * 4, rsub = lane >> 3;
-      uint32_t m_valid = 0, m_seg1 = 0, m_slow = 0;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rl = warp * 32 + it * 4 + rsub;
-        if (rl < nrows) {
-          const int sg = smap.seg(r0 + rl);
-          m_valid |= 1u << it;
-          if (sg == 1) m_seg1 |= 1u << it;
-          if (sg >= 2) m_slow |= 1u << it;
-        }
-      }
-      const bool any_slow = __any_sync(0xffffffffu, m_slow != 0);  // only when T < 128
-      float* orow = p.racc + (int64_t)(r0 + warp * 32 + rsub) * kC + c4;
       for (int cc = 0; cc < 8; ++cc) {
         const int col0 = cc * 32;
         float v[32];
@@ -289,55 +302,58 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_dconv_persist(DconvParams p, i
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty + ab);
         }
+        {
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) rowacc += v[i];
+          for (int i = 0; i < 32; ++i) s4[i & 3] += v[i];
+          rowacc += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        }
+        // the TMA store that last read this staging buffer (two chunks ago) must have finished reading it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
+        uint8_t* stg = stg_base + sbuf * kStgBytes;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(stg + lane * kStgPitch + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 8; ++i)   // row = lane, 16-byte chunk i at the 128B-swizzled position
+          *reinterpret_cast<float4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        fence_proxy_async();
         __syncwarp();
-        float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), c1 = ca;   // column sums: all rows / rows of the 2nd utterance
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if ((m_valid >> it) & 1u) {
-            const float4 o = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * kStgPitch + c4);
-            *reinterpret_cast<float4*>(orow + (int64_t)it * 4 * kC + col0) = o;
-            if (!((m_slow >> it) & 1u)) { ca.x += o.x; ca.y += o.y; ca.z += o.z; ca.w += o.w; }
-            if ((m_seg1 >> it) & 1u) { c1.x += o.x; c1.y += o.y; c1.z += o.z; c1.w += o.w; }
-            if (any_slow && ((m_slow >> it) & 1u)) {
-              const int sg = smap.seg(r0 + warp * 32 + it * 4 + rsub);
-              double* dst = p.colsum + (size_t)(smap.b_first + sg) * kC + col0 + c4;
-              atomicAdd(dst, (double)o.x); atomicAdd(dst + 1, (double)o.y);
-              atomicAdd(dst + 2, (double)o.z); atomicAdd(dst + 3, (double)o.w);
+        if (lane == 0) {
+          // [32 rows x 32 cols] box at (col0, r0 + 32 warp); rows >= M are clipped by the tensor map
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tm_racc)),
+                       "r"(smem_u32(stg)), "r"(col0), "r"(r0 + warp * 32)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        // column sums from the staged box: lane = column
+        float ca = 0.f, c1 = 0.f;
+        const int cch = lane >> 2, cw = (lane & 3) * 4;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const float x = *reinterpret_cast<const float*>(stg + i * 128 + ((cch ^ (i & 7)) << 4) + cw);
+          if ((m_valid >> i) & 1u) {
+            if (!((m_slow >> i) & 1u)) ca += x;
+            if ((m_seg1 >> i) & 1u) c1 += x;
+            if ((m_slow >> i) & 1u) {
+              const int sg = smap.seg(r0 + warp * 32 + i);
+              atomicAdd(p.colsum + (size_t)(smap.b_first + sg) * kC + col0 + lane, (double)x);
             }
           }
         }
-#pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
-          ca.x += __shfl_xor_sync(0xffffffffu, ca.x, o); ca.y += __shfl_xor_sync(0xffffffffu, ca.y, o);
-          ca.z += __shfl_xor_sync(0xffffffffu, ca.z, o); ca.w += __shfl_xor_sync(0xffffffffu, ca.w, o);
+        {
+          double* dst = p.colsum + (size_t)smap.b_first * kC + col0 + lane;
+          if (m_valid & ~m_seg1 & ~m_slow) atomicAdd(dst, (double)(ca - c1));
+          if (m_seg1) atomicAdd(dst + kC, (double)c1);
         }
-        if (nseg > 1) {
-#pragma unroll
-          for (int o = 8; o <= 16; o <<= 1) {
-            c1.x += __shfl_xor_sync(0xffffffffu, c1.x, o); c1.y += __shfl_xor_sync(0xffffffffu, c1.y, o);
-            c1.z += __shfl_xor_sync(0xffffffffu, c1.z, o); c1.w += __shfl_xor_sync(0xffffffffu, c1.w, o);
-          }
-        }
-        if (lane < 8) {
-          double* dst = p.colsum + (size_t)smap.b_first * kC + col0 + c4;
-          atomicAdd(dst, (double)(ca.x - c1.x)); atomicAdd(dst + 1, (double)(ca.y - c1.y));
-          atomicAdd(dst + 2, (double)(ca.z - c1.z)); atomicAdd(dst + 3, (double)(ca.w - c1.w));
-          if (nseg > 1) {
-            dst += kC;
-            atomicAdd(dst, (double)c1.x); atomicAdd(dst + 1, (double)c1.y);
-            atomicAdd(dst + 2, (double)c1.z); atomicAdd(dst + 3, (double)c1.w);
-          }
-        }
+        sbuf ^= 1;
       }
       if (my_rl < nrows) p.rowsum[r0 + my_rl] = rowacc;
       if (warp == 0) TL(7, 2 * k + 1);
     }
+    // shared memory must stay valid until the last tensor stores have read it
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -346,7 +362,19 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_dconv_persist(DconvParams p, i
 }
 
 int g_num_sms = 0;
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
+// 2-D fp32 row-major [rows, cols] tensor, box [box_rows, box_cols].
+bool make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
+               CUtensorMapSwizzle swz) {
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * sizeof(float)};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 }  // namespace
 
 cudaError_t dconv_persist_setup() {
@@ -355,13 +383,32 @@ cudaError_t dconv_persist_setup() {
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess) return e;
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorNotSupported;
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   return cudaFuncSetAttribute(k_dconv_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemP);
 }
 
 void launch_dconv_persist(const DconvParams& p, cudaStream_t st) {
   const int ntiles = (p.M + kTileM - 1) / kTileM;
   const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
-  k_dconv_persist<<<grid, kThreadsP, kSmemP, st>>>(p, ntiles);
+  // tensor maps of the input / output activation buffers (same buffers for every block of a forward: cached)
+  static CUtensorMap tm_p, tm_racc;
+  static const void* c_p = nullptr;
+  static const void* c_r = nullptr;
+  static int c_m = -1;
+  if (c_p != p.p_in || c_r != p.racc || c_m != p.M) {
+    if (!make_tmap(&tm_p, p.p_in, (uint64_t)p.M, kC, kRawRows, 32, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+        !make_tmap(&tm_racc, p.racc, (uint64_t)p.M, kC, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) {
+      fprintf(stderr, "septfa: cuTensorMapEncodeTiled failed\n");
+      return;
+    }
+    c_p = p.p_in; c_r = p.racc; c_m = p.M;
+  }
+  k_dconv_persist<<<grid, kThreadsP, kSmemP, st>>>(p, ntiles, tm_p, tm_racc);
   ++g_launch_count;
 }
 

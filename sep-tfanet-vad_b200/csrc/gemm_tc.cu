@@ -30,6 +30,7 @@ constexpr int kStgPitch = 36;               // floats per staged row (32 + 4 pad
 struct TcParams {
   int M, T, B;
   const __half* w_img;
+  const __half* w_img_lo;   // MODE 2: low part of the fp16 split of the weights
   const float* in;
   StreamNorm norm;
   // MODE 2 prologue
@@ -52,7 +53,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   constexpr int KDIM = (MODE == 1) ? 512 : 256;
   constexpr int NCH = KDIM / 64;
   constexpr int WCH = NT * 128;
-  constexpr int STAGE = kAChunkBytes + WCH;
+  // MODE 2 runs a 3-pass fp16 split (A = A_hi + A_lo, W = W_hi + W_lo; A_hi W_hi + A_lo W_hi + A_hi W_lo): the output
+  // conv feeds the VAD head directly and dominated its error budget, and costs < 3 % of the FLOPs.
+  constexpr int NSPLIT = (MODE == 2) ? 2 : 1;
+  constexpr int STAGE = NSPLIT * (kAChunkBytes + WCH);   // [A_hi][A_lo][W_hi][W_lo]
+  constexpr int OFF_W = NSPLIT * kAChunkBytes;
   constexpr uint32_t IDESC = make_idesc_f16(kTileM, NT);
 
   extern __shared__ uint8_t smem_raw[];
@@ -79,6 +84,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   const int b_first = smap.b_first;
   const int nseg = (r0 + nrows - 1) / p.T - b_first + 1;
   const __half* w_img = p.w_img + (size_t)blockIdx.y * NCH * (WCH / 2);
+  const __half* w_img_lo = (NSPLIT == 2) ? p.w_img_lo + (size_t)blockIdx.y * NCH * (WCH / 2) : nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -122,9 +128,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
       for (int j = 0; j < NCH; ++j) {
         const int s = j % kStages, u = j / kStages;
         if (u > 0) mbar_wait(empty + s, (u - 1) & 1, 100 + j);
-        mbar_expect_tx(full_w + s, WCH);
-        bulk_copy_g2s(smem + s * STAGE + kAChunkBytes, reinterpret_cast<const uint8_t*>(w_img) + (size_t)j * WCH, WCH,
-                      full_w + s);
+        mbar_expect_tx(full_w + s, NSPLIT * WCH);
+        bulk_copy_g2s(smem + s * STAGE + OFF_W, reinterpret_cast<const uint8_t*>(w_img) + (size_t)j * WCH, WCH, full_w + s);
+        if (NSPLIT == 2)
+          bulk_copy_g2s(smem + s * STAGE + OFF_W + WCH, reinterpret_cast<const uint8_t*>(w_img_lo) + (size_t)j * WCH, WCH,
+                        full_w + s);
       }
     }
     __syncwarp();
@@ -137,10 +145,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
         mbar_wait(full_a + s, u & 1, 300 + j);
         tc_fence_after();
         const uint64_t a_desc = make_sw128_desc(smem_u32(smem + s * STAGE));
-        const uint64_t b_desc = make_sw128_desc(smem_u32(smem + s * STAGE + kAChunkBytes));
+        const uint64_t b_desc = make_sw128_desc(smem_u32(smem + s * STAGE + OFF_W));
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // UMMA_K = 16 halves = 32 B -> +2 in the (addr >> 4) field
+        for (int kk = 0; kk < 4; ++kk) {  // UMMA_K = 16 halves = 32 B -> +2 in the (addr >> 4) field
           umma_f16(tmem_base, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESC, (j | kk) != 0);
+          if (NSPLIT == 2) {
+            const uint64_t a_lo = make_sw128_desc(smem_u32(smem + s * STAGE + kAChunkBytes));
+            const uint64_t b_lo = make_sw128_desc(smem_u32(smem + s * STAGE + OFF_W + WCH));
+            umma_f16(tmem_base, a_lo + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESC, 1u);
+            umma_f16(tmem_base, a_desc + (uint64_t)(kk * 2), b_lo + (uint64_t)(kk * 2), IDESC, 1u);
+          }
+        }
         umma_commit(empty + s);
       }
       umma_commit(acc_full);
@@ -204,6 +219,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
           const uint4 pk = make_uint4(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]),
                                       pack_half2(y[6], y[7]));
           *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
+          if (NSPLIT == 2) {
+            float r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = y[i] - __half2float(__float2half_rn(y[i]));   // exact residual in fp32
+            const uint4 pl = make_uint4(pack_half2(r[0], r[1]), pack_half2(r[2], r[3]), pack_half2(r[4], r[5]),
+                                        pack_half2(r[6], r[7]));
+            *reinterpret_cast<uint4*>(a_tile + kAChunkBytes + sw128_offset(rl, c8)) = pl;
+          }
         }
       } else {
         // q channels 64j + 8*c8 .. +7  <-  in-channels g0 .. g0+3 (out-channel o reads in-channel o/2).
@@ -378,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
 template <int MODE>
 void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
   constexpr int NT = (MODE == 2) ? 192 : 256;
-  constexpr int smem = kStages * (kAChunkBytes + NT * 128) + kAuxBytes + 1024 + (MODE == 1 ? kDconvWBytes : 0);
+  constexpr int smem = kStages * (MODE == 2 ? 2 : 1) * (kAChunkBytes + NT * 128) + kAuxBytes + 1024 + (MODE == 1 ? kDconvWBytes : 0);
   dim3 grid((p.M + kTileM - 1) / kTileM, ntiles_n);
   k_tc_gemm<MODE><<<grid, kThreads, smem, st>>>(p);
   ++g_launch_count;
@@ -399,7 +422,7 @@ cudaError_t tc_gemm_setup() {
                            kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024 + kDconvWBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_tc_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kStages * (kAChunkBytes + 192 * 128) + kAuxBytes + 1024);
+                           kStages * 2 * (kAChunkBytes + 192 * 128) + kAuxBytes + 1024);
   if (e == cudaSuccess && getenv("SEPTFA_DEBUG")) {
     int o0 = 0, o1 = 0, o2 = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, k_tc_gemm<0>, kThreads, kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024);
@@ -436,7 +459,7 @@ void launch_tc_dconv(const DconvParams& c, cudaStream_t st) {
 void launch_tc_outconv(const OutConvParams& c, cudaStream_t st) {
   TcParams p{};
   p.M = c.M; p.T = c.T; p.B = c.B;
-  p.w_img = c.w_img; p.in = c.w_in; p.norm = c.norm;
+  p.w_img = c.w_img; p.w_img_lo = c.w_img_lo; p.in = c.w_in; p.norm = c.norm;
   p.slope_o = c.slope_o; p.st_o = c.st_o; p.g_o = c.g_o; p.b_o = c.b_o;
   p.bias = c.bias;
   p.out = c.logits; p.out_stride = kLogitStride;

@@ -64,7 +64,8 @@ struct OutConvParams {
   const float* b_o;
   int M, T, B;
   const float* bias;   // [576] (zero padded)
-  const __half* w_img; // 3 N-tiles x 4 K-chunks x [192 rows x 128 B]
+  const __half* w_img; // 3 N-tiles x 4 K-chunks x [192 rows x 128 B]: high part of the fp16 split
+  const __half* w_img_lo; // low part: fp16(w - fp16(w))
   const float* w_t;    // fp32 [256 k][576 n]
   float* logits;       // [M,576]
 };

@@ -50,7 +50,7 @@ struct septfa_handle {
   std::vector<DevBlock> blocks;
   const float* ln_g = nullptr; const float* ln_b = nullptr;
   float out_a = 0.f; const float* out_g = nullptr; const float* out_be = nullptr;
-  const __half* out_img = nullptr; const float* out_wt = nullptr; const float* out_bias = nullptr;
+  const __half* out_img = nullptr; const __half* out_img_lo = nullptr; const float* out_wt = nullptr; const float* out_bias = nullptr;
   const float* vad_w1t = nullptr; float vad_b1[4]{}; float vad_a = 0.f; float vad_g[4]{}; float vad_be[4]{};
   float vad_w2[12]{}; float vad_b2 = 0.f;
   float act_k[9]{}; float act_b = 0.f; float act_a = 0.f;
@@ -311,6 +311,7 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
   h->nblk = c.layer * c.stack;
   h->ln_mode = c.apply_recursive_ln ? LN_RECURSIVE : (c.apply_residual_ln ? LN_RESIDUAL : LN_NONE);  // model.py:347-352
   build_keys(h);
+  if (const char* e = getenv("SEPTFA_DCONV_PERSISTENT")) h->dconv_persistent = atoi(e) ? 1 : 0;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, "cudaSetDevice failed"); }
   cudaError_t e = tc_gemm_setup();
   if (e == cudaSuccess) e = dconv_persist_setup();
@@ -517,12 +518,15 @@ int septfa_commit_weights(septfa_handle* h) {
     h->out_a = T_(h, "TCN.output.0.weight")[0];
     const auto w = fold_wn(T_(h, "TCN.output.2.weight_g"), T_(h, "TCN.output.2.weight_v"), kBins * 2);
     std::vector<float> wt((size_t)kC * kLogitStride, 0.f), bias(kLogitStride, 0.f);
+    std::vector<double> w_lo(w.size());   // low part of the 2-term fp16 split used by the tcgen05 output conv
+    for (size_t i = 0; i < w.size(); ++i) w_lo[i] = (double)((float)w[i] - __half2float(__float2half((float)w[i])));
     for (int n = 0; n < kBins * 2; ++n) {
       bias[n] = T_(h, "TCN.output.2.bias")[n];
       for (int k = 0; k < kC; ++k) wt[(size_t)k * kLogitStride + n] = (float)w[(size_t)n * kC + k];
     }
     if (upload(h, T_(h, "TCN.output.1.weight"), &h->out_g) || upload(h, T_(h, "TCN.output.1.bias"), &h->out_be) ||
-        upload(h, pack_image(w, kBins * 2, kC, 3, 192), &h->out_img) || upload(h, wt, &h->out_wt) ||
+        upload(h, pack_image(w, kBins * 2, kC, 3, 192), &h->out_img) || upload(h, pack_image(w_lo, kBins * 2, kC, 3, 192), &h->out_img_lo) ||
+        upload(h, wt, &h->out_wt) ||
         upload(h, bias, &h->out_bias))
       return SEPTFA_E_CUDA;
   }
@@ -633,7 +637,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   // output layer: PReLU -> GroupNorm -> conv (model.py:322-325,357)
   prof_mark(h, SEPTFA_PROF_OUTCONV, st);
   launch_out_stats(ws.w, norm, h->out_a, M, T, ws.st_o, st);
-  OutConvParams oc{ws.w, norm, h->out_a, ws.st_o, h->out_g, h->out_be, M, T, B, h->out_bias, h->out_img, h->out_wt, ws.logits};
+  OutConvParams oc{ws.w, norm, h->out_a, ws.st_o, h->out_g, h->out_be, M, T, B, h->out_bias, h->out_img, h->out_img_lo, h->out_wt, ws.logits};
   if (tc_out) launch_tc_outconv(oc, st); else launch_ref_outconv(oc, st);
 
   prof_mark(h, SEPTFA_PROF_VAD, st);
