@@ -31,7 +31,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a and link libseptfa.so next to the package."""
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("SEPTFA_NVCC_FLAGS", "").split()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "septfa.h"))
     objdir = os.path.join(HERE, "build")

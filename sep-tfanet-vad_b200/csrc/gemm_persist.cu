@@ -67,7 +67,12 @@ __device__ __forceinline__ void edge_rows(const DconvParams& p, int g0, bool okm
   }
 }
 
+// Bring-up timeline (clock64 stamps per warp role of one CTA), compiled in only with -DSEPTFA_TIMELINE.
+#ifdef SEPTFA_TIMELINE
 #define TL(role, idx) do { if (p.dbg != nullptr && blockIdx.x == 1 && lane == 0 && (idx) < 256) p.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
+#else
+#define TL(role, idx) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kThreadsP, 1) k_dconv_persist(DconvParams p, int ntiles,
                                                                 const __grid_constant__ CUtensorMap tm_p,

@@ -43,9 +43,17 @@ struct TcParams {
   float* out; int out_stride;
   Stat2* st_out;
   float* rowsum; double* colsum;
+  long long* dbg;   // optional timeline buffer (bring-up only)
 };
 
 using namespace tc;
+
+// Bring-up timeline (clock64 stamps of one CTA), compiled in only with -DSEPTFA_TIMELINE.
+#ifdef SEPTFA_TIMELINE
+#define TLG(idx) do { if (p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 0 && threadIdx.x == 0 && (idx) < 64) p.dbg[idx] = clock64(); } while (0)
+#else
+#define TLG(idx) do { } while (0)
+#endif
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
@@ -121,6 +129,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  TLG(0);
 
   if (warp == 8) {
     // ------------------------------------------------------------ weight loader (TMA bulk copies)
@@ -166,6 +175,50 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
     // lane -> (row group rg = lane/8, 16-byte chunk c8 = lane%8); each warp covers 4 rows per step.
     const int c8 = lane & 7, rg = lane >> 3;
     SegStat2 qstat;
+    if (MODE == 0) {
+      // conv1: A = (x - mean) * rstd (gamma / beta live in the weight image and the bias). The global loads of
+      // chunk j+1 are issued before chunk j is converted, so one round trip to HBM is exposed per tile, not per chunk.
+      float4 xa[2][4], xb[2][4];
+      auto issue = [&](int jj, int buf) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 32 + warp * 4 + rg;
+          if (rl < nrows) {
+            const float4* src = reinterpret_cast<const float4*>(p.in + (int64_t)(r0 + rl) * kC + jj * 64 + c8 * 8);
+            xa[buf][it] = __ldg(src);
+            xb[buf][it] = __ldg(src + 1);
+          } else {
+            xa[buf][it] = xb[buf][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
+      float2 mrs[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rl = it * 32 + warp * 4 + rg;
+        mrs[it] = rl < nrows ? tab_a[smap.seg(r0 + rl)] : make_float2(0.f, 0.f);
+      }
+      issue(0, 0);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int s = j % kStages, u = j / kStages;
+        if (j + 1 < NCH) issue(j + 1, (j + 1) & 1);
+        if (u > 0) mbar_wait(empty + s, (u - 1) & 1, 400 + j);
+        uint8_t* a_tile = smem + s * STAGE;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 32 + warp * 4 + rg;
+          const float4 x0 = xa[j & 1][it], x1 = xb[j & 1][it];
+          const float sc = mrs[it].y, nb = -mrs[it].x * mrs[it].y;
+          const uint4 pk = make_uint4(pack_half2(fmaf(x0.x, sc, nb), fmaf(x0.y, sc, nb)), pack_half2(fmaf(x0.z, sc, nb), fmaf(x0.w, sc, nb)),
+                                      pack_half2(fmaf(x1.x, sc, nb), fmaf(x1.y, sc, nb)), pack_half2(fmaf(x1.z, sc, nb), fmaf(x1.w, sc, nb)));
+          *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
+        }
+        fence_proxy_async();
+        mbar_arrive(full_a + s);
+        TLG(1 + j);
+      }
+    } else
     for (int j = 0; j < NCH; ++j) {
       const int s = j % kStages, u = j / kStages;
       if (u > 0) mbar_wait(empty + s, (u - 1) & 1, 400 + j);
@@ -302,13 +355,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
       }
       fence_proxy_async();
       mbar_arrive(full_a + s);
+      TLG(1 + j);
     }
     if (MODE == 1) qstat.flush_warp(slots, warp);
 
     // ------------------------------------------------------------ epilogue (warps 0-7)
     // warp w reads TMEM lanes 32*(w%4).. (rows) and columns (w/4)*NT/2 .. in chunks of 32.
+    TLG(10);
     mbar_wait(acc_full, 0, 500);
     tc_fence_after();
+    TLG(11);
     const int lq = warp & 3, ch = warp >> 2;
     float* stg = reinterpret_cast<float*>(smem) + warp * (32 * kStgPitch);  // aliases the (now idle) stage buffers
     const int my_rl = lq * 32 + lane;       // the row this thread owns in TMEM
@@ -319,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
       const int col0 = ch * (NT / 2) + cc * 32;
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)col0, v);
+      TLG(12 + cc * 4);
       if (MODE == 1) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) rowacc += v[i];
@@ -328,6 +385,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
       for (int i = 0; i < 8; ++i)
         *reinterpret_cast<float4*>(stg + lane * kStgPitch + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       __syncwarp();
+      TLG(13 + cc * 4);
       // coalesced copy-out: 8 lanes x float4 = one 128 B row segment, 4 rows per instruction
       const int c4 = (lane & 7) * 4;
       const int gcol = (MODE == 2 ? (int)blockIdx.y * NT : 0) + col0 + c4;
@@ -361,6 +419,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
           *reinterpret_cast<float4*>(p.out + (int64_t)row * p.out_stride + gcol) = o;
         }
       }
+      TLG(14 + cc * 4);
       if (MODE == 1) {
         // column sums: fold the 4 row groups of the warp, then one global atomic per column and utterance
 #pragma unroll
@@ -382,6 +441,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
         }
       }
     }
+    TLG(30);
     if (MODE == 0) ostat.flush_warp(slots, warp);
     if (MODE == 1) {
       // row sums: the two column halves (warps w and w+4) own the same rows
@@ -393,6 +453,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
 
   tc_fence_before();
   __syncthreads();
+  TLG(31);
   if (warp == 9) tmem_dealloc(tmem_base, 256);
   Stat2* sdst = (MODE == 0) ? p.st_out : (MODE == 1 ? p.st_q : nullptr);
   if (sdst != nullptr && blockIdx.y == 0) seg_stats_commit(slots, 8, seg_acc, nseg, sdst + b_first);
@@ -408,6 +469,8 @@ void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
 }
 
 }  // namespace
+
+long long* g_tl_conv1 = nullptr;  // bring-up timeline of one conv1 launch (SEPTFA_TIMELINE)
 
 cudaError_t tc_gemm_setup() {
   cudaError_t e;
@@ -443,6 +506,7 @@ void launch_tc_conv1(const Conv1Params& c, cudaStream_t st) {
   p.w_img = c.w_img; p.in = c.w_in; p.norm = c.norm;
   p.bias = c.bias_f; p.slope = c.slope;
   p.out = c.p_out; p.out_stride = kC; p.st_out = c.st_p;
+  p.dbg = g_tl_conv1;
   launch_mode<0>(p, 1, st);
 }
 
@@ -453,6 +517,7 @@ void launch_tc_dconv(const DconvParams& c, cudaStream_t st) {
   p.st_p = c.st_p; p.g1 = c.g1; p.be1 = c.be1; p.w2b = c.w2b; p.w2f = c.w2f; p.c2f = c.c2f;
   p.slope2 = c.slope2; p.dil = c.dil; p.st_q = c.st_q;
   p.out = c.racc; p.out_stride = kC; p.rowsum = c.rowsum; p.colsum = c.colsum;
+  p.dbg = c.dbg;
   launch_mode<1>(p, 1, st);
 }
 

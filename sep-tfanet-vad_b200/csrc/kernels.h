@@ -125,6 +125,7 @@ void launch_out_stats(const float* w, StreamNorm norm, float slope, int M, int T
 void launch_tc_conv1(const Conv1Params& p, cudaStream_t st);
 void launch_tc_dconv(const DconvParams& p, cudaStream_t st);
 void launch_tc_outconv(const OutConvParams& p, cudaStream_t st);
+extern long long* g_tl_conv1;
 cudaError_t tc_gemm_setup();  // opt-in shared memory attributes; call once per device
 // gemm_persist.cu
 cudaError_t dconv_persist_setup();

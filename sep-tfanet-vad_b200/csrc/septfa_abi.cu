@@ -596,6 +596,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     double* colsum = ws.colsum + (size_t)i * B * kC;
 
     Conv1Params c1{ws.w, norm, M, T, B, d.b1, d.a1, d.w1_img, d.b1f, d.w1_t, ws.p, st_p};
+    g_tl_conv1 = (i == 6 && getenv("SEPTFA_TIMELINE") && septfa_dbg_ptr) ? septfa_dbg_ptr + 1024 : nullptr;
     prof_mark(h, SEPTFA_PROF_CONV1, st);
     if (tc_conv1) launch_tc_conv1(c1, st); else launch_ref_conv1(c1, st);
 
@@ -673,7 +674,12 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
       long long t0 = 0;
       for (long long v : hbuf) if (v && (!t0 || v < t0)) t0 = v;
       const char* names[8] = {"rawload", "wload", "mma_ready", "tr_start", "tr_end", "mma_wready", "tr_rawready", "epi"};
-      for (int r = 0; r < 8; ++r) {
+      fprintf(stderr, "TLG dconv:");
+      for (int i2 = 0; i2 < 64; ++i2) fprintf(stderr, " %lld", hbuf[i2] ? hbuf[i2] - hbuf[0] : -1);
+      fprintf(stderr, "\nTLG conv1:");
+      for (int i2 = 0; i2 < 64; ++i2) fprintf(stderr, " %lld", hbuf[1024 + i2] ? hbuf[1024 + i2] - hbuf[1024] : -1);
+      fprintf(stderr, "\n");
+      for (int r = 0; r < 8 && h->dconv_persistent; ++r) {
         fprintf(stderr, "TL %s:", names[r]);
         for (int i2 = 0; i2 < 40; ++i2) if (hbuf[r * 256 + i2]) fprintf(stderr, " %lld", hbuf[r * 256 + i2] - t0);
         fprintf(stderr, "\n");
