@@ -124,70 +124,99 @@ void launch_vad(const VadParams& p, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Mask application + inverse STFT + overlap-add. One CTA = 8 consecutive 256-sample output blocks of
-// one utterance, BOTH speakers: the two Hermitian spectra share one complex FFT (Z = E0 + i E1 ->
-// z = e0 + i e1), and every frame is transformed once per CTA.
+// Mask application + inverse STFT + overlap-add. One CTA = 7 consecutive 256-sample output blocks of one utterance,
+// BOTH speakers: the two Hermitian spectra share one complex FFT (Z = E0 + i E1 -> z = e0 + i e1). The 8 frames the
+// blocks need are transformed four at a time by the CTA's four 64-thread groups (radix-8 FFT, fft512.cuh).
 //   E_s[f] = S[t,f] * sigmoid(logit[s,f,t]) * gate[s,t]                    (model.py:429-437,452-455)
 //   out[256 j + n] = (w[256+n] fr_j[256+n] + w[n] fr_{j+1}[n]) / (w[256+n]^2 + w[n]^2)        (:460)
-constexpr int kIstftBlocks = 8;
+constexpr int kIstftBlocks = 7;
 
 __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S, const float* __restrict__ logits,
                                                     const float* __restrict__ gate, const float* __restrict__ window,
                                                     const float2* __restrict__ twiddle, int64_t L, int T,
                                                     float* __restrict__ out) {
-  __shared__ float2 buf[kNfft];
-  __shared__ float2 tw[256];
-  const int n = threadIdx.x, b = blockIdx.y;
+  __shared__ float2 buf[4][kFftPad];
+  __shared__ float2 tw[kNfft];
+  __shared__ float2 carry[kHop];  // windowed second half of the last frame of the previous round
+  const int tid = threadIdx.x, grp = tid >> 6, j = tid & 63, b = blockIdx.y;
   const int j0 = blockIdx.x * kIstftBlocks;
-  tw[n] = __ldg(twiddle + n);
-  const float w_lo = __ldg(window + n), w_hi = __ldg(window + kHop + n);
+  tw[tid] = __ldg(twiddle + tid);
+  tw[tid + 256] = __ldg(twiddle + tid + 256);
+  const float w_lo = __ldg(window + tid), w_hi = __ldg(window + kHop + tid);
+  const float sc = 1.f / (float)kNfft;
   float* out0 = out + ((int64_t)b * 2) * L;
   float* out1 = out0 + L;
-  float2 prev = make_float2(0.f, 0.f);  // second half (x w) of the previous frame: (speaker 0, speaker 1)
-  const int t_last = min(j0 + kIstftBlocks, T - 1);
-  for (int t = j0; t <= t_last; ++t) {
-    const int64_t row = (int64_t)b * T + t;
-    float g0 = 1.f, g1 = 1.f;
-    if (gate != nullptr) {
-      g0 = __ldg(gate + ((int64_t)b * 2) * T + t);
-      g1 = __ldg(gate + ((int64_t)b * 2 + 1) * T + t);
-    }
-    const float* lr = logits + row * kLogitStride;
-    __syncthreads();  // the previous frame's reads of buf are done
-    if (n >= 1) {
-      const float2 sv = __ldg(S + row * kBins + n);
-      const float m0 = sigmoidf_acc(__ldg(lr + n)) * g0, m1 = sigmoidf_acc(__ldg(lr + kBins + n)) * g1;
-      const float a0 = sv.x * m0, b0 = sv.y * m0, a1 = sv.x * m1, b1 = sv.y * m1;
-      buf[__brev((unsigned)n) >> 23] = make_float2(a0 - b1, b0 + a1);                 // E0[f] + i E1[f]
-      buf[__brev((unsigned)(kNfft - n)) >> 23] = make_float2(a0 + b1, a1 - b0);       // conj(E0[f]) + i conj(E1[f])
-    } else {
-      const float2 sv = __ldg(S + row * kBins + 256);
-      const float m0 = sigmoidf_acc(__ldg(lr + 256)) * g0, m1 = sigmoidf_acc(__ldg(lr + kBins + 256)) * g1;
-      buf[0] = make_float2(0.f, 0.f);                                                  // DC bin is zero
-      buf[__brev(256u) >> 23] = make_float2(sv.x * m0, sv.x * m1);  // irfft ignores the imaginary part of Nyquist
-    }
-    fft512_smem<true>(buf, tw);
-    const float sc = 1.f / (float)kNfft;
-    const float2 lo = buf[n], hi = buf[kHop + n];
-    const float2 first = make_float2(lo.x * sc * w_lo, lo.y * sc * w_lo);
-    if (t > j0) {
-      const int64_t o = (int64_t)(t - 1) * kHop + n;
-      if (o < L) {
-        const float env = w_hi * w_hi + w_lo * w_lo;
-        out0[o] = (prev.x + first.x) / env;
-        out1[o] = (prev.y + first.y) / env;
+  const int t_last = min(j0 + kIstftBlocks, T - 1);   // frames j0 .. t_last
+  for (int round = 0; round < 2; ++round) {
+    const int tbase = j0 + round * 4;
+    if (tbase > t_last) break;                        // uniform
+    const int t = tbase + grp;                        // this group's frame
+    const bool vt = t <= t_last;
+    __syncthreads();                                  // previous round's reads of buf are done
+    if (vt) {
+      const int64_t row = (int64_t)b * T + t;
+      float g0 = 1.f, g1 = 1.f;
+      if (gate != nullptr) {
+        g0 = __ldg(gate + ((int64_t)b * 2) * T + t);
+        g1 = __ldg(gate + ((int64_t)b * 2 + 1) * T + t);
+      }
+      const float* lr = logits + row * kLogitStride;
+      float2* bg = buf[grp];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int f = j + 64 * r;  // 0..255
+        if (f >= 1) {
+          const float2 sv = __ldg(S + row * kBins + f);
+          const float m0 = sigmoidf_acc(__ldg(lr + f)) * g0, m1 = sigmoidf_acc(__ldg(lr + kBins + f)) * g1;
+          const float a0 = sv.x * m0, b0 = sv.y * m0, a1 = sv.x * m1, b1 = sv.y * m1;
+          bg[fft_idx(f)] = make_float2(a0 - b1, b0 + a1);               // E0[f] + i E1[f]
+          bg[fft_idx(kNfft - f)] = make_float2(a0 + b1, a1 - b0);       // conj(E0[f]) + i conj(E1[f])
+        } else {
+          const float2 sv = __ldg(S + row * kBins + 256);
+          const float m0 = sigmoidf_acc(__ldg(lr + 256)) * g0, m1 = sigmoidf_acc(__ldg(lr + kBins + 256)) * g1;
+          bg[fft_idx(0)] = make_float2(0.f, 0.f);                       // DC bin is zero
+          bg[fft_idx(256)] = make_float2(sv.x * m0, sv.x * m1);         // irfft ignores the imaginary part of Nyquist
+        }
       }
     }
-    prev = make_float2(hi.x * sc * w_hi, hi.y * sc * w_hi);
-  }
-  // the last frame of the utterance has no successor: its second half is the ragged tail
-  if (t_last == T - 1 && T - 1 < j0 + kIstftBlocks) {
-    const int64_t o = (int64_t)(T - 1) * kHop + n;
-    if (o < L) {
-      const float env = w_hi * w_hi;
-      out0[o] = prev.x / env;
-      out1[o] = prev.y / env;
+    fft512_r8<true>(buf[grp], tw, j);
+    // output blocks of this round: block t-1 = second half of frame t-1 + first half of frame t, thread = sample n
+    const int n = tid;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int tq = tbase + q;                       // frame held by group q
+      if (tq > t_last) break;
+      const float2 lo = buf[q][fft_idx(n)];
+      const float2 first = make_float2(lo.x * sc * w_lo, lo.y * sc * w_lo);
+      if (tq > j0) {
+        float2 prev;
+        if (q == 0) {
+          prev = carry[n];
+        } else {
+          const float2 hi = buf[q - 1][fft_idx(kHop + n)];
+          prev = make_float2(hi.x * sc * w_hi, hi.y * sc * w_hi);
+        }
+        const int64_t o = (int64_t)(tq - 1) * kHop + n;
+        if (o < L) {
+          const float env = w_hi * w_hi + w_lo * w_lo;
+          out0[o] = (prev.x + first.x) / env;
+          out1[o] = (prev.y + first.y) / env;
+        }
+      }
     }
+    // carry the last frame of this round; the very last frame of the utterance has no successor (ragged tail)
+    const int ql = min(3, t_last - tbase);
+    const float2 hi = buf[ql][fft_idx(kHop + n)];
+    const float2 second = make_float2(hi.x * sc * w_hi, hi.y * sc * w_hi);
+    if (tbase + ql == T - 1 && T - 1 < j0 + kIstftBlocks) {
+      const int64_t o = (int64_t)(T - 1) * kHop + n;
+      if (o < L) {
+        const float env = w_hi * w_hi;
+        out0[o] = second.x / env;
+        out1[o] = second.y / env;
+      }
+    }
+    carry[n] = second;   // read only by the same thread in the next round
   }
 }
 

@@ -1,29 +1,69 @@
-// 512-point complex FFT over shared memory, shared by the STFT front-end and the iSTFT back-end.
+// 512-point complex FFT in shared memory, radix-8 Stockham (3 passes), shared by the STFT front-end and the
+// iSTFT back-end. One FFT is computed by a group of 64 threads (8 points per thread per pass, held in
+// registers), so a 256-thread CTA runs 4 independent FFTs side by side and needs 6 block barriers per FFT
+// (the first version was radix-2: one butterfly per thread, 10 barriers, 2x the instructions).
 #pragma once
 #include <cuda_runtime.h>
 
 namespace septfa {
 
-// In-place, decimation in time; the caller has stored the input in bit-reversed order
-// (index __brev(n) >> 23). 256 threads, one radix-2 butterfly per thread per stage, twiddles
-// tw[j] = exp(-2*pi*i*j/512), j < 256. INVERSE conjugates the twiddles (unnormalised inverse).
-// Starts and ends with a block barrier.
+constexpr int kFftPad = 512 + 64;  // float2 elements per padded FFT buffer
+
+// Padded index: one float2 of padding every 8 keeps the stride-8 stores of the passes at the 2-wavefront minimum.
+__device__ __forceinline__ int fft_idx(int i) { return i + (i >> 3); }
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// 8-point DFT in registers (decimation in frequency, natural-order output). INVERSE conjugates the roots.
 template <bool INVERSE>
-__device__ __forceinline__ void fft512_smem(float2* buf, const float2* tw) {
-  const int k = threadIdx.x;
+__device__ __forceinline__ void dft8(float2 (&a)[8]) {
+  constexpr float h = 0.70710678118654752440f;
+  const float sgn = INVERSE ? 1.f : -1.f;  // imaginary sign of exp(-/+ i theta)
+  auto mul_i = [&](float2 v) { return INVERSE ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x); };  // * (-/+ i)
+  float2 b0 = cadd(a[0], a[4]), b4 = csub(a[0], a[4]);
+  float2 b1 = cadd(a[1], a[5]), b5 = csub(a[1], a[5]);
+  float2 b2 = cadd(a[2], a[6]), b6 = csub(a[2], a[6]);
+  float2 b3 = cadd(a[3], a[7]), b7 = csub(a[3], a[7]);
+  b5 = cmul(b5, make_float2(h, sgn * h));    // W8^1
+  b6 = mul_i(b6);                            // W8^2
+  b7 = cmul(b7, make_float2(-h, sgn * h));   // W8^3
+  const float2 c0 = cadd(b0, b2), c2 = csub(b0, b2), c1 = cadd(b1, b3), c3 = mul_i(csub(b1, b3));
+  const float2 c4 = cadd(b4, b6), c6 = csub(b4, b6), c5 = cadd(b5, b7), c7 = mul_i(csub(b5, b7));
+  a[0] = cadd(c0, c1); a[4] = csub(c0, c1);
+  a[2] = cadd(c2, c3); a[6] = csub(c2, c3);
+  a[1] = cadd(c4, c5); a[5] = csub(c4, c5);
+  a[3] = cadd(c6, c7); a[7] = csub(c6, c7);
+}
+
+// In-place (natural order in, natural order out) FFT of the padded buffer `buf` (kFftPad float2) by the 64 threads
+// j = 0..63 of one group; tw[i] = exp(-2*pi*i*n/512), n < 512. ALL threads of the CTA must call it together
+// (block barriers inside); the caller's writes of buf must be followed by a barrier, which pass 0 provides.
+template <bool INVERSE>
+__device__ __forceinline__ void fft512_r8(float2* buf, const float2* tw, int j) {
 #pragma unroll
-  for (int s = 0; s < 9; ++s) {
-    const int half = 1 << s;
-    const int pos = k & (half - 1);
-    const int i0 = ((k >> s) << (s + 1)) + pos;
-    const int i1 = i0 + half;
-    __syncthreads();  // also orders the caller's writes of buf / tw before the first stage
-    float2 w = tw[pos << (8 - s)];
-    if (INVERSE) w.y = -w.y;
-    const float2 a = buf[i0], b = buf[i1];
-    const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
-    buf[i0] = make_float2(a.x + t.x, a.y + t.y);
-    buf[i1] = make_float2(a.x - t.x, a.y - t.y);
+  for (int pass = 0; pass < 3; ++pass) {
+    const int ns = pass == 0 ? 1 : (pass == 1 ? 8 : 64);
+    const int k = j & (ns - 1);
+    const int j0 = ((j - k) << 3) + k;
+    float2 u[8];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) u[r] = buf[fft_idx(j + 64 * r)];
+    if (pass > 0) {
+      const int step = k * (64 / ns);  // exp(-2*pi*i*r*k/(8*ns)) = tw[r * k * 512 / (8 ns)]
+#pragma unroll
+      for (int r = 1; r < 8; ++r) {
+        float2 w = tw[r * step];
+        if (INVERSE) w.y = -w.y;
+        u[r] = cmul(u[r], w);
+      }
+    }
+    dft8<INVERSE>(u);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) buf[fft_idx(j0 + r * ns)] = u[r];
   }
   __syncthreads();
 }

@@ -9,9 +9,9 @@ namespace septfa {
 
 int g_launch_count = 0;
 
-// Twiddle table exp(-2*pi*i*j/512), j < 256, computed in double on the host.
+// Twiddle table exp(-2*pi*i*j/512), j < 512, computed in double on the host.
 void make_twiddles(float2* h) {
-  for (int j = 0; j < 256; ++j) {
+  for (int j = 0; j < 512; ++j) {
     double a = -2.0 * 3.14159265358979323846 * (double)j / 512.0;
     h[j] = make_float2((float)cos(a), (float)sin(a));
   }
@@ -23,8 +23,9 @@ constexpr int kPPitch = kBins + 3;            // dB row: [0] = bin -1 (zero pad)
 
 struct GateK { float k[9]; float bias, slope; int enabled; };
 
-// One CTA = 14 consecutive frames of one utterance. Two real frames share one complex FFT
-// (z = a + i b; A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i).
+// One CTA = 14 consecutive frames of one utterance (+1 halo frame each side). The 16 frames form 8 pairs; two real
+// frames share one complex FFT (z = a + i b; A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i), and
+// the CTA's four 64-thread groups run four radix-8 FFTs side by side (two rounds).
 // torch.stft(center=True, pad_mode='reflect', onesided), no normalisation, DC bin zeroed (model.py:24,410);
 // P = 10 log10(max(|S|^2, 1e-10)); spectrum *= PReLU(Conv2d 3x3 (zero pad 1) over the (257, T) plane),
 // rows 1..256 feed the TCN (model.py:411-421).
@@ -32,28 +33,28 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
                                                   const float* __restrict__ window, const float2* __restrict__ twiddle,
                                                   GateK gk, float2* __restrict__ S, float* __restrict__ z0,
                                                   float* __restrict__ dc_gated, Stat2* __restrict__ st0) {
-  __shared__ float2 buf[kNfft];
-  __shared__ float2 tw[256];
+  __shared__ float2 buf[4][kFftPad];
+  __shared__ float2 tw[kNfft];
   __shared__ float win[kNfft];
   __shared__ float P[kFrontRows][kPPitch];
   __shared__ float red[64];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, grp = tid >> 6, j = tid & 63;
   const int b = blockIdx.y, t0 = blockIdx.x * kFrontFrames;
   const float* xb = x + (int64_t)b * L;
   tw[tid] = __ldg(twiddle + tid);
+  tw[tid + 256] = __ldg(twiddle + tid + 256);
   win[tid] = __ldg(window + tid);
   win[tid + 256] = __ldg(window + tid + 256);
   for (int i = tid; i < kFrontRows * kPPitch; i += 256) (&P[0][0])[i] = 0.f;  // zero padding of the gate conv
   __syncthreads();
 
-  for (int pair = 0; pair < kFrontRows / 2; ++pair) {
-    const int la = 2 * pair;  // local row of frame a (rows 0 and 15 are halo rows)
+  for (int round = 0; round < 2; ++round) {
+    const int la = 2 * (round * 4 + grp);  // local row of frame a (rows 0 and 15 are halo rows)
     const int ta = t0 - 1 + la, tb = ta + 1;
     const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
-    if (!va && !vb) continue;  // uniform: both frames outside the utterance -> rows stay zero
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int n = tid + h * 256;
+    for (int r = 0; r < 8; ++r) {
+      const int n = j + 64 * r;
       float a = 0.f, c = 0.f;
       if (va) {
         int64_t i = (int64_t)ta * kHop + n - kNfft / 2;
@@ -67,15 +68,15 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
         if (i >= L) i = 2 * (L - 1) - i;
         c = __ldg(xb + i) * win[n];
       }
-      buf[__brev((unsigned)n) >> 23] = make_float2(a, c);
+      buf[grp][fft_idx(n)] = make_float2(a, c);
     }
-    fft512_smem<false>(buf, tw);
+    fft512_r8<false>(buf[grp], tw, j);
     const bool wa = va && la >= 1 && la <= kFrontFrames;  // frames this CTA owns (not halo)
     const bool wb = vb && (la + 1) <= kFrontFrames;
-    for (int f = tid; f < kBins; f += 256) {
+    for (int f = j; f < kBins; f += 64) {
       float2 A = make_float2(0.f, 0.f), Bc = A;
       if (f > 0) {
-        const float2 zk = buf[f], zn = buf[(kNfft - f) & (kNfft - 1)];
+        const float2 zk = buf[grp][fft_idx(f)], zn = buf[grp][fft_idx((kNfft - f) & (kNfft - 1))];
         A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         Bc = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
       }
@@ -84,9 +85,8 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
       if (wa) S[((int64_t)b * T + ta) * kBins + f] = A;
       if (wb) S[((int64_t)b * T + tb) * kBins + f] = Bc;
     }
-    __syncthreads();  // buf is rewritten by the next pair
+    __syncthreads();  // buf is rewritten by the next round
   }
-  __syncthreads();
 
   // activity gate; kernel index [i][j]: i over frequency, j over time (the input plane is [257, T])
   float s = 0.f, ss = 0.f;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) acc += gk.k[i * 3 + j] * P[lf - 1 + j][f + i];
+        for (int jj = 0; jj < 3; ++jj) acc += gk.k[i * 3 + jj] * P[lf - 1 + jj][f + i];
       acc += gk.bias;
       return c * prelu(acc, gk.slope);
     };

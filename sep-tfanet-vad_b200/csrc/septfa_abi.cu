@@ -401,7 +401,7 @@ int septfa_commit_weights(septfa_handle* h) {
   if (upload(h, T_(h, "spec_output.window"), &h->win_fwd)) return SEPTFA_E_CUDA;
   if (upload(h, T_(h, "inv_spec.window"), &h->win_inv)) return SEPTFA_E_CUDA;
   {
-    std::vector<float2> tw(256);
+    std::vector<float2> tw(512);
     make_twiddles(tw.data());
     if (upload(h, tw, &h->twiddle)) return SEPTFA_E_CUDA;
   }
