@@ -31,7 +31,7 @@ struct TcParams {
   int M, T, B;
   const __half* w_img;
   const __half* w_img_lo;   // MODE 2: low part of the fp16 split of the weights
-  const float* in;
+  const void* in;           // [M,256] fp32 (MODE 0/2, and MODE 1 when !H16) or fp16 (MODE 1 with H16)
   StreamNorm norm;
   // MODE 2 prologue
   float slope_o; const Stat2* st_o; const float* g_o; const float* b_o;
@@ -40,7 +40,7 @@ struct TcParams {
   float slope2; int dil; Stat2* st_q;
   // epilogue
   const float* bias; float slope;
-  float* out; int out_stride;
+  void* out; int out_stride;  // fp32, or fp16 for MODE 0/1 with H16
   Stat2* st_out;
   float* rowsum; double* colsum;
   long long* dbg;   // optional timeline buffer (bring-up only)
@@ -55,7 +55,16 @@ using namespace tc;
 #define TLG(idx) do { } while (0)
 #endif
 
-template <int MODE>
+__device__ __forceinline__ float4 ld_half4(const __half* p) {   // 4 consecutive halves (8 B) -> float4
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// H16: the activation tensor exchanged with the neighbouring contraction (conv1's output p = dconv's input; dconv's
+// output racc) is stored as fp16 instead of fp32.
+template <int MODE, bool H16>
 __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   constexpr int NT = (MODE == 2) ? 192 : 256;
   constexpr int KDIM = (MODE == 1) ? 512 : 256;
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
         for (int it = 0; it < 4; ++it) {
           const int rl = it * 32 + warp * 4 + rg;
           if (rl < nrows) {
-            const float4* src = reinterpret_cast<const float4*>(p.in + (int64_t)(r0 + rl) * kC + jj * 64 + c8 * 8);
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in) + (int64_t)(r0 + rl) * kC + jj * 64 + c8 * 8);
             xa[buf][it] = __ldg(src);
             xb[buf][it] = __ldg(src + 1);
           } else {
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
         for (int it = 0; it < 4; ++it) {
           const int rl = it * 32 + warp * 4 + rg;
           if (rl < nrows) {
-            const float4* src = reinterpret_cast<const float4*>(p.in + (int64_t)(r0 + rl) * kC + kc);
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in) + (int64_t)(r0 + rl) * kC + kc);
             x0[it] = __ldg(src);
             x1[it] = __ldg(src + 1);
           } else {
@@ -301,11 +310,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
               const int row = r0 + rl;
               const int sg = smap.seg(row);
               const int t = smap.frame(row, sg);
-              const float* src = p.in + (int64_t)row * kC + g0;
-              xc[i2] = __ldg(reinterpret_cast<const float4*>(src));
               int f = sg;
-              if (t - p.dil >= 0) { f |= 256; xm[i2] = __ldg(reinterpret_cast<const float4*>(src - (int64_t)p.dil * kC)); }
-              if (t + p.dil < p.T) { f |= 512; xp[i2] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)p.dil * kC)); }
+              if (H16) {
+                const __half* src = reinterpret_cast<const __half*>(p.in) + (int64_t)row * kC + g0;
+                xc[i2] = ld_half4(src);
+                if (t - p.dil >= 0) { f |= 256; xm[i2] = ld_half4(src - (int64_t)p.dil * kC); }
+                if (t + p.dil < p.T) { f |= 512; xp[i2] = ld_half4(src + (int64_t)p.dil * kC); }
+              } else {
+                const float* src = reinterpret_cast<const float*>(p.in) + (int64_t)row * kC + g0;
+                xc[i2] = __ldg(reinterpret_cast<const float4*>(src));
+                if (t - p.dil >= 0) { f |= 256; xm[i2] = __ldg(reinterpret_cast<const float4*>(src - (int64_t)p.dil * kC)); }
+                if (t + p.dil < p.T) { f |= 512; xp[i2] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)p.dil * kC)); }
+              }
               flg[i2] = f;
             }
           }
@@ -416,7 +432,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
               atomicAdd(dst + 2, (double)o.z); atomicAdd(dst + 3, (double)o.w);
             }
           }
-          *reinterpret_cast<float4*>(p.out + (int64_t)row * p.out_stride + gcol) = o;
+          if (H16 && MODE != 2)
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + (int64_t)row * p.out_stride + gcol) =
+                make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+          else
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (int64_t)row * p.out_stride + gcol) = o;
         }
       }
       TLG(14 + cc * 4);
@@ -459,12 +479,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   if (sdst != nullptr && blockIdx.y == 0) seg_stats_commit(slots, 8, seg_acc, nseg, sdst + b_first);
 }
 
-template <int MODE>
+template <int MODE, bool H16>
 void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
   constexpr int NT = (MODE == 2) ? 192 : 256;
   constexpr int smem = kStages * (MODE == 2 ? 2 : 1) * (kAChunkBytes + NT * 128) + kAuxBytes + 1024 + (MODE == 1 ? kDconvWBytes : 0);
   dim3 grid((p.M + kTileM - 1) / kTileM, ntiles_n);
-  k_tc_gemm<MODE><<<grid, kThreads, smem, st>>>(p);
+  k_tc_gemm<MODE, H16><<<grid, kThreads, smem, st>>>(p);
   ++g_launch_count;
 }
 
@@ -472,32 +492,22 @@ void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
 
 long long* g_tl_conv1 = nullptr;  // bring-up timeline of one conv1 launch (SEPTFA_TIMELINE)
 
+template <int MODE, bool H16>
+cudaError_t setup_one(int smem) {
+  cudaFuncSetAttribute(k_tc_gemm<MODE, H16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return cudaFuncSetAttribute(k_tc_gemm<MODE, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 cudaError_t tc_gemm_setup() {
-  cudaError_t e;
   // two CTAs per SM need (almost) the whole shared-memory carveout
-  cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(k_tc_gemm<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  e = cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024 + kDconvWBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_tc_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kStages * 2 * (kAChunkBytes + 192 * 128) + kAuxBytes + 1024);
-  if (e == cudaSuccess && getenv("SEPTFA_DEBUG")) {
-    int o0 = 0, o1 = 0, o2 = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, k_tc_gemm<0>, kThreads, kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_tc_gemm<1>, kThreads,
-                                                  kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024 + kDconvWBytes);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_tc_gemm<2>, kThreads, kStages * (kAChunkBytes + 192 * 128) + kAuxBytes + 1024);
-    int smem_sm = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-    fprintf(stderr, "septfa: k_tc_gemm occupancy (CTAs/SM): conv1 %d, dconv %d, outconv %d (smem/SM %d B)\n", o0, o1, o2, smem_sm);
-  }
-  return e;
+  const int s0 = kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024;
+  const int s2 = kStages * 2 * (kAChunkBytes + 192 * 128) + kAuxBytes + 1024;
+  cudaError_t e;
+  if ((e = setup_one<0, false>(s0)) != cudaSuccess) return e;
+  if ((e = setup_one<0, true>(s0)) != cudaSuccess) return e;
+  if ((e = setup_one<1, false>(s0 + kDconvWBytes)) != cudaSuccess) return e;
+  if ((e = setup_one<1, true>(s0 + kDconvWBytes)) != cudaSuccess) return e;
+  return setup_one<2, false>(s2);
 }
 
 void launch_tc_conv1(const Conv1Params& c, cudaStream_t st) {
@@ -507,7 +517,7 @@ void launch_tc_conv1(const Conv1Params& c, cudaStream_t st) {
   p.bias = c.bias_f; p.slope = c.slope;
   p.out = c.p_out; p.out_stride = kC; p.st_out = c.st_p;
   p.dbg = g_tl_conv1;
-  launch_mode<0>(p, 1, st);
+  if (c.half_io) launch_mode<0, true>(p, 1, st); else launch_mode<0, false>(p, 1, st);
 }
 
 void launch_tc_dconv(const DconvParams& c, cudaStream_t st) {
@@ -518,7 +528,7 @@ void launch_tc_dconv(const DconvParams& c, cudaStream_t st) {
   p.slope2 = c.slope2; p.dil = c.dil; p.st_q = c.st_q;
   p.out = c.racc; p.out_stride = kC; p.rowsum = c.rowsum; p.colsum = c.colsum;
   p.dbg = c.dbg;
-  launch_mode<1>(p, 1, st);
+  if (c.half_io) launch_mode<1, true>(p, 1, st); else launch_mode<1, false>(p, 1, st);
 }
 
 void launch_tc_outconv(const OutConvParams& c, cudaStream_t st) {
@@ -528,7 +538,7 @@ void launch_tc_outconv(const OutConvParams& c, cudaStream_t st) {
   p.slope_o = c.slope_o; p.st_o = c.st_o; p.g_o = c.g_o; p.b_o = c.b_o;
   p.bias = c.bias;
   p.out = c.logits; p.out_stride = kLogitStride;
-  launch_mode<2>(p, 3, st);
+  launch_mode<2, false>(p, 3, st);
 }
 
 }  // namespace septfa

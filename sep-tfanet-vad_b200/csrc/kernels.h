@@ -28,14 +28,15 @@ struct Conv1Params {
   const __half* w_img; // tcgen05 image of W1*diag(gamma_in): 4 K-chunks x [256 rows x 128 B], 128B-swizzled K-major
   const float* bias_f; // [256] b1 + W1 beta_in (the stream norm's affine folded into the weights; tcgen05 engine)
   const float* w_t;    // fp32 [256 k][256 n]
-  float* p_out;        // [M,256]
+  void* p_out;         // [M,256] fp32, or fp16 when half_io
   Stat2* st_p;         // [B]
+  int half_io;         // store p as fp16 (both conv1 and dconv on the tcgen05 engine)
 };
 
 // DepthConv1d second half (model/model.py:136/142,144) with GroupNorm reg2 folded into W3:
 // q = PReLU(dconv(GN1(p))), racc = (W3*diag(g2)) q  (raw accumulators), row/column sums of racc.
 struct DconvParams {
-  const float* p_in;   // [M,256]
+  const void* p_in;    // [M,256] fp32, or fp16 when half_io
   const Stat2* st_p;   // [B]
   const float* g1;     // reg1 gamma/beta [256]
   const float* be1;
@@ -47,11 +48,12 @@ struct DconvParams {
   int M, T, B;
   const __half* w_img; // 8 K-chunks x [256 rows x 128 B]
   const float* w_t;    // fp32 [512 k][256 n] (gamma2-folded)
-  float* racc;         // [M,256]
+  void* racc;          // [M,256] fp32, or fp16 when half_io
   float* rowsum;       // [M]
   double* colsum;      // [B,256] (pre-zeroed, accumulated with double atomics)
   Stat2* st_q;         // [B]
   long long* dbg;      // optional timeline buffer (bring-up only), nullptr otherwise
+  int half_io;         // p and racc are fp16
 };
 
 // TCN.output (model/model.py:322-325,357): logits = Wo GN(PReLU(y)) + bo, N = 514 padded to 576.
@@ -97,7 +99,8 @@ enum LnMode { LN_NONE = 0, LN_RECURSIVE = 1, LN_RESIDUAL = 2 };
 struct ResidParams {
   float* w;            // [M,256] residual stream, updated in place by resid_apply
   StreamNorm norm;     // affine that turns w into y
-  const float* racc;   // [M,256]
+  const void* racc;    // [M,256] fp32, or fp16 when racc_half
+  int racc_half;
   const float* ra; const float* rb; const float* gf; const float* gt;
   int M, T, B;
   int mode;            // LnMode
@@ -127,9 +130,6 @@ void launch_tc_dconv(const DconvParams& p, cudaStream_t st);
 void launch_tc_outconv(const OutConvParams& p, cudaStream_t st);
 extern long long* g_tl_conv1;
 cudaError_t tc_gemm_setup();  // opt-in shared memory attributes; call once per device
-// gemm_persist.cu
-cudaError_t dconv_persist_setup();
-void launch_dconv_persist(const DconvParams& p, cudaStream_t st);
 // backend.cu
 struct VadParams {
   const float* logits;   // [M,576]

@@ -47,7 +47,7 @@ __device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
 //   y = w * Ay + By            Ay = rstd_y * gamma_y, By = beta_y - mean_y * Ay      (stream norm)
 //   r*g = gt[row] * (racc * G1 + G2)      G1 = ra * gf, G2 = rb * gf             (TF-attention gates)
 //   v = y + r*g (recursive) | r*g (residual);  out = y + v * Av + Bv   (Av, Bv: ln_first / ln_modules)
-template <int MODE>
+template <int MODE, bool H16>
 __global__ void __launch_bounds__(256, 4) k_resid(ResidParams p) {
   __shared__ float2 tab_y[kMaxSegs];   // stream norm
   __shared__ float2 tab_v[kMaxSegs];   // stats of v (MODE 1)
@@ -102,7 +102,14 @@ __global__ void __launch_bounds__(256, 4) k_resid(ResidParams p) {
       if (i + k < c.nrows) {
         const int row = c.r0 + i + k;
         w[k] = *reinterpret_cast<const float4*>(p.w + (int64_t)row * kC + c0);  // coherent: rewritten in place
-        ra4[k] = ld4(p.racc + (int64_t)row * kC + c0);
+        if (H16) {
+          const uint2 hv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.racc) + (int64_t)row * kC + c0));
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+          ra4[k] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        } else {
+          ra4[k] = ld4(reinterpret_cast<const float*>(p.racc) + (int64_t)row * kC + c0);
+        }
         gt[k] = __ldg(p.gt + row);
       }
     }
@@ -142,11 +149,13 @@ __global__ void __launch_bounds__(256, 4) k_resid(ResidParams p) {
 }
 
 void launch_resid_stats(const ResidParams& p, cudaStream_t st) {
-  k_resid<0><<<(p.M + kRowsPerCta - 1) / kRowsPerCta, 256, 0, st>>>(p);
+  const int grid = (p.M + kRowsPerCta - 1) / kRowsPerCta;
+  if (p.racc_half) k_resid<0, true><<<grid, 256, 0, st>>>(p); else k_resid<0, false><<<grid, 256, 0, st>>>(p);
   ++g_launch_count;
 }
 void launch_resid_apply(const ResidParams& p, cudaStream_t st) {
-  k_resid<1><<<(p.M + kRowsPerCta - 1) / kRowsPerCta, 256, 0, st>>>(p);
+  const int grid = (p.M + kRowsPerCta - 1) / kRowsPerCta;
+  if (p.racc_half) k_resid<1, true><<<grid, 256, 0, st>>>(p); else k_resid<1, false><<<grid, 256, 0, st>>>(p);
   ++g_launch_count;
 }
 
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(256) k_ref_conv1(Conv1Params p) {
 #pragma unroll 8
   for (int k = 0; k < kC; ++k) acc = fmaf(y[k], __ldg(p.w_t + k * kC + n), acc);
   const float o = prelu(acc + __ldg(p.bias + n), p.slope);
-  p.p_out[(int64_t)row * kC + n] = o;
+  reinterpret_cast<float*>(p.p_out)[(int64_t)row * kC + n] = o;
   block_stat_atomic(o, o * o, p.st_p + b, red);
 }
 
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(256) k_ref_dconv(DconvParams p) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int tt = t + (k - 1) * p.dil;
-    h[k] = (tt >= 0 && tt < p.T) ? ((__ldg(p.p_in + (int64_t)(row + (k - 1) * p.dil) * kC + c) - mr.x) * mr.y) * g + be
+    h[k] = (tt >= 0 && tt < p.T) ? ((__ldg(reinterpret_cast<const float*>(p.p_in) + (int64_t)(row + (k - 1) * p.dil) * kC + c) - mr.x) * mr.y) * g + be
                                  : 0.f;
   }
   float s = 0.f, ss = 0.f;
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(256) k_ref_dconv(DconvParams p) {
   float acc = 0.f;
 #pragma unroll 8
   for (int k = 0; k < kH; ++k) acc = fmaf(q[k], __ldg(p.w_t + k * kC + c), acc);
-  p.racc[(int64_t)row * kC + c] = acc;
+  reinterpret_cast<float*>(p.racc)[(int64_t)row * kC + c] = acc;
   atomicAdd(p.colsum + b * kC + c, (double)acc);
   float rs = warp_sum(acc);
   if ((c & 31) == 0) red[c >> 5] = rs;
