@@ -35,6 +35,7 @@ FS = 16000
 MAC_PER_FRAME = 4899657                     # algorithmic MACs per STFT frame
 DCONV_MAC_PER_FRAME = 131072 + 1536         # res_out 512->256 + depthwise k3 (the dominant kernel's share)
 CONV1_MAC_PER_FRAME = 65536
+DCONV_DRAM_BYTES_NCU = 34750208           # k_tc_gemm<1,1>, 256 x 4 s: 33.78 MB read + 0.97 MB written (profiles/r1_ncu_summary.md)
 
 
 def measured_peaks():
@@ -57,7 +58,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
@@ -228,7 +229,6 @@ def main():
     if world > 1:
         dist.barrier()
     t_dev = gather_max_time(e0.elapsed_time(e1) * 1e-3)
-    clocks = sampler.stop() if sampler else None
     launches = model.last_launch_count * a.steps
 
     # ---- per-kernel-class timing (separate pass; events inside forward on the same stream)
@@ -250,6 +250,7 @@ def main():
         out_h = model.forward_host(x_host, kw, device=local_rank)
     t_e2e = gather_max_time(time.perf_counter() - t0)
     assert out_h[0].shape == (B, 2, L)
+    clocks = sampler.stop() if sampler else None   # sampled over the timed, profiled and end-to-end legs
 
     # ---- online mode (BASELINE.json configs[2]): S concurrent streams, one hop-step = forward on the current 3 s
     # windows + per-stream L1-PIT + reorder + append; latency per hop-step from CUDA events, windows resident
@@ -310,7 +311,11 @@ def main():
             "model_flops_utilization": 2.0 * MAC_PER_FRAME * M * world * a.steps / t_dev / 1e12 / (peak_tf * world),
             "roofline": {"kernel": "k_tc_gemm<1> (depthwise conv prologue + res_out 512->256 tcgen05 GEMM)",
                          "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak_tf, "traffic": DCONV_DRAM_BYTES_NCU if (B, L) == (256, 64000) else None,
+                         "traffic_source": "profiles/r1_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                           "k_tc_gemm<1,1> launch (ncu --set full); the other 31 MB of its 65.8 MB algorithmic "
+                                           "fp16 in/out bytes are served by / left in the 126 MB L2",
+                         "peak_source": peak_src,
                          "ms_per_launch": dconv_ms, "flop_per_launch": flop_per_launch,
                          "conv1_tflops": conv1_tf},
             "kernels": kernels,

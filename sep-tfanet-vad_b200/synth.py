@@ -152,9 +152,14 @@ def make_mixture(index, length, base_seed=1234, fs=16000):
     Gaussian "speakers" with independent on/off envelopes, SIR U(0,5) dB, white noise at
     SNR U(0,15) dB (create_data/data_conifg_wham.yaml:60-61), then min-max normalised to
     [-0.9, 0.9] exactly as only_inference.py:81. Returns float32 [length]."""
-    rng = np.random.default_rng(base_seed + index)
-    s1 = _bandlimited_noise(rng, length, fs) * _onoff_envelope(rng, length, fs)
-    s2 = _bandlimited_noise(rng, length, fs) * _onoff_envelope(rng, length, fs)
+    for attempt in range(16):
+        # attempt 0 keeps the original stream; short clips can draw two all-off envelopes (a silent mixture, which
+        # min-max normalisation would turn into NaNs) - those are re-drawn from a derived seed
+        rng = np.random.default_rng(base_seed + index if attempt == 0 else [base_seed + index, attempt])
+        s1 = _bandlimited_noise(rng, length, fs) * _onoff_envelope(rng, length, fs)
+        s2 = _bandlimited_noise(rng, length, fs) * _onoff_envelope(rng, length, fs)
+        if np.mean((s1 + s2) ** 2) > 1e-8:
+            break
     p1 = np.mean(s1 ** 2) + 1e-12
     p2 = np.mean(s2 ** 2) + 1e-12
     sir = rng.uniform(0.0, 5.0)
