@@ -728,7 +728,8 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
   // Independent utterances: the batch is cut into chunks that alternate between two stream "lanes". Each lane
   // runs copy-in -> kernels -> copy-out in order on its own stream and workspace; the two lanes overlap each
   // other's copies with kernels and keep the SMs filled while one lane's (smaller) grids drain.
-  int nchunk = h->host_chunks > 0 ? h->host_chunks : (B >= 128 ? 4 : (B >= 32 ? 2 : 1));
+  // measured on B200, 256 x 4 s (tools/e2e_sweep.py): 1 chunk 8.9 ms, 2 chunks 7.5 ms, 4 chunks 8.5 ms, 8 chunks 12.7 ms
+  int nchunk = h->host_chunks > 0 ? h->host_chunks : (B >= 64 ? 2 : 1);
   nchunk = std::min(std::min(nchunk, kHostChunksMax), B);
   const int Bc = (B + nchunk - 1) / nchunk;
   const size_t nx = (size_t)B * L * sizeof(float), nout = nx * 2, nvad = (size_t)B * 2 * T * sizeof(float);
