@@ -18,7 +18,9 @@ constexpr int kVadWPitch = 264;
 __global__ void __launch_bounds__(256) k_vad_partial(const float* __restrict__ logits, int M,
                                                      const float* __restrict__ w1t, float* __restrict__ part) {
   __shared__ float w[20][kVadWPitch];
-  for (int i = threadIdx.x; i < 20 * kBins; i += 256) w[i / kBins][i % kBins] = __ldg(w1t + i);
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < 20 * kBins; i += 256) w[i / kBins][i % kBins] = __ldg(w1t + i);   // static weights
+  pdl_wait();
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < kVadRowsPerCta; r += 8) {
@@ -56,6 +58,8 @@ __global__ void __launch_bounds__(256) k_vad_partial(const float* __restrict__ l
 __global__ void __launch_bounds__(256) k_vad_final(VadParams p) {
   __shared__ double red[2][8];
   __shared__ float2 s_mr;
+  pdl_launch_dependents();
+  pdl_wait();
   const int bs = blockIdx.x, b = bs >> 1, s = bs & 1;
   float* c4 = p.c4 + (int64_t)bs * p.T * 4;
   float* prob = p.prob + (int64_t)bs * p.T;
@@ -118,9 +122,8 @@ __global__ void __launch_bounds__(256) k_vad_final(VadParams p) {
 }
 
 void launch_vad(const VadParams& p, cudaStream_t st) {
-  k_vad_partial<<<(p.M + kVadRowsPerCta - 1) / kVadRowsPerCta, 256, 0, st>>>(p.logits, p.M, p.w1t, p.part);
-  k_vad_final<<<p.B * 2, 256, 0, st>>>(p);
-  g_launch_count += 2;
+  launch_k(k_vad_partial, dim3((p.M + kVadRowsPerCta - 1) / kVadRowsPerCta), dim3(256), 0, st, true, p.logits, p.M, p.w1t, p.part);
+  launch_k(k_vad_final, dim3(p.B * 2), dim3(256), 0, st, true, p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -144,6 +147,8 @@ __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S
   tw[tid + 256] = __ldg(twiddle + tid + 256);
   const float w_lo = __ldg(window + tid), w_hi = __ldg(window + kHop + tid);
   const float sc = 1.f / (float)kNfft;
+  pdl_launch_dependents();
+  pdl_wait();
   float* out0 = out + ((int64_t)b * 2) * L;
   float* out1 = out0 + L;
   const int t_last = min(j0 + kIstftBlocks, T - 1);   // frames j0 .. t_last
@@ -223,8 +228,7 @@ __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S
 void launch_mask_istft(const float2* S, const float* logits, const float* gate, const float* window,
                        const float2* twiddle, int B, int64_t L, int T, float* out, cudaStream_t st) {
   dim3 grid((T + kIstftBlocks - 1) / kIstftBlocks, B);
-  k_mask_istft<<<grid, 256, 0, st>>>(S, logits, gate, window, twiddle, L, T, out);
-  ++g_launch_count;
+  launch_k(k_mask_istft, grid, dim3(256), 0, st, true, S, logits, gate, window, twiddle, L, T, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -238,6 +242,8 @@ __global__ void __launch_bounds__(256) k_export(const float2* __restrict__ S, co
   __shared__ float tl[32][33];   // logits tile [t][f]
   __shared__ float2 ts[32][33];  // S tile
   __shared__ float tz[32][33];   // gated spectrum tile
+  pdl_launch_dependents();
+  pdl_wait();
   const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32, b = blockIdx.z >> 1, s = blockIdx.z & 1;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
@@ -272,8 +278,7 @@ void launch_export(const float2* S, const float* logits, const float* gate, cons
                    int B, int T, float2* est, float* mask, float* spectrum, float* logits_out, cudaStream_t st) {
   if (est == nullptr && mask == nullptr && spectrum == nullptr && logits_out == nullptr) return;
   dim3 grid((T + 31) / 32, (kBins + 31) / 32, B * 2);
-  k_export<<<grid, 256, 0, st>>>(S, logits, gate, z0, dc_gated, T, est, mask, spectrum, logits_out);
-  ++g_launch_count;
+  launch_k(k_export, grid, dim3(256), 0, st, true, S, logits, gate, z0, dc_gated, T, est, mask, spectrum, logits_out);
 }
 
 }  // namespace septfa

@@ -6,6 +6,13 @@
 
 namespace septfa {
 
+// Programmatic dependent launch (PDL): every kernel of the forward is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, lets its successor be scheduled early (launch_dependents)
+// and waits for its predecessor to complete and flush (griddepcontrol.wait) before it touches any global
+// memory another kernel of the chain writes or reads. Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 constexpr int kNfft = 512;
 constexpr int kHop = 256;
 constexpr int kBins = 257;       // n_fft/2 + 1

@@ -8,6 +8,7 @@
 namespace septfa {
 
 int g_launch_count = 0;
+int g_use_pdl = 1;
 
 // Twiddle table exp(-2*pi*i*j/512), j < 512, computed in double on the host.
 void make_twiddles(float2* h) {
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
   __shared__ float win[kNfft];
   __shared__ float P[kFrontRows][kPPitch];
   __shared__ float red[64];
+  pdl_launch_dependents();
   const int tid = threadIdx.x, grp = tid >> 6, j = tid & 63;
   const int b = blockIdx.y, t0 = blockIdx.x * kFrontFrames;
   const float* xb = x + (int64_t)b * L;
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
   win[tid] = __ldg(window + tid);
   win[tid + 256] = __ldg(window + tid + 256);
   for (int i = tid; i < kFrontRows * kPPitch; i += 256) (&P[0][0])[i] = 0.f;  // zero padding of the gate conv
+  pdl_wait();  // S / z0 / statistics of the previous forward may still be in use by its last kernels
   __syncthreads();
 
   for (int round = 0; round < 2; ++round) {
@@ -123,8 +126,8 @@ void launch_frontend(const float* x, int B, int64_t L, int T, const float* windo
   gk.slope = slope;
   gk.enabled = enabled;
   dim3 grid((T + kFrontFrames - 1) / kFrontFrames, B);
-  k_frontend<<<grid, 256, 0, st>>>(x, L, T, window, twiddle, gk, S, z0, dc_gated, st0);
-  ++g_launch_count;
+  // first kernel of the chain: it follows a memset, so it is launched without the PDL attribute
+  launch_k(k_frontend, grid, dim3(256), 0, st, false, x, L, T, window, twiddle, gk, S, z0, dc_gated, st0);
 }
 
 }  // namespace septfa

@@ -114,6 +114,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 256);
+  pdl_launch_dependents();
+  if (MODE == 1) {
+    // folded depthwise taps (static weights): staged before waiting for the previous kernel
+    // staged as [chunk j][output o][lane chunk c8] so that the 8 lane groups of a warp read consecutive words
+    for (int i = threadIdx.x; i < kH; i += kThreads) {
+      const int jj = i >> 6, cc = (i >> 3) & 7, oo = i & 7, d = (jj * 8 + oo) * 8 + cc;
+      w2f_s[d] = __ldg(p.w2f + i);
+      c2f_s[d] = __ldg(p.c2f + i);
+    }
+  }
+  pdl_wait();   // everything below reads what earlier kernels of the chain wrote
   {
     const double inv_n = 1.0 / ((double)kC * p.T);
     for (int i = threadIdx.x; i < nseg; i += kThreads) {
@@ -126,14 +137,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
       }
     }
     for (int i = threadIdx.x; i < 2 * nseg; i += kThreads) seg_acc[i] = 0.f;
-    if (MODE == 1) {
-      // staged as [chunk j][output o][lane chunk c8] so that the 8 lane groups of a warp read consecutive words
-      for (int i = threadIdx.x; i < kH; i += kThreads) {
-        const int jj = i >> 6, cc = (i >> 3) & 7, oo = i & 7, d = (jj * 8 + oo) * 8 + cc;
-        w2f_s[d] = __ldg(p.w2f + i);
-        c2f_s[d] = __ldg(p.c2f + i);
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -511,8 +514,7 @@ void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
   constexpr int NT = (MODE == 2) ? 192 : 256;
   constexpr int smem = kStages * (MODE == 2 ? 2 : 1) * (kAChunkBytes + NT * 128) + kAuxBytes + 1024 + (MODE == 1 ? kDconvWBytes : 0);
   dim3 grid((p.M + kTileM - 1) / kTileM, ntiles_n);
-  k_tc_gemm<MODE, H16><<<grid, kThreads, smem, st>>>(p);
-  ++g_launch_count;
+  launch_k(k_tc_gemm<MODE, H16>, grid, dim3(kThreads), smem, st, true, p);
 }
 
 }  // namespace

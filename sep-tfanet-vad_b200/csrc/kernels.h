@@ -157,5 +157,23 @@ void launch_online_emit(const float* pred /*[S,2,Lw]*/, int64_t Lw, const int32_
                         cudaStream_t st);
 
 extern int g_launch_count;  // kernels launched since last reset (host counter)
+extern int g_use_pdl;       // launch with the programmatic-stream-serialization attribute
+
+// Kernel launch with (optional) programmatic dependent launch; counts the launch.
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && g_use_pdl) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  ++g_launch_count;
+}
 
 }  // namespace septfa

@@ -310,6 +310,7 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
   h->nblk = c.layer * c.stack;
   h->ln_mode = c.apply_recursive_ln ? LN_RECURSIVE : (c.apply_residual_ln ? LN_RESIDUAL : LN_NONE);  // model.py:347-352
   build_keys(h);
+  if (const char* e = getenv("SEPTFA_PDL")) g_use_pdl = atoi(e) ? 1 : 0;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, "cudaSetDevice failed"); }
   cudaError_t e = tc_gemm_setup();
   if (e != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, std::string("tc_gemm_setup: ") + cudaGetErrorString(e)); }
@@ -362,6 +363,10 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "profile") == 0) {
     h->profile = value ? 1 : 0;
+    return 0;
+  }
+  if (std::strcmp(name, "pdl") == 0) {
+    g_use_pdl = value ? 1 : 0;   // process-wide: programmatic dependent launch of the forward's kernel chain
     return 0;
   }
   if (std::strcmp(name, "host_chunks") == 0) {

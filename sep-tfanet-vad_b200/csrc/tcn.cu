@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(256, 4) k_resid(ResidParams p) {
   __shared__ float2 tab_v[kMaxSegs];   // stats of v (MODE 1)
   __shared__ float acc_sm[kMaxSegs * 2];
   __shared__ float slots[8 * 4];
+  pdl_launch_dependents();
+  pdl_wait();
   const RowCtx c = row_ctx(p.M, p.T);
   const bool has_norm = p.norm.gamma != nullptr;
   const bool use_v_norm = MODE == 1 && p.mode != LN_NONE;
@@ -150,13 +152,13 @@ __global__ void __launch_bounds__(256, 4) k_resid(ResidParams p) {
 
 void launch_resid_stats(const ResidParams& p, cudaStream_t st) {
   const int grid = (p.M + kRowsPerCta - 1) / kRowsPerCta;
-  if (p.racc_half) k_resid<0, true><<<grid, 256, 0, st>>>(p); else k_resid<0, false><<<grid, 256, 0, st>>>(p);
-  ++g_launch_count;
+  if (p.racc_half) launch_k(k_resid<0, true>, dim3(grid), dim3(256), 0, st, true, p);
+  else launch_k(k_resid<0, false>, dim3(grid), dim3(256), 0, st, true, p);
 }
 void launch_resid_apply(const ResidParams& p, cudaStream_t st) {
   const int grid = (p.M + kRowsPerCta - 1) / kRowsPerCta;
-  if (p.racc_half) k_resid<1, true><<<grid, 256, 0, st>>>(p); else k_resid<1, false><<<grid, 256, 0, st>>>(p);
-  ++g_launch_count;
+  if (p.racc_half) launch_k(k_resid<1, true>, dim3(grid), dim3(256), 0, st, true, p);
+  else launch_k(k_resid<1, false>, dim3(grid), dim3(256), 0, st, true, p);
 }
 
 // Statistics of PReLU(y) for the output GroupNorm (model.py:322-323,357).
@@ -165,6 +167,8 @@ __global__ void __launch_bounds__(256) k_out_stats(const float* __restrict__ w, 
   __shared__ float2 tab_y[kMaxSegs];
   __shared__ float acc_sm[kMaxSegs * 2];
   __shared__ float slots[8 * 4];
+  pdl_launch_dependents();
+  pdl_wait();
   const RowCtx c = row_ctx(M, T);
   const bool has_norm = norm.gamma != nullptr;
   if (has_norm) fill_seg_table(tab_y, norm.st, norm.inv_n, norm.eps, c.b_first, c.nseg);
@@ -191,8 +195,7 @@ __global__ void __launch_bounds__(256) k_out_stats(const float* __restrict__ w, 
 }
 
 void launch_out_stats(const float* w, StreamNorm norm, float slope, int M, int T, Stat2* st_o, cudaStream_t st) {
-  k_out_stats<<<(M + kRowsPerCta - 1) / kRowsPerCta, 256, 0, st>>>(w, norm, slope, M, T, st_o);
-  ++g_launch_count;
+  launch_k(k_out_stats, dim3((M + kRowsPerCta - 1) / kRowsPerCta), dim3(256), 0, st, true, w, norm, slope, M, T, st_o);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -224,6 +227,8 @@ __global__ void __launch_bounds__(256) k_tf_gate(GateParams p) {
   __shared__ float red[32];
   __shared__ float s_ra, s_mu, s_rbmean;
   const int b = blockIdx.x, tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (tid == 0) {
     const float2 mr = stat_mean_rstd(p.st_q + b, 1.0 / ((double)kH * p.T), 1e-8f);
     s_mu = mr.x;
@@ -259,8 +264,7 @@ __global__ void __launch_bounds__(256) k_tf_gate(GateParams p) {
 }
 
 void launch_tf_gate(const GateParams& p, cudaStream_t st) {
-  k_tf_gate<<<p.B, 256, p.T * sizeof(float), st>>>(p);
-  ++g_launch_count;
+  launch_k(k_tf_gate, dim3(p.B), dim3(256), p.T * sizeof(float), st, true, p);
 }
 
 // ------------------------------------------------------------------------------------------
