@@ -124,6 +124,13 @@ void launch_tf_gate(const GateParams& p, cudaStream_t st);
 void launch_resid_stats(const ResidParams& p, cudaStream_t st);
 void launch_resid_apply(const ResidParams& p, cudaStream_t st);
 void launch_out_stats(const float* w, StreamNorm norm, float slope, int M, int T, Stat2* st_o, cudaStream_t st);
+// resid_fused.cu
+cudaError_t resid_fused_setup();
+int resid_fused_cluster_size(int T);   // 0: the utterance does not fit one cluster
+bool launch_resid_fused(const ResidParams& rp, const GateParams& gp, cudaStream_t st);
+#ifdef SEPTFA_TIMELINE
+void resid_fused_dump_timeline();
+#endif
 // gemm_tc.cu
 void launch_tc_conv1(const Conv1Params& p, cudaStream_t st);
 void launch_tc_dconv(const DconvParams& p, cudaStream_t st);

@@ -1,0 +1,627 @@
+// Cluster-resident post-block update: TF-attention gates + both GroupNorm residual steps of a TCN block in ONE
+// kernel. A thread-block cluster owns one utterance; its residual stream tile (fp32) and raw res_out accumulators
+// (fp16) are read from HBM once into the cluster's shared memory, the two global statistics (of v and of the new
+// stream) are reduced across the cluster through distributed shared memory in a fixed order (bit-reproducible, no
+// atomics), and the new stream is written back once. Replaces k_tf_gate + k_resid<0> + k_resid<1> (which read the
+// two tensors twice) whenever an utterance fits a cluster of <= 8 CTAs (T <= 1152 frames, 18 s).
+// Reference: model/model.py:197-208 (TF_Attention), :347-352 (post-block norms).
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace septfa {
+
+namespace {
+
+constexpr int kFusedThreads = 256;
+constexpr int kFusedWarps = kFusedThreads / 32;
+constexpr int kRowBytes = kC * 4 + kC * 2;   // fp32 stream row + fp16 accumulator row in shared memory
+
+__device__ __forceinline__ float tf_chain2(const float* m, int n, int j, const float* w1, float b1, const float* w2,
+                                           float b2, float slope) {
+  // u1 = conv(k3,p1,d1)(m); u2 = conv(k3,p2,d2)(u1); both zero-pad their own input (model.py:184-185,190-191)
+  float u2 = b2;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = j + 2 * (k - 1);
+    if (i < 0 || i >= n) continue;
+    float u1 = b1;
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      const int ii = i + kk - 1;
+      if (ii >= 0 && ii < n) u1 += w1[kk] * m[ii];
+    }
+    u2 += w2[k] * u1;
+  }
+  return sigmoidf_acc(prelu(u2, slope));
+}
+
+struct FusedParams {
+  float* w;                 // [M,256] residual stream, updated in place
+  const __half* racc;       // [M,256] raw res_out accumulators (fp16)
+  StreamNorm norm;          // affine that turns w into y
+  const Stat2* st_q;        // [B] statistics of q (GroupNorm reg2, folded into res_out)
+  const float* s3; const float* c03;
+  const float* rowsum;      // [M]
+  const double* colsum;     // [B,256]
+  TfParams tf;
+  int T, B, Tc;             // Tc = frames per CTA
+  int mode;                 // LnMode
+  const float* g_a; const float* b_a;   // ln_first / ln_modules
+  Stat2* st_w;              // [B] statistics of the new stream (recursive mode), accumulated into a zeroed slot
+};
+
+// fixed-order block reduction of (s, q) in double; result valid in all threads
+__device__ __forceinline__ double2 block_sum2(float s, float q, double* red /*[2*kFusedWarps]*/) {
+  double ds = warp_sum((double)s), dq = warp_sum((double)q);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[w] = ds; red[kFusedWarps + w] = dq; }
+  __syncthreads();
+  double ts = 0.0, tq = 0.0;
+  for (int i = 0; i < kFusedWarps; ++i) { ts += red[i]; tq += red[kFusedWarps + i]; }
+  __syncthreads();
+  return make_double2(ts, tq);
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 2) k_resid_fused(FusedParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / CS;
+  const int t0 = rank * p.Tc, nt = max(0, min(p.Tc, p.T - t0));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  float* w_s = reinterpret_cast<float*>(smem);                                   // [Tc][256] fp32
+  __half* r_s = reinterpret_cast<__half*>(smem + (size_t)p.Tc * kC * 4);        // [Tc][256] fp16
+  uint8_t* aux = smem + (size_t)p.Tc * kRowBytes;
+  double* red = reinterpret_cast<double*>(aux);                                  // [2*kFusedWarps]
+  double* xch = red + 2 * kFusedWarps;                                           // [2 phases][2] cluster exchange
+  float* mf_s = reinterpret_cast<float*>(xch + 4);                               // [256]
+  float* gf_s = mf_s + kC;                                                       // [256]
+  float* rb_s = gf_s + kC;                                                       // [256]
+  float* mt_s = rb_s + kC;                                                       // [Tc + 6]
+  float* gt_s = mt_s + p.Tc + 8;                                                 // [Tc]
+  __shared__ float s_misc[4];
+
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // ---- stage the tile: 16-byte cp.async, one stream row = 64 pieces, one accumulator row = 32 pieces
+  {
+    const int64_t row0 = (int64_t)b * p.T + t0;
+    const float* wg = p.w + row0 * kC;
+    const __half* rg = p.racc + row0 * kC;
+    const uint32_t ws_a = (uint32_t)__cvta_generic_to_shared(w_s), rs_a = (uint32_t)__cvta_generic_to_shared(r_s);
+    for (int i = tid; i < nt * 64; i += kFusedThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ws_a + i * 16), "l"(wg + i * 4) : "memory");
+    for (int i = tid; i < nt * 32; i += kFusedThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rs_a + i * 16), "l"(rg + i * 8) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  // ---- gates (overlaps the staging): affine of r from the reg2 statistics, channel / time means, conv chains
+  const float2 mrq = stat_mean_rstd(p.st_q + b, 1.0 / ((double)kH * p.T), 1e-8f);
+  const float ra = mrq.y;
+  float rbv = 0.f;
+  if (tid < kC) {
+    rbv = __ldg(p.c03 + tid) - ra * mrq.x * __ldg(p.s3 + tid);
+    rb_s[tid] = rbv;
+    mf_s[tid] = ra * (float)(__ldg(p.colsum + b * kC + tid) / (double)p.T) + rbv;
+  }
+  {
+    const double2 t = block_sum2(rbv, 0.f, red);   // contains barriers: mf_s / rb_s are visible afterwards
+    if (tid == 0) s_misc[0] = (float)(t.x / kC);
+  }
+  __syncthreads();
+  const float rbmean = s_misc[0];
+  // m_t for this CTA's frames and 3 neighbours each side (inside the utterance)
+  for (int i = tid; i < nt + 6; i += kFusedThreads) {
+    const int t = t0 - 3 + i;
+    mt_s[i] = (t >= 0 && t < p.T) ? ra * (__ldg(p.rowsum + (int64_t)b * p.T + t) / (float)kC) + rbmean : 0.f;
+  }
+  if (tid < kC) gf_s[tid] = p.tf.enabled ? tf_chain2(mf_s, kC, tid, p.tf.wf1, p.tf.bf1, p.tf.wf2, p.tf.bf2, p.tf.af) : 1.f;
+  __syncthreads();
+  for (int i = tid; i < nt; i += kFusedThreads)
+    gt_s[i] = p.tf.enabled ? tf_chain2(mt_s + 3 - t0, p.T, t0 + i, p.tf.wt1, p.tf.bt1, p.tf.wt2, p.tf.bt2, p.tf.at) : 1.f;
+
+  // ---- per-lane channel coefficients (lane = 8 channels)
+  const int c0 = lane * 8;
+  float Ay[8], By[8], G1[8], G2[8];
+  {
+    const bool has_norm = p.norm.gamma != nullptr;
+    float2 my = make_float2(0.f, 1.f);
+    if (has_norm) my = stat_mean_rstd(p.norm.st + b, p.norm.inv_n, p.norm.eps);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float g = has_norm ? __ldg(p.norm.gamma + c0 + j) : 1.f, be = has_norm ? __ldg(p.norm.beta + c0 + j) : 0.f;
+      Ay[j] = my.y * g;
+      By[j] = be - my.x * Ay[j];
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();   // tile, gf_s, gt_s, rb_s visible
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { G1[j] = ra * gf_s[c0 + j]; G2[j] = rb_s[c0 + j] * gf_s[c0 + j]; }
+
+  auto load_row = [&](int i, float (&y)[8], float (&v)[8]) {
+    const float4 a0 = *reinterpret_cast<const float4*>(w_s + i * kC + c0), a1 = *reinterpret_cast<const float4*>(w_s + i * kC + c0 + 4);
+    const uint4 h = *reinterpret_cast<const uint4*>(r_s + i * kC + c0);
+    const float wv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), r1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&h.z)), r3 = __half22float2(*reinterpret_cast<const __half2*>(&h.w));
+    const float rv[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
+    const float gt = gt_s[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      y[j] = fmaf(wv[j], Ay[j], By[j]);
+      const float r = gt * fmaf(rv[j], G1[j], G2[j]);
+      v[j] = (p.mode == LN_RECURSIVE) ? y[j] + r : r;
+    }
+  };
+
+  // ---- phase 1: statistics of v over the whole utterance (cluster reduction through distributed shared memory)
+  float2 mv = make_float2(0.f, 1.f);
+  if (p.mode != LN_NONE) {
+    float s = 0.f, q = 0.f;
+    for (int i = warp; i < nt; i += kFusedWarps) {
+      float y[8], v[8];
+      load_row(i, y, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s += v[j]; q = fmaf(v[j], v[j], q); }
+    }
+    const double2 part = block_sum2(s, q, red);
+    if (tid == 0) { xch[0] = part.x; xch[1] = part.y; }
+    cluster.sync();
+    Stat2 tot{0.0, 0.0};
+    for (int r = 0; r < CS; ++r) {
+      const double* rx = cluster.map_shared_rank(xch, r);
+      tot.s += rx[0];
+      tot.ss += rx[1];
+    }
+    mv = stat_mean_rstd(&tot, 1.0 / ((double)kC * p.T), 1e-5f);
+  }
+
+  // ---- phase 2: new stream = y + GN(v) (or y + v), kept in shared memory; statistics of the new stream
+  float Av[8], Bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float g = (p.mode != LN_NONE) ? __ldg(p.g_a + c0 + j) : 1.f, be = (p.mode != LN_NONE) ? __ldg(p.b_a + c0 + j) : 0.f;
+    Av[j] = mv.y * g;
+    Bv[j] = be - mv.x * Av[j];
+  }
+  float s2 = 0.f, q2 = 0.f;
+  float* wout = p.w + ((int64_t)b * p.T + t0) * kC;
+  for (int i = warp; i < nt; i += kFusedWarps) {
+    float y[8], v[8], o[8];
+    load_row(i, y, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = (p.mode == LN_NONE) ? y[j] + v[j] : y[j] + fmaf(v[j], Av[j], Bv[j]);
+      s2 += o[j];
+      q2 = fmaf(o[j], o[j], q2);
+    }
+    *reinterpret_cast<float4*>(wout + (int64_t)i * kC + c0) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(wout + (int64_t)i * kC + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+  if (p.mode == LN_RECURSIVE) {
+    const double2 part = block_sum2(s2, q2, red);
+    if (tid == 0) { xch[2] = part.x; xch[3] = part.y; }
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+      Stat2 tot{0.0, 0.0};
+      for (int r = 0; r < CS; ++r) {
+        const double* rx = cluster.map_shared_rank(xch + 2, r);
+        tot.s += rx[0];
+        tot.ss += rx[1];
+      }
+      atomicAdd(&p.st_w[b].s, tot.s);
+      atomicAdd(&p.st_w[b].ss, tot.ss);
+    }
+  }
+  cluster.sync();   // no CTA may exit while its shared memory can still be read by a peer
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant for utterances of at most 8 CTAs x kMaxTc frames (T <= 576, 9.2 s; the 4 s clips of the headline
+// workload run with 8 CTAs x 32 frames, two CTAs per SM). The grid is as many clusters as the device keeps resident;
+// a cluster walks utterances b = cluster, cluster + n, ... . One thread brings the cluster's tile of the NEXT
+// utterance into the other half of a shared-memory double buffer with two TMA bulk copies (the rows of a CTA are
+// contiguous in HBM: 1 KB of stream + 512 B of accumulators per frame) while all threads take the current utterance
+// through gates -> statistics of v -> cluster exchange -> new stream, so the memory system always has the next tile
+// in flight and CTA launch / teardown happens once per SM, not once per tile.
+// The statistics of v cross the cluster with one push-style exchange (every CTA stores its partial into every peer's
+// shared memory, ONE cluster barrier, then only local reads); the statistics of the new stream go out as one double
+// atomic pair per CTA. A thread owns 4 channels (two packed pairs: FFMA2) of every 8th frame of the CTA's tile.
+#ifdef SEPTFA_TIMELINE
+__device__ unsigned long long g_fused_tl[32 * 128];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define FTL(k) do { if (threadIdx.x == 0 && blockIdx.x < 32 && (k) < 128) g_fused_tl[blockIdx.x * 128 + (k)] = gtimer(); } while (0)
+#else
+#define FTL(k) do { } while (0)
+#endif
+constexpr int kPersistThreads = 512;
+constexpr int kMaxTc = 72;
+
+__global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParams p) {
+  using namespace tc;
+  extern __shared__ __align__(16) uint8_t smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
+  const int TC = p.Tc;
+  const int t0 = rank * TC, nt = min(TC, p.T - t0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c0 = (tid & 63) * 4, rg = tid >> 6;
+  const uint32_t buf_bytes = (uint32_t)TC * kRowBytes;   // [TC][256] fp32 stream rows, then [TC][256] fp16 accumulator rows
+
+  __shared__ float mf_s[kC], gf_s[kC], rb_s[kC];
+  __shared__ float mt_s[kMaxTc + 8], gt_s[kMaxTc];
+  __shared__ float red_a[16], red_b[16];
+  __shared__ __align__(16) double xch[2][16];   // [parity][rank][2]: partial (sum, sum of squares) of v from the peers
+  __shared__ float s_sc[8];
+  __shared__ float s_nx[2][4];
+  __shared__ __align__(8) uint64_t full[2];
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  FTL(0);
+  cluster.barrier_arrive();   // "this CTA runs": peers wait for it before they store into our shared memory
+  pdl_launch_dependents();
+  __syncthreads();
+  pdl_wait();
+  FTL(1);
+
+  auto fetch = [&](int b, int buf) {   // one thread: two bulk copies onto the buffer's mbarrier
+    uint8_t* dst = smem + (size_t)buf * buf_bytes;
+    const int64_t row0 = (int64_t)b * p.T + t0;
+    mbar_expect_tx(&full[buf], (uint32_t)nt * kRowBytes);
+    bulk_copy_g2s(dst, p.w + row0 * kC, (uint32_t)nt * kC * 4, &full[buf]);
+    bulk_copy_g2s(dst + (size_t)TC * kC * 4, p.racc + row0 * kC, (uint32_t)nt * kC * 2, &full[buf]);
+  };
+  if (tid == 0 && cluster_id < p.B) fetch(cluster_id, 0);
+
+  const bool has_norm = p.norm.gamma != nullptr;
+  const bool recursive = p.mode == LN_RECURSIVE;
+  const double inv_T = 1.0 / (double)p.T;
+  // static per-channel operands, once per CTA
+  float c03v = 0.f, s3v = 0.f;
+  if (tid < kC) { c03v = __ldg(p.c03 + tid); s3v = __ldg(p.s3 + tid); }
+  float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (has_norm) { g4 = __ldg(reinterpret_cast<const float4*>(p.norm.gamma + c0)); b4 = __ldg(reinterpret_cast<const float4*>(p.norm.beta + c0)); }
+  float4 ga4 = make_float4(1.f, 1.f, 1.f, 1.f), ba4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.mode != LN_NONE) { ga4 = __ldg(reinterpret_cast<const float4*>(p.g_a + c0)); ba4 = __ldg(reinterpret_cast<const float4*>(p.b_a + c0)); }
+
+  // per-utterance small operands, fetched one utterance ahead. The four scalars every thread needs (rstd and mean of
+  // q, mean and rstd of the incoming stream) involve double arithmetic: ONE thread computes them for the next utterance
+  // and leaves them in shared memory (s_nx[parity]); 16 warps repeating that code was a third of the kernel's issue slots.
+  double csv = 0.0;
+  float rsv = 0.f;
+  auto scalars_for = [&](int b, int par) {   // one thread
+    const Stat2 sq{__ldg(&p.st_q[b].s), __ldg(&p.st_q[b].ss)};
+    const float2 mrq = stat_mean_rstd(&sq, 1.0 / ((double)kH * p.T), 1e-8f);
+    float2 my = make_float2(0.f, 1.f);
+    if (has_norm) {
+      const Stat2 sy{__ldg(&p.norm.st[b].s), __ldg(&p.norm.st[b].ss)};
+      my = stat_mean_rstd(&sy, p.norm.inv_n, p.norm.eps);
+    }
+    s_nx[par][0] = mrq.y; s_nx[par][1] = mrq.x; s_nx[par][2] = my.x; s_nx[par][3] = my.y;
+  };
+  auto fetch_small = [&](int b) {
+    if (tid < kC) {
+      csv = __ldg(p.colsum + b * kC + tid);
+    } else if (tid - kC < nt + 6) {
+      const int t = t0 - 3 + (tid - kC);
+      rsv = (t >= 0 && t < p.T) ? __ldg(p.rowsum + (int64_t)b * p.T + t) : 0.f;
+    }
+  };
+  if (cluster_id < p.B) {
+    fetch_small(cluster_id);
+    if (tid == kPersistThreads - 1) scalars_for(cluster_id, 0);
+  }
+  __syncthreads();
+
+  // fixed-order block reduction of two floats; the double totals are valid in every lane of warp 0
+  auto block_total = [&](float s, float q, double& ts, double& tq) {
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) { red_a[warp] = s; red_b[warp] = q; }
+    __syncthreads();
+    if (warp == 0) {
+      ts = warp_sum(lane < 16 ? (double)red_a[lane] : 0.0);
+      tq = warp_sum(lane < 16 ? (double)red_b[lane] : 0.0);
+    }
+  };
+
+  bool peers_up = false;
+  for (int b = cluster_id, it = 0; b < p.B; b += n_clusters, ++it) {
+    const int buf = it & 1;
+    const float* w_s = reinterpret_cast<const float*>(smem + (size_t)buf * buf_bytes);
+    const __half* r_s = reinterpret_cast<const __half*>(smem + (size_t)buf * buf_bytes + (size_t)TC * kC * 4);
+    const int b_next = b + n_clusters;
+    FTL(8 + it * 8 + 0);
+    if (tid == 0 && b_next < p.B) fetch(b_next, buf ^ 1);   // the other buffer was released by the barrier that ended it-1
+
+    // ---- gates: affine of r from the reg2 statistics, channel / time means, two stacked 3-tap convs each
+    const float ra = s_nx[buf][0], mean_y = s_nx[buf][2], rstd_y = s_nx[buf][3];
+    {
+      if (tid < kC) {
+        const float rbv = c03v - ra * s_nx[buf][1] * s3v;
+        rb_s[tid] = rbv;
+        mf_s[tid] = ra * (float)(csv * inv_T) + rbv;
+        const float s = warp_sum(rbv);
+        if (lane == 0) red_a[warp] = s;
+      }
+    }
+    const float rsv_cur = rsv;
+    if (b_next < p.B) {
+      fetch_small(b_next);
+      if (tid == kPersistThreads - 1) scalars_for(b_next, buf ^ 1);   // read after this iteration's closing barrier
+    }
+    __syncthreads();
+    if (tid < kC) {
+      gf_s[tid] = p.tf.enabled ? tf_chain2(mf_s, kC, tid, p.tf.wf1, p.tf.bf1, p.tf.wf2, p.tf.bf2, p.tf.af) : 1.f;
+    } else if (tid - kC < nt + 6) {
+      float rbsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rbsum += red_a[k];
+      const int t = t0 - 3 + (tid - kC);
+      mt_s[tid - kC] = (t >= 0 && t < p.T) ? ra * (rsv_cur / (float)kC) + rbsum / (float)kC : 0.f;
+    }
+    __syncthreads();
+    if (tid < nt)
+      gt_s[tid] = p.tf.enabled ? tf_chain2(mt_s + 3 - t0, p.T, t0 + tid, p.tf.wt1, p.tf.bt1, p.tf.wt2, p.tf.bt2, p.tf.at) : 1.f;
+
+    // ---- per-thread channel coefficients, as two packed pairs (channels c0,c0+1 | c0+2,c0+3): FFMA2 on sm_100
+    float2 Ay[2], By[2], G1[2], G2[2];
+    {
+      const float4 gf4 = *reinterpret_cast<const float4*>(gf_s + c0), rb4 = *reinterpret_cast<const float4*>(rb_s + c0);
+      const float2 rs2 = make_float2(rstd_y, rstd_y), nm2 = make_float2(-mean_y, -mean_y), ra2 = make_float2(ra, ra);
+      Ay[0] = __fmul2_rn(rs2, make_float2(g4.x, g4.y));
+      Ay[1] = __fmul2_rn(rs2, make_float2(g4.z, g4.w));
+      By[0] = __ffma2_rn(nm2, Ay[0], make_float2(b4.x, b4.y));
+      By[1] = __ffma2_rn(nm2, Ay[1], make_float2(b4.z, b4.w));
+      G1[0] = __fmul2_rn(ra2, make_float2(gf4.x, gf4.y));
+      G1[1] = __fmul2_rn(ra2, make_float2(gf4.z, gf4.w));
+      G2[0] = __fmul2_rn(make_float2(rb4.x, rb4.y), make_float2(gf4.x, gf4.y));
+      G2[1] = __fmul2_rn(make_float2(rb4.z, rb4.w), make_float2(gf4.z, gf4.w));
+    }
+    FTL(8 + it * 8 + 1);
+    mbar_wait(&full[buf], (it >> 1) & 1, 700);   // the tile has landed
+    __syncthreads();
+    FTL(8 + it * 8 + 2);                              // gt_s visible
+
+    // ---- statistics of v = y + gt (G1 r + G2)  (recursive)  |  gt (G1 r + G2)  (residual) over the whole utterance
+    float2 mv = make_float2(0.f, 1.f);
+    if (p.mode != LN_NONE) {
+      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+      for (int i0 = rg; i0 < nt; i0 += 32)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + 8 * j;
+        if (i >= nt) break;
+        const float g = gt_s[i];
+        const float2 gt2 = make_float2(g, g);
+        const float4 wv = *reinterpret_cast<const float4*>(w_s + i * kC + c0);
+        const uint2 hv = *reinterpret_cast<const uint2*>(r_s + i * kC + c0);
+        const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
+        const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+        float2 v0 = __fmul2_rn(gt2, __ffma2_rn(r0, G1[0], G2[0])), v1 = __fmul2_rn(gt2, __ffma2_rn(r1, G1[1], G2[1]));
+        if (recursive) {
+          v0 = __fadd2_rn(v0, __ffma2_rn(make_float2(wv.x, wv.y), Ay[0], By[0]));
+          v1 = __fadd2_rn(v1, __ffma2_rn(make_float2(wv.z, wv.w), Ay[1], By[1]));
+        }
+        s2 = __fadd2_rn(s2, __fadd2_rn(v0, v1));
+        q2 = __ffma2_rn(v0, v0, q2);
+        q2 = __ffma2_rn(v1, v1, q2);
+      }
+      double ts = 0.0, tq = 0.0;
+      block_total(s2.x + s2.y, q2.x + q2.y, ts, tq);
+      FTL(8 + it * 8 + 3);
+      if (!peers_up) { cluster.barrier_wait(); peers_up = true; }   // every peer is running: its shared memory may be written
+      if (warp == 0 && lane < CS) {
+        double* rx = cluster.map_shared_rank(&xch[buf][0], lane);
+        rx[2 * rank] = ts;
+        rx[2 * rank + 1] = tq;
+      }
+      cluster.sync();                        // release our stores / acquire the peers'
+      FTL(8 + it * 8 + 4);
+      if (tid == 0) {
+        Stat2 tot{0.0, 0.0};
+        for (int r = 0; r < CS; ++r) { tot.s += xch[buf][2 * r]; tot.ss += xch[buf][2 * r + 1]; }
+        const float2 m = stat_mean_rstd(&tot, 1.0 / ((double)kC * p.T), 1e-5f);
+        s_sc[4] = m.x;
+        s_sc[5] = m.y;
+      }
+      __syncthreads();
+      mv = make_float2(s_sc[4], s_sc[5]);
+    }
+
+    // ---- new stream o = y + Av v + Bv, folded into one affine per operand:
+    //   o = P w + Q + gt (R1 r + R2),   P = k Ay, Q = k By + Bv, R1 = Av G1, R2 = Av G2,  k = 1 + Av (recursive) | 1
+    float2 P[2], Q[2], R1[2], R2[2];
+    {
+      float2 Av[2] = {make_float2(1.f, 1.f), make_float2(1.f, 1.f)}, Bv[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      if (p.mode != LN_NONE) {
+        const float2 rs2 = make_float2(mv.y, mv.y), nm2 = make_float2(-mv.x, -mv.x);
+        Av[0] = __fmul2_rn(rs2, make_float2(ga4.x, ga4.y));
+        Av[1] = __fmul2_rn(rs2, make_float2(ga4.z, ga4.w));
+        Bv[0] = __ffma2_rn(nm2, Av[0], make_float2(ba4.x, ba4.y));
+        Bv[1] = __ffma2_rn(nm2, Av[1], make_float2(ba4.z, ba4.w));
+      }
+      const float2 one2 = make_float2(1.f, 1.f);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float2 kk = recursive ? __fadd2_rn(one2, Av[k]) : one2;
+        P[k] = __fmul2_rn(kk, Ay[k]);
+        Q[k] = __ffma2_rn(kk, By[k], Bv[k]);
+        R1[k] = __fmul2_rn(Av[k], G1[k]);
+        R2[k] = __fmul2_rn(Av[k], G2[k]);
+      }
+    }
+    float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+    float* wout = p.w + ((int64_t)b * p.T + t0) * kC + c0;
+    for (int i0 = rg; i0 < nt; i0 += 32)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + 8 * j;
+      if (i >= nt) break;
+      const float g = gt_s[i];
+      const float2 gt2 = make_float2(g, g);
+      const float4 wv = *reinterpret_cast<const float4*>(w_s + i * kC + c0);
+      const uint2 hv = *reinterpret_cast<const uint2*>(r_s + i * kC + c0);
+      const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
+      const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+      const float2 o0 = __ffma2_rn(gt2, __ffma2_rn(r0, R1[0], R2[0]), __ffma2_rn(make_float2(wv.x, wv.y), P[0], Q[0]));
+      const float2 o1 = __ffma2_rn(gt2, __ffma2_rn(r1, R1[1], R2[1]), __ffma2_rn(make_float2(wv.z, wv.w), P[1], Q[1]));
+      s2 = __fadd2_rn(s2, __fadd2_rn(o0, o1));
+      q2 = __ffma2_rn(o0, o0, q2);
+      q2 = __ffma2_rn(o1, o1, q2);
+      *reinterpret_cast<float4*>(wout + (int64_t)i * kC) = make_float4(o0.x, o0.y, o1.x, o1.y);
+    }
+    FTL(8 + it * 8 + 5);
+    if (recursive) {
+      double ts = 0.0, tq = 0.0;
+      block_total(s2.x + s2.y, q2.x + q2.y, ts, tq);
+      if (tid == 0) { atomicAdd(&p.st_w[b].s, ts); atomicAdd(&p.st_w[b].ss, tq); }
+    }
+    __syncthreads();   // every thread is done with this buffer and the exchange scratch: the next fetch may overwrite it
+  }
+  if (!peers_up) cluster.barrier_wait();
+  FTL(2);
+}
+
+}  // namespace
+
+// Programmatic early launch of the cluster kernels is OFF: a persistent grid that becomes resident while the tail of
+// the dconv grid is still running takes SM slots away from it (measured: 5.86 ms per step with, 5.09 ms without).
+static int g_fused_pdl = 0;
+static int g_fused_variant = 0;   // 0: register-resident kernel when the utterance fits, 1: shared-memory kernel only
+static size_t g_fused_smem_max = 0;   // dynamic shared memory the kernel may use (opt-in limit minus its static part)
+static int g_fused_pref_bytes = 110 * 1024;   // preferred tile footprint: two CTAs per SM overlap each other's phases
+
+static size_t fused_smem_bytes(int tc) {
+  return (size_t)tc * kRowBytes + 2 * kFusedWarps * 8 + 4 * 8 + 3 * kC * 4 + (2 * tc + 16) * 4 + 64;
+}
+
+int resid_fused_cluster_size(int T) {
+  // smallest cluster whose per-CTA tile allows two CTAs per SM; otherwise the smallest that fits at all
+  for (int pass = 0; pass < 2; ++pass) {
+    const size_t lim = pass == 0 ? (size_t)g_fused_pref_bytes : g_fused_smem_max;
+    for (int cs = 1; cs <= 8; cs *= 2)
+      if (fused_smem_bytes((T + cs - 1) / cs) <= lim) return cs;
+  }
+  return 0;   // utterance too long for one cluster: use the streaming kernels
+}
+
+#ifdef SEPTFA_TIMELINE
+void resid_fused_dump_timeline() {
+  static unsigned long long h[32 * 128];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_fused_tl, sizeof(h));
+  for (int c = 0; c < 32; c += 1) {
+    const unsigned long long* t = h + c * 128;
+    printf("cta %2d: start->pdl %6llu total %6llu |", c, t[1] - t[0], t[2] - t[0]);
+    for (int it = 0; it < 9; ++it) {
+      const unsigned long long* u = t + 8 + it * 8;
+      if (u[0] == 0) break;
+      printf(" [top@%llu gates %llu tile %llu ph1 %llu xchg %llu ph2 %llu]", u[0] - t[0], u[1] - u[0], u[2] - u[1], u[3] - u[2], u[4] - u[3], u[5] - u[4]);
+    }
+    printf("\n");
+  }
+}
+#endif
+
+cudaError_t resid_fused_setup() {
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncAttributes fa{};
+  cudaError_t e = cudaFuncGetAttributes(&fa, k_resid_fused);
+  if (e != cudaSuccess) return e;
+  g_fused_smem_max = (size_t)optin - fa.sharedSizeBytes;
+  if (const char* s = getenv("SEPTFA_FUSED_TILE_KB")) g_fused_pref_bytes = atoi(s) * 1024;
+  if (const char* s = getenv("SEPTFA_FUSED_VARIANT")) g_fused_variant = atoi(s);
+  if (const char* s = getenv("SEPTFA_FUSED_PDL")) g_fused_pdl = atoi(s);
+  e = cudaFuncGetAttributes(&fa, k_resid_persist);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_resid_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_resid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_fused_smem_max);
+}
+
+
+// Clusters of `cs` CTAs of the persistent kernel the device keeps resident at once (cached per cluster size / footprint).
+static int persist_clusters(int cs, size_t smem) {
+  static int cache[9][2] = {};
+  static size_t cache_smem[9][2] = {};
+  const int slot = smem > 110 * 1024 ? 1 : 0;
+  if (cache[cs][slot] != 0 && cache_smem[cs][slot] == smem) return cache[cs][slot];
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cs * 1024);
+  cfg.blockDim = dim3(kPersistThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k_resid_persist, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[cs][slot] = n;
+  cache_smem[cs][slot] = smem;
+  return n;
+}
+
+template <typename K>
+static void launch_cluster(K kernel, const FusedParams& p, int nclusters, int cs, int threads, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nclusters * cs);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (g_use_pdl && g_fused_pdl) ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kernel, p);
+  ++g_launch_count;
+}
+
+// Returns false if the utterance does not fit a cluster (caller falls back to k_tf_gate + k_resid<0,1>).
+bool launch_resid_fused(const ResidParams& rp, const GateParams& gp, cudaStream_t st) {
+  if (!rp.racc_half) return false;
+  FusedParams p{};
+  p.w = rp.w; p.racc = reinterpret_cast<const __half*>(rp.racc); p.norm = rp.norm;
+  p.st_q = gp.st_q; p.s3 = gp.s3; p.c03 = gp.c03; p.rowsum = gp.rowsum; p.colsum = gp.colsum; p.tf = gp.tf;
+  p.T = rp.T; p.B = rp.B;
+  p.mode = rp.mode; p.g_a = rp.g_a; p.b_a = rp.b_a; p.st_w = rp.st_w;
+  if (g_fused_variant == 0 && rp.T <= 8 * kMaxTc) {
+    const int cs = std::min(8, (rp.T + 31) / 32);
+    p.Tc = (rp.T + cs - 1) / cs;
+    const size_t smem = 2 * (size_t)p.Tc * kRowBytes;
+    const int n_clusters = persist_clusters(cs, smem);
+    if (n_clusters > 0) {
+      launch_cluster(k_resid_persist, p, std::min(n_clusters, rp.B), cs, kPersistThreads, smem, st);
+      return true;
+    }
+  }
+  const int cs = resid_fused_cluster_size(rp.T);
+  if (cs == 0) return false;
+  p.Tc = (rp.T + cs - 1) / cs;
+  launch_cluster(k_resid_fused, p, rp.B, cs, kFusedThreads, fused_smem_bytes(p.Tc), st);
+  return true;
+}
+
+}  // namespace septfa

@@ -60,6 +60,7 @@ struct septfa_handle {
   cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
   cudaEvent_t hev_in[8] = {}, hev_done[8] = {};
   int host_chunks = 0;  // 0 = automatic
+  int fused_resid = 1;  // cluster-resident gate + residual kernel when the utterance fits a cluster
   float* hx_dev = nullptr; float* hout_dev = nullptr; float* hvad_dev = nullptr; void* hws = nullptr; void* hws_b = nullptr;
   float* hx_pin = nullptr; float* hout_pin = nullptr; float* hvad_pin = nullptr;
   size_t hcap_x = 0, hcap_out = 0, hcap_vad = 0, hcap_ws = 0, hcap_ws_b = 0;
@@ -311,8 +312,10 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
   h->ln_mode = c.apply_recursive_ln ? LN_RECURSIVE : (c.apply_residual_ln ? LN_RESIDUAL : LN_NONE);  // model.py:347-352
   build_keys(h);
   if (const char* e = getenv("SEPTFA_PDL")) g_use_pdl = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SEPTFA_FUSED_RESID")) h->fused_resid = atoi(e) ? 1 : 0;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, "cudaSetDevice failed"); }
   cudaError_t e = tc_gemm_setup();
+  if (e == cudaSuccess) e = resid_fused_setup();
   if (e != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, std::string("tc_gemm_setup: ") + cudaGetErrorString(e)); }
   *out = h;
   return 0;
@@ -363,6 +366,10 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "profile") == 0) {
     h->profile = value ? 1 : 0;
+    return 0;
+  }
+  if (std::strcmp(name, "fused_resid") == 0) {
+    h->fused_resid = value ? 1 : 0;
     return 0;
   }
   if (std::strcmp(name, "pdl") == 0) {
@@ -615,26 +622,22 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
 
     prof_mark(h, SEPTFA_PROF_GATE, st);
     GateParams gp{st_q, tc_dconv ? d.s3_tc : d.s3_ref, d.c03, ws.rowsum, colsum, d.tf, M, T, B, ws.ra, ws.rb, ws.gf, ws.gt};
-    launch_tf_gate(gp, st);
-    prof_mark(h, SEPTFA_PROF_RESID, st);
-
     ResidParams rp{};
     rp.w = ws.w; rp.norm = norm; rp.racc = ws.racc; rp.racc_half = half_io; rp.ra = ws.ra; rp.rb = ws.rb; rp.gf = ws.gf; rp.gt = ws.gt;
     rp.M = M; rp.T = T; rp.B = B; rp.mode = h->ln_mode; rp.st_v = st_v; rp.st_w = st_w;
-    if (h->ln_mode == LN_RECURSIVE) {         // output = ln_second(output + ln_first(output + residual)), model.py:347-348
-      rp.g_a = d.lf_g; rp.b_a = d.lf_b;
-      launch_resid_stats(rp, st);
+    if (h->ln_mode == LN_RECURSIVE) { rp.g_a = d.lf_g; rp.b_a = d.lf_b; }        // model.py:347-348
+    else if (h->ln_mode == LN_RESIDUAL) { rp.g_a = d.lm_g; rp.b_a = d.lm_b; }    // model.py:349-350
+    // gates + both residual GroupNorm steps in one cluster-resident kernel when an utterance fits a cluster
+    const bool fused = h->fused_resid && half_io && resid_fused_cluster_size(T) > 0;
+    prof_mark(h, fused ? SEPTFA_PROF_RESID : SEPTFA_PROF_GATE, st);
+    if (!(fused && launch_resid_fused(rp, gp, st))) {
+      launch_tf_gate(gp, st);
+      prof_mark(h, SEPTFA_PROF_RESID, st);
+      if (h->ln_mode != LN_NONE) launch_resid_stats(rp, st);
       launch_resid_apply(rp, st);
-      norm = StreamNorm{st_w, d.ls_g, d.ls_b, 1e-5f, inv_n};
-    } else if (h->ln_mode == LN_RESIDUAL) {   // output = output + ln(residual), model.py:349-350
-      rp.g_a = d.lm_g; rp.b_a = d.lm_b;
-      launch_resid_stats(rp, st);
-      launch_resid_apply(rp, st);
-      norm = StreamNorm{nullptr, nullptr, nullptr, 0.f, inv_n};
-    } else {                                  // output = output + residual, model.py:351-352
-      launch_resid_apply(rp, st);
-      norm = StreamNorm{nullptr, nullptr, nullptr, 0.f, inv_n};
     }
+    if (h->ln_mode == LN_RECURSIVE) norm = StreamNorm{st_w, d.ls_g, d.ls_b, 1e-5f, inv_n};   // output = ln_second(...)
+    else norm = StreamNorm{nullptr, nullptr, nullptr, 0.f, inv_n};
   }
   // output layer: PReLU -> GroupNorm -> conv (model.py:322-325,357)
   prof_mark(h, SEPTFA_PROF_OUTCONV, st);
@@ -664,6 +667,9 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   prof_mark(h, SEPTFA_PROF_EXPORT, st);
   launch_export(ws.S, ws.logits, gate, ws.w, ws.dcg, B, T, reinterpret_cast<float2*>(est_stft), mask, nullptr, logits_out, st);
   prof_mark(h, -1, st);
+#ifdef SEPTFA_TIMELINE
+  if (getenv("SEPTFA_FUSED_TL")) resid_fused_dump_timeline();
+#endif
   if (getenv("SEPTFA_TIMELINE")) {
     long long* dptr = nullptr;
     // the static buffer lives in the block loop above; re-fetch it through a second static handle

@@ -45,7 +45,7 @@ def run_golden(cuda_models, name, engine):
     st = meta["stride"]
     for i, kw in enumerate(meta["kws"]):
         out, vad, est = m(x, dict(kw) if kw else {})
-        assert m.last_launch_count > 100  # our kernels ran (no library / CPU path exists)
+        assert m.last_launch_count > 75  # our kernels ran (no library / CPU path exists)
         o = out.cpu().numpy()[..., ::st]
         ref = g[f"kw{i}_out"]
         assert o.shape == ref.shape
@@ -150,6 +150,37 @@ def test_engines_agree(cuda_models):
     assert (o7 - o0).abs().max().item() < 5e-4
     assert (v7 - v0).abs().max().item() < 1e-3
     assert sisdr_db(o0.cpu().numpy(), o7.cpu().numpy()) > 60
+
+
+@pytest.mark.parametrize("cfg_name", ["with", "without"])
+@pytest.mark.parametrize("B,L", [(3, 64000), (2, 30000), (5, 9000), (2, 100000), (1, 200000)])
+def test_fused_residual_kernel_equals_streaming_kernels(cuda_models, cfg_name, B, L):
+    """The cluster-resident gate + residual kernel (resid_fused.cu) against k_tf_gate + k_resid<0,1> on the
+    same buffers: same arithmetic, different summation grouping of the GroupNorm statistics, so they agree
+    to the fp16 operand noise level. Also bit-reproducible run to run (no atomics in the fused kernel)."""
+    args = synth.CONFIG_WITH_VAD if cfg_name == "with" else synth.CONFIG_WITHOUT_VAD
+    m = cuda_models(args, 33, 0)
+    kw = dict(synth.DEFAULT_INFERENCE_KW) if cfg_name == "with" else {}
+    x = torch.from_numpy(synth.make_mixtures(B, L, 777)).cuda()
+    try:
+        m.set_option("fused_resid", 0)
+        o0, v0, _ = m(x, kw)
+        n0 = m.last_launch_count
+        m.set_option("fused_resid", 1)
+        o1, v1, _ = m(x, kw)
+        n1 = m.last_launch_count
+        o2, v2, _ = m(x, kw)
+    finally:
+        m.set_option("fused_resid", 1)
+    assert n1 < n0, (n0, n1)            # the fused kernel really replaced three launches per block
+    assert (o1 - o0).abs().max().item() < 5e-4
+    assert sisdr_db(o1.cpu().numpy(), o0.cpu().numpy()) > 60
+    if v0.numel():
+        # two fp16-noisy evaluations of the same probabilities: each is within 1e-3 of the fp32 reference
+        # (test_against_oracle_seeded), so their mutual distance is bounded by 2e-3
+        assert (v1.float() - v0.float()).abs().max().item() < 2e-3
+    if L >= 32768:
+        assert torch.equal(o1, o2)
 
 
 def test_batch_invariance_and_determinism(cuda_models):
