@@ -25,7 +25,7 @@ constexpr int kAChunkBytes = kTileM * 128;  // one K-chunk (64 halves = 128 B) o
 constexpr int kStages = 2;
 constexpr int kThreads = 320;
 constexpr int kAuxBytes = 4096;
-constexpr int kDconvWBytes = 512 * 16 + 512 * 4;  // MODE 1: folded depthwise taps staged in shared memory
+constexpr int kDconvWBytes = 2 * 256 * 16 + 256 * 8;  // MODE 1: folded depthwise taps staged in shared memory (10 KB)
 constexpr int kStgPitch = 36;               // floats per staged row (32 + 4 pad, 16 B aligned)
 
 struct TcParams {
@@ -37,7 +37,7 @@ struct TcParams {
   // MODE 2 prologue
   float slope_o; const Stat2* st_o; const float* g_o; const float* b_o;
   // MODE 1 prologue
-  const Stat2* st_p; const float* g1; const float* be1; const float4* w2b; const float4* w2f; const float* c2f;
+  const Stat2* st_p; const float4* wtab; const float* bog;
   float slope2; int dil; Stat2* st_q;
   // epilogue
   const float* bias; float slope;
@@ -65,7 +65,8 @@ __device__ __forceinline__ float4 ld_half4(const __half* p) {   // 4 consecutive
 
 // H16: the activation tensor exchanged with the neighbouring contraction (conv1's output p = dconv's input; dconv's
 // output racc) is stored as fp16 instead of fp32.
-template <int MODE, bool H16>
+// AMAX (MODE 1): the PReLU slope of the depthwise stage is <= 1, so PReLU(x) = max(x, a x); otherwise min(x, a x).
+template <int MODE, bool H16, bool AMAX = true>
 __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   constexpr int NT = (MODE == 2) ? 192 : 256;
   constexpr int KDIM = (MODE == 1) ? 512 : 256;
@@ -92,8 +93,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   float* seg_acc = reinterpret_cast<float*>(tab_b + kMaxSegs);
   float* rs_x = seg_acc + 2 * kMaxSegs;  // [128] row-sum exchange between the two column halves
   float* slots = rs_x + kTileM;          // [8 warps][4] per-warp statistics partials
-  float4* w2f_s = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + kAuxBytes);  // MODE 1: [512] folded taps
-  float* c2f_s = reinterpret_cast<float*>(w2f_s + kH);                                       // MODE 1: [512]
+  // MODE 1: folded depthwise taps in pair order, [chunk 8][pair 4][c8 8] each (pack_dconv_taps)
+  float4* wA_s = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + kAuxBytes);   // {wx_a, wx_b, wy_a, wy_b}
+  float4* wB_s = wA_s + 256;                                                                  // {wz_a, wz_b, sw_a, sw_b}
+  float2* wC_s = reinterpret_cast<float2*>(wB_s + 256);                                       // {c2f_a, c2f_b}
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * kTileM;
@@ -116,20 +119,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   if (warp == 9) tmem_alloc(tmem_slot, 256);
   pdl_launch_dependents();
   if (MODE == 1) {
-    // folded depthwise taps (static weights): staged before waiting for the previous kernel
-    // staged as [chunk j][output o][lane chunk c8] so that the 8 lane groups of a warp read consecutive words
-    for (int i = threadIdx.x; i < kH; i += kThreads) {
-      const int jj = i >> 6, cc = (i >> 3) & 7, oo = i & 7, d = (jj * 8 + oo) * 8 + cc;
-      w2f_s[d] = __ldg(p.w2f + i);
-      c2f_s[d] = __ldg(p.c2f + i);
-    }
+    // folded depthwise taps (static weights): staged before waiting for the previous kernel; the global image already
+    // has the shared-memory layout (consecutive c8 = consecutive 16 B: conflict-free LDS.128 across a warp)
+    for (int i = threadIdx.x; i < kDconvWBytes / 16; i += kThreads) wA_s[i] = __ldg(p.wtab + i);
   }
   pdl_wait();   // everything below reads what earlier kernels of the chain wrote
   {
     const double inv_n = 1.0 / ((double)kC * p.T);
     for (int i = threadIdx.x; i < nseg; i += kThreads) {
       if (MODE == 1) {
-        tab_a[i] = stat_mean_rstd(p.st_p + b_first + i, inv_n, 1e-8f);
+        const float2 mr = stat_mean_rstd(p.st_p + b_first + i, inv_n, 1e-8f);
+        tab_a[i] = mr;
+        tab_b[i] = make_float2(mr.x, 1.0f / mr.y);   // (mean, 1 / rstd): the input value that normalises to zero
       } else {
         tab_a[i] = p.norm.gamma != nullptr ? stat_mean_rstd(p.norm.st + b_first + i, p.norm.inv_n, p.norm.eps)
                                            : make_float2(0.f, 1.f);
@@ -233,107 +234,150 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
       }
     } else if (MODE == 1) {
       // dconv + res_out: q channels 64j + 8*c8 .. +7  <-  in-channels g0 .. g0+3 (out-channel o reads in-channel o/2).
-      // GroupNorm reg1 is folded into the taps (w2f = w * gamma, c2f = b2 + beta * sum(w)):
-      //   q = PReLU(c2f + rstd * (sum_k w2f[k] p[t+(k-1)d] - mean * sum_k w2f[k]))      (all taps inside the utterance)
-      // A K-chunk is produced in two steps of 2 row groups; the global loads of step st+1 are issued before step st is
-      // computed (register double buffer), so the round trip to L2/HBM overlaps the arithmetic instead of being paid
-      // twice per chunk (measured: 5700 -> cycles per chunk).
+      // GroupNorm reg1 is folded into the taps (w2f = w * gamma, sw = sum_k w2f, c2f = b2 + beta * sum_k w):
+      //   q = PReLU(rstd * sum_k w2f[k] p[t+(k-1)d] + (c2f - rstd * mean * sw))
+      // evaluated on PAIRS of outputs with the packed fp32 pipe (FFMA2): a pair is the two outputs of equal parity of
+      // two neighbouring input channels, so its three taps multiply the float2 that one half2 -> float2 conversion of
+      // the input yields; the tap table is staged in that pair order (see pack_dconv_taps in septfa_abi.cu).
+      // PReLU is max(x, a x) for a <= 1 (min for a > 1): exact, no predicate.
+      // Zero padding: the reference pads the NORMALISED signal, so a tap outside the utterance must contribute 0. The
+      // folded formula gives exactly that when the missing input is replaced by the value that normalises to zero,
+      // p0[c] = mean - (beta[c] / gamma[c]) / rstd - one FFMA2 per channel pair and no separate code path for the
+      // frames within `dil` of an utterance edge (a quarter of all rows at these dilations).
+      // The global loads of step st+1 (two rows of the next half chunk) are issued before step st is computed.
       using RawT = typename std::conditional<H16, uint2, float4>::type;
-      struct Step { RawT xm[2], xc[2], xp[2]; int flg[2]; };   // flg: segment | (t-d) ok << 8 | (t+d) ok << 9 | row valid << 10
+      struct Step { RawT xm[2], xc[2], xp[2]; };
       auto ldraw = [](const void* base, int64_t off) -> RawT {
         if constexpr (H16) return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + off));
         else return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
       };
-      auto to4 = [](const RawT& v, float (&o)[4]) {
+      auto to_pairs = [](const RawT& v, float2 (&o)[2]) {
         if constexpr (H16) {
-          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-          o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+          o[0] = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+          o[1] = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
         } else {
-          o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+          o[0] = make_float2(v.x, v.y);
+          o[1] = make_float2(v.z, v.w);
         }
       };
-      auto issue = [&](int st, Step& sp) {
-        const int jj = st >> 1, half = st & 1, g0 = jj * 32 + c8 * 4;
+      // the four rows this lane owns in every chunk: segment | (t-d) inside << 8 | (t+d) inside << 9 | row valid << 10
+      int rflag[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rl = it * 32 + warp * 4 + rg;
+        rflag[it] = 0;
+        if (rl < nrows) {
+          const int row = r0 + rl, sg = smap.seg(row), t = smap.frame(row, sg);
+          rflag[it] = sg | 1024 | (t - p.dil >= 0 ? 256 : 0) | (t + p.dil < p.T ? 512 : 0);
+        }
+      }
+      const int64_t lane_off = (int64_t)(r0 + warp * 4 + rg) * kC + c8 * 4;   // element offset of row it = 0, chunk 0
+      const int dil_off = p.dil * kC;
+      const float2 slope2 = make_float2(p.slope2, p.slope2);
+      // statistics of q per row slot (a lane owns the same four rows in every chunk); routed to the utterance
+      // accumulators once per tile. Rows past the end of the tensor run through the arithmetic like any other (their
+      // inputs read as zero; row m of A only reaches row m of the accumulator, which the epilogue never stores) and are
+      // dropped here.
+      float2 accS[4], accQ[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) accS[it] = accQ[it] = make_float2(0.f, 0.f);
+      RawT zero_raw;
+      if constexpr (H16) zero_raw = make_uint2(0u, 0u); else zero_raw = make_float4(0.f, 0.f, 0.f, 0.f);
+
+      auto issue = [&](int jj, int half, Step& sp) {
 #pragma unroll
         for (int i2 = 0; i2 < 2; ++i2) {
-          const int rl = (half * 2 + i2) * 32 + warp * 4 + rg;
-          sp.flg[i2] = 0;
-          if (rl < nrows) {
-            const int row = r0 + rl;
-            const int sg = smap.seg(row);
-            const int t = smap.frame(row, sg);
-            int f = sg | 1024;
-            const int64_t off = (int64_t)row * kC + g0;
-            sp.xc[i2] = ldraw(p.in, off);
-            if (t - p.dil >= 0) { f |= 256; sp.xm[i2] = ldraw(p.in, off - (int64_t)p.dil * kC); }
-            if (t + p.dil < p.T) { f |= 512; sp.xp[i2] = ldraw(p.in, off + (int64_t)p.dil * kC); }
-            sp.flg[i2] = f;
-          }
+          const int f = half ? rflag[2 + i2] : rflag[i2];
+          const int64_t off = lane_off + ((half * 2 + i2) * 32 * kC + jj * 32);
+          sp.xc[i2] = (f & 1024) ? ldraw(p.in, off) : zero_raw;
+          sp.xm[i2] = (f & 256) ? ldraw(p.in, off - dil_off) : zero_raw;
+          sp.xp[i2] = (f & 512) ? ldraw(p.in, off + dil_off) : zero_raw;
         }
       };
-      auto compute = [&](int st, const Step& sp) {
-        const int jj = st >> 1, half = st & 1, g0 = jj * 32 + c8 * 4;
+      auto compute = [&](int jj, int half, const Step& sp) {
         uint8_t* a_tile = smem + (jj % kStages) * STAGE;
-        const float4* wf = w2f_s + jj * 64 + c8;   // folded taps of this lane's 8 output channels: wf[o * 8]
-        const float* cf = c2f_s + jj * 64 + c8;
+        const float4* WA = wA_s + jj * 32 + c8;   // [chunk][pair][c8]: {wx_a, wx_b, wy_a, wy_b}
+        const float4* WB = wB_s + jj * 32 + c8;   //                    {wz_a, wz_b, sw_a, sw_b}
+        const float2* WC = wC_s + jj * 32 + c8;   //                    {c2f_a, c2f_b}
+        float2 vm[2][2], vc[2][2], vp[2][2], rs2[2], nr2[2];
+#pragma unroll
+        for (int i2 = 0; i2 < 2; ++i2) {
+          const int f = half ? rflag[2 + i2] : rflag[i2];
+          const float2 mr = tab_a[f & 255];
+          const float nr = -mr.x * mr.y;
+          rs2[i2] = make_float2(mr.y, mr.y);
+          nr2[i2] = make_float2(nr, nr);
+          to_pairs(sp.xc[i2], vc[i2]);
+          to_pairs(sp.xm[i2], vm[i2]);
+          to_pairs(sp.xp[i2], vp[i2]);
+          if ((f & 768) != 768) {   // a tap outside the utterance: substitute the input that normalises to zero
+            const float2 mi = tab_b[f & 255];   // (mean, 1 / rstd)
+            const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bog + jj * 32 + c8 * 4));
+            const float2 ni = make_float2(-mi.y, -mi.y), mm = make_float2(mi.x, mi.x);
+            const float2 pad0 = __ffma2_rn(ni, make_float2(bg.x, bg.y), mm), pad1 = __ffma2_rn(ni, make_float2(bg.z, bg.w), mm);
+            if (!(f & 256)) { vm[i2][0] = pad0; vm[i2][1] = pad1; }
+            if (!(f & 512)) { vp[i2][0] = pad0; vp[i2][1] = pad1; }
+          }
+        }
+        uint32_t pk[2][4];
+#pragma unroll
+        for (int gp = 0; gp < 2; ++gp) {
+          float2 P[2][2];
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            const float4 wa = WA[(gp * 2 + par) * 8], wb = WB[(gp * 2 + par) * 8];
+            const float2 cc = WC[(gp * 2 + par) * 8];
+#pragma unroll
+            for (int i2 = 0; i2 < 2; ++i2) {
+              float2 conv = __fmul2_rn(make_float2(wa.x, wa.y), vm[i2][gp]);
+              conv = __ffma2_rn(make_float2(wa.z, wa.w), vc[i2][gp], conv);
+              conv = __ffma2_rn(make_float2(wb.x, wb.y), vp[i2][gp], conv);
+              const float2 k0 = __ffma2_rn(nr2[i2], make_float2(wb.z, wb.w), cc);
+              const float2 x = __ffma2_rn(rs2[i2], conv, k0);
+              const float2 ax = __fmul2_rn(slope2, x);
+              float2 q;
+              if constexpr (AMAX) q = make_float2(fmaxf(x.x, ax.x), fmaxf(x.y, ax.y));
+              else q = make_float2(fminf(x.x, ax.x), fminf(x.y, ax.y));
+              accS[half * 2 + i2] = __fadd2_rn(accS[half * 2 + i2], q);
+              accQ[half * 2 + i2] = __ffma2_rn(q, q, accQ[half * 2 + i2]);
+              P[par][i2] = q;
+            }
+          }
+#pragma unroll
+          for (int i2 = 0; i2 < 2; ++i2) {
+            pk[i2][gp * 2] = pack_half2(P[0][i2].x, P[1][i2].x);
+            pk[i2][gp * 2 + 1] = pack_half2(P[0][i2].y, P[1][i2].y);
+          }
+        }
 #pragma unroll
         for (int i2 = 0; i2 < 2; ++i2) {
           const int rl = (half * 2 + i2) * 32 + warp * 4 + rg;
-          float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (sp.flg[i2] & 1024) {
-            const int sg = sp.flg[i2] & 255;
-            const bool okm = sp.flg[i2] & 256, okp = sp.flg[i2] & 512;
-            const float2 mr = tab_a[sg];
-            float vm[4] = {0.f, 0.f, 0.f, 0.f}, vc[4], vp[4] = {0.f, 0.f, 0.f, 0.f};
-            to4(sp.xc[i2], vc);
-            if (okm) to4(sp.xm[i2], vm);
-            if (okp) to4(sp.xp[i2], vp);
-            if (okm && okp) {
-              const float nmu = -mr.x;
-#pragma unroll
-              for (int o = 0; o < 8; ++o) {
-                const float4 w = wf[o * 8];
-                const float conv = fmaf(w.z, vp[o >> 1], fmaf(w.y, vc[o >> 1], w.x * vm[o >> 1]));
-                q[o] = prelu(fmaf(mr.y, fmaf(nmu, w.w, conv), cf[o * 8]), p.slope2);
-              }
-            } else {
-              // frames within `dil` of an utterance edge: taps outside are zero padding of the *normalised* signal
-              const float4 ga = __ldg(reinterpret_cast<const float4*>(p.g1 + g0));
-              const float4 be = __ldg(reinterpret_cast<const float4*>(p.be1 + g0));
-              const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const float hm = okm ? ((vm[g] - mr.x) * mr.y) * gam[g] + bet[g] : 0.f;
-                const float hc = ((vc[g] - mr.x) * mr.y) * gam[g] + bet[g];
-                const float hp = okp ? ((vp[g] - mr.x) * mr.y) * gam[g] + bet[g] : 0.f;
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const float4 w = __ldg(p.w2b + 2 * (g0 + g) + e);
-                  q[2 * g + e] = prelu(w.w + w.x * hm + w.y * hc + w.z * hp, p.slope2);
-                }
-              }
-            }
-            qstat.add(sg, q, seg_acc);
-          }
-          const uint4 pk = make_uint4(pack_half2(q[0], q[1]), pack_half2(q[2], q[3]), pack_half2(q[4], q[5]),
-                                      pack_half2(q[6], q[7]));
-          *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
+          *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = make_uint4(pk[i2][0], pk[i2][1], pk[i2][2], pk[i2][3]);
         }
       };
       Step sa, sb;
-      issue(0, sa);
+      issue(0, 0, sa);
 #pragma unroll 1
       for (int j = 0; j < NCH; ++j) {
         const int s = j % kStages, u = j / kStages;
-        issue(2 * j + 1, sb);
+        issue(j, 1, sb);
         if (u > 0) mbar_wait(empty + s, (u - 1) & 1, 400 + j);
-        compute(2 * j, sa);
-        if (j + 1 < NCH) issue(2 * j + 2, sa);
-        compute(2 * j + 1, sb);
+        compute(j, 0, sa);
+        if (j + 1 < NCH) issue(j + 1, 0, sa);
+        compute(j, 1, sb);
         fence_proxy_async();
         mbar_arrive(full_a + s);
         TLG(1 + j);
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (rflag[it] & 1024) {
+          const int sg = rflag[it] & 255;
+          const float sv = accS[it].x + accS[it].y, qv = accQ[it].x + accQ[it].y;
+          if (sg == 0) { qstat.s0 += sv; qstat.q0 += qv; }
+          else if (sg == 1) { qstat.s1 += sv; qstat.q1 += qv; }
+          else { atomicAdd(seg_acc + 2 * sg, sv); atomicAdd(seg_acc + 2 * sg + 1, qv); }
+        }
       }
     } else
     for (int j = 0; j < NCH; ++j) {
@@ -509,22 +553,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   if (sdst != nullptr && blockIdx.y == 0) seg_stats_commit(slots, 8, seg_acc, nseg, sdst + b_first);
 }
 
-template <int MODE, bool H16>
+template <int MODE, bool H16, bool AMAX = true>
 void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
   constexpr int NT = (MODE == 2) ? 192 : 256;
   constexpr int smem = kStages * (MODE == 2 ? 2 : 1) * (kAChunkBytes + NT * 128) + kAuxBytes + 1024 + (MODE == 1 ? kDconvWBytes : 0);
   dim3 grid((p.M + kTileM - 1) / kTileM, ntiles_n);
-  launch_k(k_tc_gemm<MODE, H16>, grid, dim3(kThreads), smem, st, true, p);
+  launch_k(k_tc_gemm<MODE, H16, AMAX>, grid, dim3(kThreads), smem, st, true, p);
 }
 
 }  // namespace
 
 long long* g_tl_conv1 = nullptr;  // bring-up timeline of one conv1 launch (SEPTFA_TIMELINE)
 
-template <int MODE, bool H16>
+template <int MODE, bool H16, bool AMAX = true>
 cudaError_t setup_one(int smem) {
-  cudaFuncSetAttribute(k_tc_gemm<MODE, H16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  return cudaFuncSetAttribute(k_tc_gemm<MODE, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_tc_gemm<MODE, H16, AMAX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return cudaFuncSetAttribute(k_tc_gemm<MODE, H16, AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 cudaError_t tc_gemm_setup() {
@@ -536,6 +580,8 @@ cudaError_t tc_gemm_setup() {
   if ((e = setup_one<0, true>(s0)) != cudaSuccess) return e;
   if ((e = setup_one<1, false>(s0 + kDconvWBytes)) != cudaSuccess) return e;
   if ((e = setup_one<1, true>(s0 + kDconvWBytes)) != cudaSuccess) return e;
+  if ((e = setup_one<1, false, false>(s0 + kDconvWBytes)) != cudaSuccess) return e;
+  if ((e = setup_one<1, true, false>(s0 + kDconvWBytes)) != cudaSuccess) return e;
   return setup_one<2, false>(s2);
 }
 
@@ -553,11 +599,15 @@ void launch_tc_dconv(const DconvParams& c, cudaStream_t st) {
   TcParams p{};
   p.M = c.M; p.T = c.T; p.B = c.B;
   p.w_img = c.w_img; p.in = c.p_in;
-  p.st_p = c.st_p; p.g1 = c.g1; p.be1 = c.be1; p.w2b = c.w2b; p.w2f = c.w2f; p.c2f = c.c2f;
+  p.st_p = c.st_p; p.wtab = c.wtab; p.bog = c.bog;
   p.slope2 = c.slope2; p.dil = c.dil; p.st_q = c.st_q;
   p.out = c.racc; p.out_stride = kC; p.rowsum = c.rowsum; p.colsum = c.colsum;
   p.dbg = c.dbg;
-  if (c.half_io) launch_mode<1, true>(p, 1, st); else launch_mode<1, false>(p, 1, st);
+  if (c.slope2 <= 1.f) {
+    if (c.half_io) launch_mode<1, true, true>(p, 1, st); else launch_mode<1, false, true>(p, 1, st);
+  } else {
+    if (c.half_io) launch_mode<1, true, false>(p, 1, st); else launch_mode<1, false, false>(p, 1, st);
+  }
 }
 
 void launch_tc_outconv(const OutConvParams& c, cudaStream_t st) {

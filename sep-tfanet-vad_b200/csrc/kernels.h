@@ -54,6 +54,8 @@ struct DconvParams {
   Stat2* st_q;         // [B]
   long long* dbg;      // optional timeline buffer (bring-up only), nullptr otherwise
   int half_io;         // p and racc are fp16
+  const float4* wtab;  // tcgen05 engine: the folded taps in pair order, 640 float4 (septfa_abi.cu: dconv tap table)
+  const float* bog;    // tcgen05 engine: [256] beta1 / gamma1 (zero-padding substitute, see gemm_tc.cu)
 };
 
 // TCN.output (model/model.py:322-325,357): logits = Wo GN(PReLU(y)) + bo, N = 514 padded to 576.

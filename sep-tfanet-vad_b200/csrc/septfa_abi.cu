@@ -27,6 +27,7 @@ struct KeySpec {
 struct DevBlock {
   const __half* w1_img; const float* w1_t; const float* b1; const float* b1f; float a1; const float* g1; const float* be1;
   const float4* w2b; const float4* w2f; const float* c2f; float a2; int dil;
+  const float4* wtab; const float* bog;   // tcgen05 dconv producer: pair-ordered tap table, beta1 / gamma1
   const __half* w3_img; const float* w3_t; const float* s3_tc; const float* s3_ref; const float* c03;
   TfParams tf;
   const float* lf_g; const float* lf_b; const float* ls_g; const float* ls_b;  // recursive
@@ -465,6 +466,41 @@ int septfa_commit_weights(septfa_handle* h) {
       }
       if (upload(h, w2b, &d.w2b) || upload(h, w2f, &d.w2f) || upload(h, c2f, &d.c2f)) return SEPTFA_E_CUDA;
       d.a2 = T_(h, p + ".nonlinearity2.weight")[0];
+      // tcgen05 producer (gemm_tc.cu, MODE 1): the same folded taps arranged for packed pairs. Lane chunk c8 of K-chunk j
+      // produces outputs 64 j + 8 c8 + e; pair (gp, par) = outputs e = 4 gp + par and e + 2, i.e. the equal-parity outputs
+      // of input channels 2 gp and 2 gp + 1. Tables [j][pair][c8]: A = {wx_a, wx_b, wy_a, wy_b}, B = {wz_a, wz_b, sw_a,
+      // sw_b}, C = {c2f_a, c2f_b}. Zero padding is realised by substituting the input that normalises to zero,
+      // mean - (beta / gamma) / rstd, so gamma must not vanish: |gamma| is clamped to 1e-20 (the folded tap w * gamma and
+      // the substitute then still multiply to the exact -w * beta / rstd).
+      {
+        std::vector<float> tab(2560), bog(kC);
+        auto gsafe = [&](int c) { const double g = g1v[c]; return std::fabs(g) < 1e-20 ? (g < 0 ? -1e-20 : 1e-20) : g; };
+        for (int c = 0; c < kC; ++c) bog[c] = (float)((double)be1v[c] / gsafe(c));
+        for (int j = 0; j < 8; ++j)
+          for (int pr = 0; pr < 4; ++pr)
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const int idx = (j * 4 + pr) * 8 + c8, gp = pr >> 1, par = pr & 1;
+              const int oa = 64 * j + 8 * c8 + 4 * gp + par, ob = oa + 2;
+              double f[2][3], sw[2], cf[2];
+              const int oo[2] = {oa, ob};
+              for (int e = 0; e < 2; ++e) {
+                const int o = oo[e];
+                const double g = gsafe(o / 2), be = be1v[o / 2];
+                for (int k = 0; k < 3; ++k) f[e][k] = w[o * 3 + k] * g;
+                sw[e] = f[e][0] + f[e][1] + f[e][2];
+                cf[e] = (double)b2[o] + be * (w[o * 3] + w[o * 3 + 1] + w[o * 3 + 2]);
+              }
+              float* A = tab.data() + idx * 4;
+              float* Bt = tab.data() + 1024 + idx * 4;
+              float* Ct = tab.data() + 2048 + idx * 2;
+              A[0] = (float)f[0][0]; A[1] = (float)f[1][0]; A[2] = (float)f[0][1]; A[3] = (float)f[1][1];
+              Bt[0] = (float)f[0][2]; Bt[1] = (float)f[1][2]; Bt[2] = (float)sw[0]; Bt[3] = (float)sw[1];
+              Ct[0] = (float)cf[0]; Ct[1] = (float)cf[1];
+            }
+        const float* tptr = nullptr;
+        if (upload(h, tab, &tptr) || upload(h, bog, &d.bog)) return SEPTFA_E_CUDA;
+        d.wtab = reinterpret_cast<const float4*>(tptr);
+      }
     }
     // res_out 512 -> 256 with GroupNorm reg2 folded in:  r = rstd2 * (W3g q - mu2 * s3) + c03
     {
@@ -611,7 +647,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
 
     prof_mark(h, SEPTFA_PROF_DCONV, st);
     DconvParams dc{ws.p, st_p, d.g1, d.be1, d.w2b, d.w2f, d.c2f, d.a2, d.dil, M, T, B, d.w3_img, d.w3_t, ws.racc, ws.rowsum, colsum, st_q,
-                   nullptr, half_io};
+                   nullptr, half_io, d.wtab, d.bog};
     long long*& s_dbg = septfa_dbg_ptr;   // bring-up timeline (SEPTFA_TIMELINE=1): block 5 of the persistent dconv kernel
     if (i == 5 && getenv("SEPTFA_TIMELINE")) {
       if (!s_dbg) { cudaMalloc(reinterpret_cast<void**>(&s_dbg), 8 * 256 * sizeof(long long)); }
