@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S
   tw[tid + 256] = __ldg(twiddle + tid + 256);
   const float w_lo = __ldg(window + tid), w_hi = __ldg(window + kHop + tid);
   const float sc = 1.f / (float)kNfft;
+  const float inv_env = 1.f / (w_hi * w_hi + w_lo * w_lo), inv_env_tail = 1.f / (w_hi * w_hi);   // one division per thread, not per sample
   pdl_launch_dependents();
   pdl_wait();
   float* out0 = out + ((int64_t)b * 2) * L;
@@ -172,13 +173,13 @@ __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S
         const int f = j + 64 * r;  // 0..255
         if (f >= 1) {
           const float2 sv = __ldg(S + row * kBins + f);
-          const float m0 = sigmoidf_acc(__ldg(lr + f)) * g0, m1 = sigmoidf_acc(__ldg(lr + kBins + f)) * g1;
+          const float m0 = sigmoidf_fast(__ldg(lr + f)) * g0, m1 = sigmoidf_fast(__ldg(lr + kBins + f)) * g1;
           const float a0 = sv.x * m0, b0 = sv.y * m0, a1 = sv.x * m1, b1 = sv.y * m1;
           bg[fft_idx(f)] = make_float2(a0 - b1, b0 + a1);               // E0[f] + i E1[f]
           bg[fft_idx(kNfft - f)] = make_float2(a0 + b1, a1 - b0);       // conj(E0[f]) + i conj(E1[f])
         } else {
           const float2 sv = __ldg(S + row * kBins + 256);
-          const float m0 = sigmoidf_acc(__ldg(lr + 256)) * g0, m1 = sigmoidf_acc(__ldg(lr + kBins + 256)) * g1;
+          const float m0 = sigmoidf_fast(__ldg(lr + 256)) * g0, m1 = sigmoidf_fast(__ldg(lr + kBins + 256)) * g1;
           bg[fft_idx(0)] = make_float2(0.f, 0.f);                       // DC bin is zero
           bg[fft_idx(256)] = make_float2(sv.x * m0, sv.x * m1);         // irfft ignores the imaginary part of Nyquist
         }
@@ -203,9 +204,8 @@ __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S
         }
         const int64_t o = (int64_t)(tq - 1) * kHop + n;
         if (o < L) {
-          const float env = w_hi * w_hi + w_lo * w_lo;
-          out0[o] = (prev.x + first.x) / env;
-          out1[o] = (prev.y + first.y) / env;
+          out0[o] = (prev.x + first.x) * inv_env;
+          out1[o] = (prev.y + first.y) * inv_env;
         }
       }
     }
@@ -216,9 +216,8 @@ __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S
     if (tbase + ql == T - 1 && T - 1 < j0 + kIstftBlocks) {
       const int64_t o = (int64_t)(T - 1) * kHop + n;
       if (o < L) {
-        const float env = w_hi * w_hi;
-        out0[o] = second.x / env;
-        out1[o] = second.y / env;
+        out0[o] = second.x * inv_env_tail;
+        out1[o] = second.y * inv_env_tail;
       }
     }
     carry[n] = second;   // read only by the same thread in the next round
@@ -260,7 +259,7 @@ __global__ void __launch_bounds__(256) k_export(const float2* __restrict__ S, co
     const int f = f0 + i, t = t0 + tx;
     if (t < T && f < kBins) {
       const float lg = tl[tx][i];
-      const float m = sigmoidf_acc(lg);
+      const float m = sigmoidf_fast(lg);
       const int64_t o = (((int64_t)b * 2 + s) * kBins + f) * T + t;
       if (mask != nullptr) mask[o] = m;
       if (logits_out != nullptr) logits_out[o] = lg;  // [B, 514, T] with n = s*257 + f

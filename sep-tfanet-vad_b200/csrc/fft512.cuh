@@ -13,8 +13,9 @@ constexpr int kFftPad = 512 + 64;  // float2 elements per padded FFT buffer
 __device__ __forceinline__ int fft_idx(int i) { return i + (i >> 3); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract on the packed fp32 pipe (FADD2, sm_100): half the instructions of two scalar adds
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 
 // 8-point DFT in registers (decimation in frequency, natural-order output). INVERSE conjugates the roots.
 template <bool INVERSE>
@@ -38,8 +39,13 @@ __device__ __forceinline__ void dft8(float2 (&a)[8]) {
 }
 
 // In-place (natural order in, natural order out) FFT of the padded buffer `buf` (kFftPad float2) by the 64 threads
-// j = 0..63 of one group; tw[i] = exp(-2*pi*i*n/512), n < 512. ALL threads of the CTA must call it together
-// (block barriers inside); the caller's writes of buf must be followed by a barrier, which pass 0 provides.
+// j = 0..63 of one group. `tw` is the per-pass twiddle table of make_twiddles (512 float2):
+//   tw[(r-1)*8 + k]       = exp(-2 pi i r k / 64),  k < 8   (pass 1)
+//   tw[64 + (r-1)*64 + k] = exp(-2 pi i r k / 512), k < 64  (pass 2)
+// so that the lanes of a warp (consecutive k) read consecutive words: the natural exp(-2 pi i n / 512) table read at
+// r * step was an up-to-8-way bank conflict (25 M conflicts per iSTFT launch).
+// ALL threads of the CTA must call it together (block barriers inside); the caller's writes of buf must be followed
+// by a barrier, which pass 0 provides.
 template <bool INVERSE>
 __device__ __forceinline__ void fft512_r8(float2* buf, const float2* tw, int j) {
 #pragma unroll
@@ -52,10 +58,11 @@ __device__ __forceinline__ void fft512_r8(float2* buf, const float2* tw, int j) 
 #pragma unroll
     for (int r = 0; r < 8; ++r) u[r] = buf[fft_idx(j + 64 * r)];
     if (pass > 0) {
-      const int step = k * (64 / ns);  // exp(-2*pi*i*r*k/(8*ns)) = tw[r * k * 512 / (8 ns)]
+      const float2* twp = pass == 1 ? tw + k : tw + 64 + k;
+      const int pitch = pass == 1 ? 8 : 64;
 #pragma unroll
       for (int r = 1; r < 8; ++r) {
-        float2 w = tw[r * step];
+        float2 w = twp[(r - 1) * pitch];
         if (INVERSE) w.y = -w.y;
         u[r] = cmul(u[r], w);
       }
