@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S
         }
       }
     }
-    fft512_r8<true>(buf[grp], tw, j);
+    fft512_r8<true>(buf[grp], tw, j, grp);
     // output blocks of this round: block t-1 = second half of frame t-1 + first half of frame t, thread = sample n
     const int n = tid;
 #pragma unroll

@@ -38,23 +38,28 @@ __device__ __forceinline__ void dft8(float2 (&a)[8]) {
   a[3] = cadd(c6, c7); a[7] = csub(c6, c7);
 }
 
+// Barrier among the 64 threads (two warps) of FFT group `grp` only: the four groups of a CTA work on independent
+// buffers, so they need not wait for each other between passes (named barriers 1..4; 0 is __syncthreads).
+__device__ __forceinline__ void group_barrier(int grp) { asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory"); }
+
 // In-place (natural order in, natural order out) FFT of the padded buffer `buf` (kFftPad float2) by the 64 threads
 // j = 0..63 of one group. `tw` is the per-pass twiddle table of make_twiddles (512 float2):
 //   tw[(r-1)*8 + k]       = exp(-2 pi i r k / 64),  k < 8   (pass 1)
 //   tw[64 + (r-1)*64 + k] = exp(-2 pi i r k / 512), k < 64  (pass 2)
 // so that the lanes of a warp (consecutive k) read consecutive words: the natural exp(-2 pi i n / 512) table read at
 // r * step was an up-to-8-way bank conflict (25 M conflicts per iSTFT launch).
-// ALL threads of the CTA must call it together (block barriers inside); the caller's writes of buf must be followed
-// by a barrier, which pass 0 provides.
+// ALL threads of the CTA must call it together: the passes synchronise per group, the final barrier is block-wide
+// (callers read other groups' buffers afterwards). The caller's writes of buf - by the group's own threads - are
+// ordered by the barrier of pass 0.
 template <bool INVERSE>
-__device__ __forceinline__ void fft512_r8(float2* buf, const float2* tw, int j) {
+__device__ __forceinline__ void fft512_r8(float2* buf, const float2* tw, int j, int grp) {
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
     const int ns = pass == 0 ? 1 : (pass == 1 ? 8 : 64);
     const int k = j & (ns - 1);
     const int j0 = ((j - k) << 3) + k;
     float2 u[8];
-    __syncthreads();
+    group_barrier(grp);
 #pragma unroll
     for (int r = 0; r < 8; ++r) u[r] = buf[fft_idx(j + 64 * r)];
     if (pass > 0) {
@@ -68,7 +73,7 @@ __device__ __forceinline__ void fft512_r8(float2* buf, const float2* tw, int j) 
       }
     }
     dft8<INVERSE>(u);
-    __syncthreads();
+    group_barrier(grp);
 #pragma unroll
     for (int r = 0; r < 8; ++r) buf[fft_idx(j0 + r * ns)] = u[r];
   }

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
       }
       buf[grp][fft_idx(n)] = make_float2(a, c);
     }
-    fft512_r8<false>(buf[grp], tw, j);
+    fft512_r8<false>(buf[grp], tw, j, grp);
     const bool wa = va && la >= 1 && la <= kFrontFrames;  // frames this CTA owns (not halo)
     const bool wb = vb && (la + 1) <= kFrontFrames;
     for (int f = j; f < kBins; f += 64) {
