@@ -260,9 +260,9 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
   const int c0 = (tid & 63) * 4, rg = tid >> 6;
   const uint32_t buf_bytes = (uint32_t)TC * kRowBytes;   // [TC][256] fp32 stream rows, then [TC][256] fp16 accumulator rows
 
-  __shared__ float mf_s[kC], gf_s[kC], rb_s[kC];
-  __shared__ float mt_s[kMaxTc + 8], gt_s[kMaxTc];
-  __shared__ float red_a[16], red_b[16];
+  __shared__ float mf_s[kC], mt_s[kMaxTc + 8];                              // channel / time means (scratch of the gate stages)
+  __shared__ __align__(16) float gf_s[2][kC], rb_s[2][kC], gt_s[2][kMaxTc];   // [parity of the utterance]
+  __shared__ float red_a[16], red_b[16], red_c[8];
   __shared__ __align__(16) double xch[2][16];   // [parity][rank][2]: partial (sum, sum of squares) of v from the peers
   __shared__ float s_sc[8];
   __shared__ float s_nx[2][4];
@@ -323,9 +323,44 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
       rsv = (t >= 0 && t < p.T) ? __ldg(p.rowsum + (int64_t)b * p.T + t) : 0.f;
     }
   };
+  // Gates of one utterance (model.py:197-208) in three stages separated by block barriers: affine of r from the reg2
+  // statistics and channel means -> frequency gate chain and time means -> time gate chain. Inside the loop the stages
+  // of the NEXT utterance ride on the barriers the current one needs anyway (after the cluster exchange, after the
+  // statistics broadcast, after the final reduction), so the gates cost no barrier and no exposed latency of their own.
+  auto gate_stage0 = [&](int par) {
+    if (tid < kC) {
+      const float ra = s_nx[par][0];
+      const float rbv = c03v - ra * s_nx[par][1] * s3v;
+      rb_s[par][tid] = rbv;
+      mf_s[tid] = ra * (float)(csv * inv_T) + rbv;
+      const float s = warp_sum(rbv);
+      if (lane == 0) red_c[warp] = s;
+    }
+  };
+  auto gate_stage1 = [&](int par) {
+    if (tid < kC) {
+      gf_s[par][tid] = p.tf.enabled ? tf_chain2(mf_s, kC, tid, p.tf.wf1, p.tf.bf1, p.tf.wf2, p.tf.bf2, p.tf.af) : 1.f;
+    } else if (tid - kC < nt + 6) {
+      float rbsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rbsum += red_c[k];
+      const int t = t0 - 3 + (tid - kC);
+      mt_s[tid - kC] = (t >= 0 && t < p.T) ? s_nx[par][0] * (rsv / (float)kC) + rbsum / (float)kC : 0.f;
+    }
+  };
+  auto gate_stage2 = [&](int par) {
+    if (tid < nt)
+      gt_s[par][tid] = p.tf.enabled ? tf_chain2(mt_s + 3 - t0, p.T, t0 + tid, p.tf.wt1, p.tf.bt1, p.tf.wt2, p.tf.bt2, p.tf.at) : 1.f;
+  };
   if (cluster_id < p.B) {
     fetch_small(cluster_id);
     if (tid == kPersistThreads - 1) scalars_for(cluster_id, 0);
+    __syncthreads();
+    gate_stage0(0);
+    __syncthreads();
+    gate_stage1(0);
+    __syncthreads();
+    gate_stage2(0);
   }
   __syncthreads();
 
@@ -347,43 +382,20 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
     const float* w_s = reinterpret_cast<const float*>(smem + (size_t)buf * buf_bytes);
     const __half* r_s = reinterpret_cast<const __half*>(smem + (size_t)buf * buf_bytes + (size_t)TC * kC * 4);
     const int b_next = b + n_clusters;
+    const bool has_next = b_next < p.B;
     FTL(8 + it * 8 + 0);
-    if (tid == 0 && b_next < p.B) fetch(b_next, buf ^ 1);   // the other buffer was released by the barrier that ended it-1
-
-    // ---- gates: affine of r from the reg2 statistics, channel / time means, two stacked 3-tap convs each
+    if (has_next) {
+      if (tid == 0) fetch(b_next, buf ^ 1);   // the other buffer was released by the barrier that ended it-1
+      fetch_small(b_next);                    // consumed by the gate stages further down
+      if (tid == kPersistThreads - 1) scalars_for(b_next, buf ^ 1);
+    }
     const float ra = s_nx[buf][0], mean_y = s_nx[buf][2], rstd_y = s_nx[buf][3];
-    {
-      if (tid < kC) {
-        const float rbv = c03v - ra * s_nx[buf][1] * s3v;
-        rb_s[tid] = rbv;
-        mf_s[tid] = ra * (float)(csv * inv_T) + rbv;
-        const float s = warp_sum(rbv);
-        if (lane == 0) red_a[warp] = s;
-      }
-    }
-    const float rsv_cur = rsv;
-    if (b_next < p.B) {
-      fetch_small(b_next);
-      if (tid == kPersistThreads - 1) scalars_for(b_next, buf ^ 1);   // read after this iteration's closing barrier
-    }
-    __syncthreads();
-    if (tid < kC) {
-      gf_s[tid] = p.tf.enabled ? tf_chain2(mf_s, kC, tid, p.tf.wf1, p.tf.bf1, p.tf.wf2, p.tf.bf2, p.tf.af) : 1.f;
-    } else if (tid - kC < nt + 6) {
-      float rbsum = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) rbsum += red_a[k];
-      const int t = t0 - 3 + (tid - kC);
-      mt_s[tid - kC] = (t >= 0 && t < p.T) ? ra * (rsv_cur / (float)kC) + rbsum / (float)kC : 0.f;
-    }
-    __syncthreads();
-    if (tid < nt)
-      gt_s[tid] = p.tf.enabled ? tf_chain2(mt_s + 3 - t0, p.T, t0 + tid, p.tf.wt1, p.tf.bt1, p.tf.wt2, p.tf.bt2, p.tf.at) : 1.f;
+    const float* gt_cur = gt_s[buf];
 
     // ---- per-thread channel coefficients, as two packed pairs (channels c0,c0+1 | c0+2,c0+3): FFMA2 on sm_100
     float2 Ay[2], By[2], G1[2], G2[2];
     {
-      const float4 gf4 = *reinterpret_cast<const float4*>(gf_s + c0), rb4 = *reinterpret_cast<const float4*>(rb_s + c0);
+      const float4 gf4 = *reinterpret_cast<const float4*>(gf_s[buf] + c0), rb4 = *reinterpret_cast<const float4*>(rb_s[buf] + c0);
       const float2 rs2 = make_float2(rstd_y, rstd_y), nm2 = make_float2(-mean_y, -mean_y), ra2 = make_float2(ra, ra);
       Ay[0] = __fmul2_rn(rs2, make_float2(g4.x, g4.y));
       Ay[1] = __fmul2_rn(rs2, make_float2(g4.z, g4.w));
@@ -395,9 +407,8 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
       G2[1] = __fmul2_rn(make_float2(rb4.z, rb4.w), make_float2(gf4.z, gf4.w));
     }
     FTL(8 + it * 8 + 1);
-    mbar_wait(&full[buf], (it >> 1) & 1, 700);   // the tile has landed
-    __syncthreads();
-    FTL(8 + it * 8 + 2);                              // gt_s visible
+    mbar_wait(&full[buf], (it >> 1) & 1, 700);   // the tile has landed (every thread observes the barrier itself)
+    FTL(8 + it * 8 + 2);
 
     // ---- statistics of v = y + gt (G1 r + G2)  (recursive)  |  gt (G1 r + G2)  (residual) over the whole utterance
     float2 mv = make_float2(0.f, 1.f);
@@ -408,7 +419,7 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
       for (int j = 0; j < 4; ++j) {
         const int i = i0 + 8 * j;
         if (i >= nt) break;
-        const float g = gt_s[i];
+        const float g = gt_cur[i];
         const float2 gt2 = make_float2(g, g);
         const float4 wv = *reinterpret_cast<const float4*>(w_s + i * kC + c0);
         const uint2 hv = *reinterpret_cast<const uint2*>(r_s + i * kC + c0);
@@ -441,9 +452,10 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
         s_sc[4] = m.x;
         s_sc[5] = m.y;
       }
-      __syncthreads();
-      mv = make_float2(s_sc[4], s_sc[5]);
     }
+    if (has_next) gate_stage0(buf ^ 1);
+    __syncthreads();
+    if (p.mode != LN_NONE) mv = make_float2(s_sc[4], s_sc[5]);
 
     // ---- new stream o = y + Av v + Bv, folded into one affine per operand:
     //   o = P w + Q + gt (R1 r + R2),   P = k Ay, Q = k By + Bv, R1 = Av G1, R2 = Av G2,  k = 1 + Av (recursive) | 1
@@ -474,7 +486,7 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
     for (int j = 0; j < 4; ++j) {
       const int i = i0 + 8 * j;
       if (i >= nt) break;
-      const float g = gt_s[i];
+      const float g = gt_cur[i];
       const float2 gt2 = make_float2(g, g);
       const float4 wv = *reinterpret_cast<const float4*>(w_s + i * kC + c0);
       const uint2 hv = *reinterpret_cast<const uint2*>(r_s + i * kC + c0);
@@ -488,12 +500,14 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
       *reinterpret_cast<float4*>(wout + (int64_t)i * kC) = make_float4(o0.x, o0.y, o1.x, o1.y);
     }
     FTL(8 + it * 8 + 5);
-    if (recursive) {
+    if (has_next) gate_stage1(buf ^ 1);
+    {
       double ts = 0.0, tq = 0.0;
-      block_total(s2.x + s2.y, q2.x + q2.y, ts, tq);
-      if (tid == 0) { atomicAdd(&p.st_w[b].s, ts); atomicAdd(&p.st_w[b].ss, tq); }
+      block_total(s2.x + s2.y, q2.x + q2.y, ts, tq);   // its barrier also orders stage 1 before stage 2
+      if (recursive && tid == 0) { atomicAdd(&p.st_w[b].s, ts); atomicAdd(&p.st_w[b].ss, tq); }
     }
-    __syncthreads();   // every thread is done with this buffer and the exchange scratch: the next fetch may overwrite it
+    if (has_next) gate_stage2(buf ^ 1);
+    __syncthreads();   // every thread is done with this buffer and the scratch arrays: the next fetch may overwrite it
   }
   if (!peers_up) cluster.barrier_wait();
   FTL(2);
