@@ -1,9 +1,9 @@
 // Cluster-resident post-block update: TF-attention gates + both GroupNorm residual steps of a TCN block in ONE
-// kernel. A thread-block cluster owns one utterance; its residual stream tile (fp32) and raw res_out accumulators
-// (fp16) are read from HBM once into the cluster's shared memory, the two global statistics (of v and of the new
-// stream) are reduced across the cluster through distributed shared memory in a fixed order (bit-reproducible, no
-// atomics), and the new stream is written back once. Replaces k_tf_gate + k_resid<0> + k_resid<1> (which read the
-// two tensors twice) whenever an utterance fits a cluster of <= 8 CTAs (T <= 1152 frames, 18 s).
+// kernel. A thread-block cluster owns one utterance at a time; the residual stream tile (fp32) and the raw res_out
+// accumulators (fp16) are read from HBM once into shared memory, the statistics of v cross the cluster through
+// distributed shared memory in a fixed order, the statistics of the new stream leave as one double atomic pair per CTA,
+// and the new stream is written back once. Replaces k_tf_gate + k_resid<0> + k_resid<1> (which read the two tensors
+// twice) whenever an utterance fits a cluster of <= 8 CTAs (T <= 1152 frames, 18 s).
 // Reference: model/model.py:197-208 (TF_Attention), :347-352 (post-block norms).
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -18,8 +18,6 @@ namespace septfa {
 
 namespace {
 
-constexpr int kFusedThreads = 256;
-constexpr int kFusedWarps = kFusedThreads / 32;
 constexpr int kRowBytes = kC * 4 + kC * 2;   // fp32 stream row + fp16 accumulator row in shared memory
 
 __device__ __forceinline__ float tf_chain2(const float* m, int n, int j, const float* w1, float b1, const float* w2,
@@ -56,177 +54,6 @@ struct FusedParams {
   Stat2* st_w;              // [B] statistics of the new stream (recursive mode), accumulated into a zeroed slot
 };
 
-// fixed-order block reduction of (s, q) in double; result valid in all threads
-__device__ __forceinline__ double2 block_sum2(float s, float q, double* red /*[2*kFusedWarps]*/) {
-  double ds = warp_sum((double)s), dq = warp_sum((double)q);
-  const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { red[w] = ds; red[kFusedWarps + w] = dq; }
-  __syncthreads();
-  double ts = 0.0, tq = 0.0;
-  for (int i = 0; i < kFusedWarps; ++i) { ts += red[i]; tq += red[kFusedWarps + i]; }
-  __syncthreads();
-  return make_double2(ts, tq);
-}
-
-__global__ void __launch_bounds__(kFusedThreads, 2) k_resid_fused(FusedParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-  const int b = blockIdx.x / CS;
-  const int t0 = rank * p.Tc, nt = max(0, min(p.Tc, p.T - t0));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  float* w_s = reinterpret_cast<float*>(smem);                                   // [Tc][256] fp32
-  __half* r_s = reinterpret_cast<__half*>(smem + (size_t)p.Tc * kC * 4);        // [Tc][256] fp16
-  uint8_t* aux = smem + (size_t)p.Tc * kRowBytes;
-  double* red = reinterpret_cast<double*>(aux);                                  // [2*kFusedWarps]
-  double* xch = red + 2 * kFusedWarps;                                           // [2 phases][2] cluster exchange
-  float* mf_s = reinterpret_cast<float*>(xch + 4);                               // [256]
-  float* gf_s = mf_s + kC;                                                       // [256]
-  float* rb_s = gf_s + kC;                                                       // [256]
-  float* mt_s = rb_s + kC;                                                       // [Tc + 6]
-  float* gt_s = mt_s + p.Tc + 8;                                                 // [Tc]
-  __shared__ float s_misc[4];
-
-  pdl_launch_dependents();
-  pdl_wait();
-
-  // ---- stage the tile: 16-byte cp.async, one stream row = 64 pieces, one accumulator row = 32 pieces
-  {
-    const int64_t row0 = (int64_t)b * p.T + t0;
-    const float* wg = p.w + row0 * kC;
-    const __half* rg = p.racc + row0 * kC;
-    const uint32_t ws_a = (uint32_t)__cvta_generic_to_shared(w_s), rs_a = (uint32_t)__cvta_generic_to_shared(r_s);
-    for (int i = tid; i < nt * 64; i += kFusedThreads)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ws_a + i * 16), "l"(wg + i * 4) : "memory");
-    for (int i = tid; i < nt * 32; i += kFusedThreads)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rs_a + i * 16), "l"(rg + i * 8) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-
-  // ---- gates (overlaps the staging): affine of r from the reg2 statistics, channel / time means, conv chains
-  const float2 mrq = stat_mean_rstd(p.st_q + b, 1.0 / ((double)kH * p.T), 1e-8f);
-  const float ra = mrq.y;
-  float rbv = 0.f;
-  if (tid < kC) {
-    rbv = __ldg(p.c03 + tid) - ra * mrq.x * __ldg(p.s3 + tid);
-    rb_s[tid] = rbv;
-    mf_s[tid] = ra * (float)(__ldg(p.colsum + b * kC + tid) / (double)p.T) + rbv;
-  }
-  {
-    const double2 t = block_sum2(rbv, 0.f, red);   // contains barriers: mf_s / rb_s are visible afterwards
-    if (tid == 0) s_misc[0] = (float)(t.x / kC);
-  }
-  __syncthreads();
-  const float rbmean = s_misc[0];
-  // m_t for this CTA's frames and 3 neighbours each side (inside the utterance)
-  for (int i = tid; i < nt + 6; i += kFusedThreads) {
-    const int t = t0 - 3 + i;
-    mt_s[i] = (t >= 0 && t < p.T) ? ra * (__ldg(p.rowsum + (int64_t)b * p.T + t) / (float)kC) + rbmean : 0.f;
-  }
-  if (tid < kC) gf_s[tid] = p.tf.enabled ? tf_chain2(mf_s, kC, tid, p.tf.wf1, p.tf.bf1, p.tf.wf2, p.tf.bf2, p.tf.af) : 1.f;
-  __syncthreads();
-  for (int i = tid; i < nt; i += kFusedThreads)
-    gt_s[i] = p.tf.enabled ? tf_chain2(mt_s + 3 - t0, p.T, t0 + i, p.tf.wt1, p.tf.bt1, p.tf.wt2, p.tf.bt2, p.tf.at) : 1.f;
-
-  // ---- per-lane channel coefficients (lane = 8 channels)
-  const int c0 = lane * 8;
-  float Ay[8], By[8], G1[8], G2[8];
-  {
-    const bool has_norm = p.norm.gamma != nullptr;
-    float2 my = make_float2(0.f, 1.f);
-    if (has_norm) my = stat_mean_rstd(p.norm.st + b, p.norm.inv_n, p.norm.eps);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float g = has_norm ? __ldg(p.norm.gamma + c0 + j) : 1.f, be = has_norm ? __ldg(p.norm.beta + c0 + j) : 0.f;
-      Ay[j] = my.y * g;
-      By[j] = be - my.x * Ay[j];
-    }
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();   // tile, gf_s, gt_s, rb_s visible
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { G1[j] = ra * gf_s[c0 + j]; G2[j] = rb_s[c0 + j] * gf_s[c0 + j]; }
-
-  auto load_row = [&](int i, float (&y)[8], float (&v)[8]) {
-    const float4 a0 = *reinterpret_cast<const float4*>(w_s + i * kC + c0), a1 = *reinterpret_cast<const float4*>(w_s + i * kC + c0 + 4);
-    const uint4 h = *reinterpret_cast<const uint4*>(r_s + i * kC + c0);
-    const float wv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), r1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
-    const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&h.z)), r3 = __half22float2(*reinterpret_cast<const __half2*>(&h.w));
-    const float rv[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
-    const float gt = gt_s[i];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      y[j] = fmaf(wv[j], Ay[j], By[j]);
-      const float r = gt * fmaf(rv[j], G1[j], G2[j]);
-      v[j] = (p.mode == LN_RECURSIVE) ? y[j] + r : r;
-    }
-  };
-
-  // ---- phase 1: statistics of v over the whole utterance (cluster reduction through distributed shared memory)
-  float2 mv = make_float2(0.f, 1.f);
-  if (p.mode != LN_NONE) {
-    float s = 0.f, q = 0.f;
-    for (int i = warp; i < nt; i += kFusedWarps) {
-      float y[8], v[8];
-      load_row(i, y, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { s += v[j]; q = fmaf(v[j], v[j], q); }
-    }
-    const double2 part = block_sum2(s, q, red);
-    if (tid == 0) { xch[0] = part.x; xch[1] = part.y; }
-    cluster.sync();
-    Stat2 tot{0.0, 0.0};
-    for (int r = 0; r < CS; ++r) {
-      const double* rx = cluster.map_shared_rank(xch, r);
-      tot.s += rx[0];
-      tot.ss += rx[1];
-    }
-    mv = stat_mean_rstd(&tot, 1.0 / ((double)kC * p.T), 1e-5f);
-  }
-
-  // ---- phase 2: new stream = y + GN(v) (or y + v), kept in shared memory; statistics of the new stream
-  float Av[8], Bv[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float g = (p.mode != LN_NONE) ? __ldg(p.g_a + c0 + j) : 1.f, be = (p.mode != LN_NONE) ? __ldg(p.b_a + c0 + j) : 0.f;
-    Av[j] = mv.y * g;
-    Bv[j] = be - mv.x * Av[j];
-  }
-  float s2 = 0.f, q2 = 0.f;
-  float* wout = p.w + ((int64_t)b * p.T + t0) * kC;
-  for (int i = warp; i < nt; i += kFusedWarps) {
-    float y[8], v[8], o[8];
-    load_row(i, y, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      o[j] = (p.mode == LN_NONE) ? y[j] + v[j] : y[j] + fmaf(v[j], Av[j], Bv[j]);
-      s2 += o[j];
-      q2 = fmaf(o[j], o[j], q2);
-    }
-    *reinterpret_cast<float4*>(wout + (int64_t)i * kC + c0) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4*>(wout + (int64_t)i * kC + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-  }
-  if (p.mode == LN_RECURSIVE) {
-    const double2 part = block_sum2(s2, q2, red);
-    if (tid == 0) { xch[2] = part.x; xch[3] = part.y; }
-    cluster.sync();
-    if (rank == 0 && tid == 0) {
-      Stat2 tot{0.0, 0.0};
-      for (int r = 0; r < CS; ++r) {
-        const double* rx = cluster.map_shared_rank(xch + 2, r);
-        tot.s += rx[0];
-        tot.ss += rx[1];
-      }
-      atomicAdd(&p.st_w[b].s, tot.s);
-      atomicAdd(&p.st_w[b].ss, tot.ss);
-    }
-  }
-  cluster.sync();   // no CTA may exit while its shared memory can still be read by a peer
-}
-
-
 // ---------------------------------------------------------------------------------------------------------------
 // Persistent variant for utterances of at most 8 CTAs x kMaxTc frames (T <= 576, 9.2 s; the 4 s clips of the headline
 // workload run with 8 CTAs x 32 frames, two CTAs per SM). The grid is as many clusters as the device keeps resident;
@@ -245,10 +72,12 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #else
 #define FTL(k) do { } while (0)
 #endif
-constexpr int kPersistThreads = 512;
-constexpr int kMaxTc = 72;
+constexpr int kPersistThreads = 256;
+constexpr int kPersistWarps = kPersistThreads / 32;
+constexpr int kRowGroups = kPersistThreads / 64;   // a thread owns 4 channels of every kRowGroups-th frame of the tile
+constexpr int kMaxTc = 144;
 
-__global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParams p) {
+__global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParams p) {
   using namespace tc;
   extern __shared__ __align__(16) uint8_t smem[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -258,7 +87,6 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
   const int t0 = rank * TC, nt = min(TC, p.T - t0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c0 = (tid & 63) * 4, rg = tid >> 6;
-  const uint32_t buf_bytes = (uint32_t)TC * kRowBytes;   // [TC][256] fp32 stream rows, then [TC][256] fp16 accumulator rows
 
   __shared__ float mf_s[kC], mt_s[kMaxTc + 8];                              // channel / time means (scratch of the gate stages)
   __shared__ __align__(16) float gf_s[2][kC], rb_s[2][kC], gt_s[2][kMaxTc];   // [parity of the utterance]
@@ -266,11 +94,10 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
   __shared__ __align__(16) double xch[2][16];   // [parity][rank][2]: partial (sum, sum of squares) of v from the peers
   __shared__ float s_sc[8];
   __shared__ float s_nx[2][4];
-  __shared__ __align__(8) uint64_t full[2];
+  __shared__ __align__(8) uint64_t full;
 
   if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    mbar_init(&full, 1);
     fence_mbar_init();
   }
   FTL(0);
@@ -280,21 +107,19 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
   pdl_wait();
   FTL(1);
 
-  auto fetch = [&](int b, int buf) {   // one thread: two bulk copies onto the buffer's mbarrier
-    uint8_t* dst = smem + (size_t)buf * buf_bytes;
+  auto fetch = [&](int b) {   // one thread: two bulk copies onto the tile's mbarrier
     const int64_t row0 = (int64_t)b * p.T + t0;
-    mbar_expect_tx(&full[buf], (uint32_t)nt * kRowBytes);
-    bulk_copy_g2s(dst, p.w + row0 * kC, (uint32_t)nt * kC * 4, &full[buf]);
-    bulk_copy_g2s(dst + (size_t)TC * kC * 4, p.racc + row0 * kC, (uint32_t)nt * kC * 2, &full[buf]);
+    mbar_expect_tx(&full, (uint32_t)nt * kRowBytes);
+    bulk_copy_g2s(smem, p.w + row0 * kC, (uint32_t)nt * kC * 4, &full);
+    bulk_copy_g2s(smem + (size_t)TC * kC * 4, p.racc + row0 * kC, (uint32_t)nt * kC * 2, &full);
   };
-  if (tid == 0 && cluster_id < p.B) fetch(cluster_id, 0);
+  if (tid == 0 && cluster_id < p.B) fetch(cluster_id);
 
   const bool has_norm = p.norm.gamma != nullptr;
   const bool recursive = p.mode == LN_RECURSIVE;
   const double inv_T = 1.0 / (double)p.T;
   // static per-channel operands, once per CTA
-  float c03v = 0.f, s3v = 0.f;
-  if (tid < kC) { c03v = __ldg(p.c03 + tid); s3v = __ldg(p.s3 + tid); }
+  const float c03v = __ldg(p.c03 + tid), s3v = __ldg(p.s3 + tid);
   float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (has_norm) { g4 = __ldg(reinterpret_cast<const float4*>(p.norm.gamma + c0)); b4 = __ldg(reinterpret_cast<const float4*>(p.norm.beta + c0)); }
   float4 ga4 = make_float4(1.f, 1.f, 1.f, 1.f), ba4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -316,10 +141,9 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
     s_nx[par][0] = mrq.y; s_nx[par][1] = mrq.x; s_nx[par][2] = my.x; s_nx[par][3] = my.y;
   };
   auto fetch_small = [&](int b) {
-    if (tid < kC) {
-      csv = __ldg(p.colsum + b * kC + tid);
-    } else if (tid - kC < nt + 6) {
-      const int t = t0 - 3 + (tid - kC);
+    csv = __ldg(p.colsum + b * kC + tid);
+    if (tid < nt + 6) {
+      const int t = t0 - 3 + tid;
       rsv = (t >= 0 && t < p.T) ? __ldg(p.rowsum + (int64_t)b * p.T + t) : 0.f;
     }
   };
@@ -327,25 +151,23 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
   // statistics and channel means -> frequency gate chain and time means -> time gate chain. Inside the loop the stages
   // of the NEXT utterance ride on the barriers the current one needs anyway (after the cluster exchange, after the
   // statistics broadcast, after the final reduction), so the gates cost no barrier and no exposed latency of their own.
+  static_assert(kPersistThreads == kC, "gate stages: one thread per channel");
   auto gate_stage0 = [&](int par) {
-    if (tid < kC) {
-      const float ra = s_nx[par][0];
-      const float rbv = c03v - ra * s_nx[par][1] * s3v;
-      rb_s[par][tid] = rbv;
-      mf_s[tid] = ra * (float)(csv * inv_T) + rbv;
-      const float s = warp_sum(rbv);
-      if (lane == 0) red_c[warp] = s;
-    }
+    const float ra = s_nx[par][0];
+    const float rbv = c03v - ra * s_nx[par][1] * s3v;
+    rb_s[par][tid] = rbv;
+    mf_s[tid] = ra * (float)(csv * inv_T) + rbv;
+    const float s = warp_sum(rbv);
+    if (lane == 0) red_c[warp] = s;
   };
   auto gate_stage1 = [&](int par) {
-    if (tid < kC) {
-      gf_s[par][tid] = p.tf.enabled ? tf_chain2(mf_s, kC, tid, p.tf.wf1, p.tf.bf1, p.tf.wf2, p.tf.bf2, p.tf.af) : 1.f;
-    } else if (tid - kC < nt + 6) {
+    gf_s[par][tid] = p.tf.enabled ? tf_chain2(mf_s, kC, tid, p.tf.wf1, p.tf.bf1, p.tf.wf2, p.tf.bf2, p.tf.af) : 1.f;
+    if (tid < nt + 6) {
       float rbsum = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) rbsum += red_c[k];
-      const int t = t0 - 3 + (tid - kC);
-      mt_s[tid - kC] = (t >= 0 && t < p.T) ? s_nx[par][0] * (rsv / (float)kC) + rbsum / (float)kC : 0.f;
+      for (int k = 0; k < kPersistWarps; ++k) rbsum += red_c[k];
+      const int t = t0 - 3 + tid;
+      mt_s[tid] = (t >= 0 && t < p.T) ? s_nx[par][0] * (rsv / (float)kC) + rbsum / (float)kC : 0.f;
     }
   };
   auto gate_stage2 = [&](int par) {
@@ -371,21 +193,20 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
     if (lane == 0) { red_a[warp] = s; red_b[warp] = q; }
     __syncthreads();
     if (warp == 0) {
-      ts = warp_sum(lane < 16 ? (double)red_a[lane] : 0.0);
-      tq = warp_sum(lane < 16 ? (double)red_b[lane] : 0.0);
+      ts = warp_sum(lane < kPersistWarps ? (double)red_a[lane] : 0.0);
+      tq = warp_sum(lane < kPersistWarps ? (double)red_b[lane] : 0.0);
     }
   };
 
   bool peers_up = false;
   for (int b = cluster_id, it = 0; b < p.B; b += n_clusters, ++it) {
     const int buf = it & 1;
-    const float* w_s = reinterpret_cast<const float*>(smem + (size_t)buf * buf_bytes);
-    const __half* r_s = reinterpret_cast<const __half*>(smem + (size_t)buf * buf_bytes + (size_t)TC * kC * 4);
+    const float* w_s = reinterpret_cast<const float*>(smem);                                   // [TC][256] fp32 stream rows
+    const __half* r_s = reinterpret_cast<const __half*>(smem + (size_t)TC * kC * 4);           // [TC][256] fp16 accumulators
     const int b_next = b + n_clusters;
     const bool has_next = b_next < p.B;
     FTL(8 + it * 8 + 0);
     if (has_next) {
-      if (tid == 0) fetch(b_next, buf ^ 1);   // the other buffer was released by the barrier that ended it-1
       fetch_small(b_next);                    // consumed by the gate stages further down
       if (tid == kPersistThreads - 1) scalars_for(b_next, buf ^ 1);
     }
@@ -407,17 +228,17 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
       G2[1] = __fmul2_rn(make_float2(rb4.z, rb4.w), make_float2(gf4.z, gf4.w));
     }
     FTL(8 + it * 8 + 1);
-    mbar_wait(&full[buf], (it >> 1) & 1, 700);   // the tile has landed (every thread observes the barrier itself)
+    mbar_wait(&full, it & 1, 700);   // the tile has landed (every thread observes the barrier itself)
     FTL(8 + it * 8 + 2);
 
     // ---- statistics of v = y + gt (G1 r + G2)  (recursive)  |  gt (G1 r + G2)  (residual) over the whole utterance
     float2 mv = make_float2(0.f, 1.f);
     if (p.mode != LN_NONE) {
       float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-      for (int i0 = rg; i0 < nt; i0 += 32)
+      for (int i0 = rg; i0 < nt; i0 += 4 * kRowGroups)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int i = i0 + 8 * j;
+        const int i = i0 + kRowGroups * j;
         if (i >= nt) break;
         const float g = gt_cur[i];
         const float2 gt2 = make_float2(g, g);
@@ -481,10 +302,10 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
     }
     float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
     float* wout = p.w + ((int64_t)b * p.T + t0) * kC + c0;
-    for (int i0 = rg; i0 < nt; i0 += 32)
+    for (int i0 = rg; i0 < nt; i0 += 4 * kRowGroups)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int i = i0 + 8 * j;
+      const int i = i0 + kRowGroups * j;
       if (i >= nt) break;
       const float g = gt_cur[i];
       const float2 gt2 = make_float2(g, g);
@@ -503,8 +324,11 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
     if (has_next) gate_stage1(buf ^ 1);
     {
       double ts = 0.0, tq = 0.0;
-      block_total(s2.x + s2.y, q2.x + q2.y, ts, tq);   // its barrier also orders stage 1 before stage 2
-      if (recursive && tid == 0) { atomicAdd(&p.st_w[b].s, ts); atomicAdd(&p.st_w[b].ss, tq); }
+      block_total(s2.x + s2.y, q2.x + q2.y, ts, tq);   // its barrier also orders stage 1 before stage 2 ...
+      if (tid == 0) {
+        if (has_next) fetch(b_next);                  // ... and every thread's last read of the tile before this refill
+        if (recursive) { atomicAdd(&p.st_w[b].s, ts); atomicAdd(&p.st_w[b].ss, tq); }
+      }
     }
     if (has_next) gate_stage2(buf ^ 1);
     __syncthreads();   // every thread is done with this buffer and the scratch arrays: the next fetch may overwrite it
@@ -515,69 +339,31 @@ __global__ void __launch_bounds__(kPersistThreads, 2) k_resid_persist(FusedParam
 
 }  // namespace
 
-// Programmatic early launch of the cluster kernels is OFF: a persistent grid that becomes resident while the tail of
+// Programmatic early launch of the cluster kernel is OFF: a persistent grid that becomes resident while the tail of
 // the dconv grid is still running takes SM slots away from it (measured: 5.86 ms per step with, 5.09 ms without).
 static int g_fused_pdl = 0;
-static int g_fused_variant = 0;   // 0: register-resident kernel when the utterance fits, 1: shared-memory kernel only
-static size_t g_fused_smem_max = 0;   // dynamic shared memory the kernel may use (opt-in limit minus its static part)
-static int g_fused_pref_bytes = 110 * 1024;   // preferred tile footprint: two CTAs per SM overlap each other's phases
 
-static size_t fused_smem_bytes(int tc) {
-  return (size_t)tc * kRowBytes + 2 * kFusedWarps * 8 + 4 * 8 + 3 * kC * 4 + (2 * tc + 16) * 4 + 64;
+int resid_fused_cluster_size(int T) {   // 0: the utterance does not fit one cluster (caller uses the streaming kernels)
+  if (T > 8 * kMaxTc) return 0;
+  return std::min(8, (T + 31) / 32);
 }
-
-int resid_fused_cluster_size(int T) {
-  // smallest cluster whose per-CTA tile allows two CTAs per SM; otherwise the smallest that fits at all
-  for (int pass = 0; pass < 2; ++pass) {
-    const size_t lim = pass == 0 ? (size_t)g_fused_pref_bytes : g_fused_smem_max;
-    for (int cs = 1; cs <= 8; cs *= 2)
-      if (fused_smem_bytes((T + cs - 1) / cs) <= lim) return cs;
-  }
-  return 0;   // utterance too long for one cluster: use the streaming kernels
-}
-
-#ifdef SEPTFA_TIMELINE
-void resid_fused_dump_timeline() {
-  static unsigned long long h[32 * 128];
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(h, g_fused_tl, sizeof(h));
-  for (int c = 0; c < 32; c += 1) {
-    const unsigned long long* t = h + c * 128;
-    printf("cta %2d: start->pdl %6llu total %6llu |", c, t[1] - t[0], t[2] - t[0]);
-    for (int it = 0; it < 9; ++it) {
-      const unsigned long long* u = t + 8 + it * 8;
-      if (u[0] == 0) break;
-      printf(" [top@%llu gates %llu tile %llu ph1 %llu xchg %llu ph2 %llu]", u[0] - t[0], u[1] - u[0], u[2] - u[1], u[3] - u[2], u[4] - u[3], u[5] - u[4]);
-    }
-    printf("\n");
-  }
-}
-#endif
 
 cudaError_t resid_fused_setup() {
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  cudaFuncAttributes fa{};
-  cudaError_t e = cudaFuncGetAttributes(&fa, k_resid_fused);
-  if (e != cudaSuccess) return e;
-  g_fused_smem_max = (size_t)optin - fa.sharedSizeBytes;
-  if (const char* s = getenv("SEPTFA_FUSED_TILE_KB")) g_fused_pref_bytes = atoi(s) * 1024;
-  if (const char* s = getenv("SEPTFA_FUSED_VARIANT")) g_fused_variant = atoi(s);
   if (const char* s = getenv("SEPTFA_FUSED_PDL")) g_fused_pdl = atoi(s);
-  e = cudaFuncGetAttributes(&fa, k_resid_persist);
+  cudaFuncAttributes fa{};
+  cudaError_t e = cudaFuncGetAttributes(&fa, k_resid_persist);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_resid_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_resid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_fused_smem_max);
+  return cudaFuncSetAttribute(k_resid_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
 }
-
 
 // Clusters of `cs` CTAs of the persistent kernel the device keeps resident at once (cached per cluster size / footprint).
 static int persist_clusters(int cs, size_t smem) {
   static int cache[9][2] = {};
   static size_t cache_smem[9][2] = {};
-  const int slot = smem > 110 * 1024 ? 1 : 0;
+  const int slot = smem > 100 * 1024 ? 1 : 0;
   if (cache[cs][slot] != 0 && cache_smem[cs][slot] == smem) return cache[cs][slot];
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cs * 1024);
@@ -615,26 +401,17 @@ static void launch_cluster(K kernel, const FusedParams& p, int nclusters, int cs
 
 // Returns false if the utterance does not fit a cluster (caller falls back to k_tf_gate + k_resid<0,1>).
 bool launch_resid_fused(const ResidParams& rp, const GateParams& gp, cudaStream_t st) {
-  if (!rp.racc_half) return false;
+  const int cs = resid_fused_cluster_size(rp.T);
+  if (!rp.racc_half || cs == 0) return false;
   FusedParams p{};
   p.w = rp.w; p.racc = reinterpret_cast<const __half*>(rp.racc); p.norm = rp.norm;
   p.st_q = gp.st_q; p.s3 = gp.s3; p.c03 = gp.c03; p.rowsum = gp.rowsum; p.colsum = gp.colsum; p.tf = gp.tf;
-  p.T = rp.T; p.B = rp.B;
+  p.T = rp.T; p.B = rp.B; p.Tc = (rp.T + cs - 1) / cs;
   p.mode = rp.mode; p.g_a = rp.g_a; p.b_a = rp.b_a; p.st_w = rp.st_w;
-  if (g_fused_variant == 0 && rp.T <= 8 * kMaxTc) {
-    const int cs = std::min(8, (rp.T + 31) / 32);
-    p.Tc = (rp.T + cs - 1) / cs;
-    const size_t smem = 2 * (size_t)p.Tc * kRowBytes;
-    const int n_clusters = persist_clusters(cs, smem);
-    if (n_clusters > 0) {
-      launch_cluster(k_resid_persist, p, std::min(n_clusters, rp.B), cs, kPersistThreads, smem, st);
-      return true;
-    }
-  }
-  const int cs = resid_fused_cluster_size(rp.T);
-  if (cs == 0) return false;
-  p.Tc = (rp.T + cs - 1) / cs;
-  launch_cluster(k_resid_fused, p, rp.B, cs, kFusedThreads, fused_smem_bytes(p.Tc), st);
+  const size_t smem = (size_t)p.Tc * kRowBytes;
+  const int n_clusters = persist_clusters(cs, smem);
+  if (n_clusters <= 0) return false;
+  launch_cluster(k_resid_persist, p, std::min(n_clusters, rp.B), cs, kPersistThreads, smem, st);
   return true;
 }
 
