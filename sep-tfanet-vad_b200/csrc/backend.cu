@@ -8,50 +8,10 @@
 namespace septfa {
 
 // ------------------------------------------------------------------------------------------
-// VAD.common.conv1_1 (257 -> 4, k5, pad 2) as per-row partial products: every logits row is read
-// once and dotted with the 20 (tap, channel) weight vectors of each speaker;
+// VAD head. VAD.common.conv1_1 (257 -> 4, k5, pad 2) is linear in the logits, so its per-frame partial products
 //   part[row][s][k*4+j] = sum_f w[j][f][k] * logit[row][s*257 + f]
-// the taps are combined by k_vad_final. One warp per frame, weights staged in shared memory.
-constexpr int kVadRowsPerCta = 16;
-constexpr int kVadWPitch = 264;
-
-__global__ void __launch_bounds__(256) k_vad_partial(const float* __restrict__ logits, int M,
-                                                     const float* __restrict__ w1t, float* __restrict__ part) {
-  __shared__ float w[20][kVadWPitch];
-  pdl_launch_dependents();
-  for (int i = threadIdx.x; i < 20 * kBins; i += 256) w[i / kBins][i % kBins] = __ldg(w1t + i);   // static weights
-  pdl_wait();
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < kVadRowsPerCta; r += 8) {
-    const int row = blockIdx.x * kVadRowsPerCta + r;
-    if (row >= M) break;
-    const float* lr = logits + (int64_t)row * kLogitStride;
-    float a0[20], a1[20];
-#pragma unroll
-    for (int i = 0; i < 20; ++i) a0[i] = a1[i] = 0.f;
-    for (int f = lane; f < kBins; f += 32) {
-      const float x0 = __ldg(lr + f), x1 = __ldg(lr + kBins + f);
-#pragma unroll
-      for (int i = 0; i < 20; ++i) {
-        const float wv = w[i][f];
-        a0[i] = fmaf(wv, x0, a0[i]);
-        a1[i] = fmaf(wv, x1, a1[i]);
-      }
-    }
-    float o0 = 0.f, o1 = 0.f;  // lane i < 20 keeps speaker 0 / value i, lane i >= 20 ... speaker 1 via o1
-#pragma unroll
-    for (int i = 0; i < 20; ++i) {
-      const float s0 = warp_sum(a0[i]), s1 = warp_sum(a1[i]);
-      if (lane == i) { o0 = s0; o1 = s1; }
-    }
-    if (lane < 20) {
-      part[(int64_t)row * 40 + lane] = o0;
-      part[(int64_t)row * 40 + 20 + lane] = o1;
-    }
-  }
-}
-
+// are produced by the output convolution itself as 40 extra columns (composite weights, septfa_abi.cu) in the padding
+// of the logits rows; this kernel combines the taps.
 // Tap combination + PReLU + GroupNorm(1,4) over the [4,T] plane -> output_layer_vad (4 -> 1, k3, pad 1)
 // -> sigmoid; then the inference-only threshold (>=) and [1,0,1] neighbour-OR smoothing with edge copy
 // (model.py:173-179, 449-451). One CTA owns one (utterance, speaker): its statistics need no atomics.
@@ -70,7 +30,7 @@ __global__ void __launch_bounds__(256) k_vad_final(VadParams p) {
     for (int k = 0; k < 5; ++k) {
       const int tt = t + k - 2;
       if (tt < 0 || tt >= p.T) continue;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p.part + ((int64_t)b * p.T + tt) * 40 + s * 20 + k * 4));
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.logits + ((int64_t)b * p.T + tt) * kLogitStride + kVadCol0 + s * 20 + k * 4));
       c[0] += v.x; c[1] += v.y; c[2] += v.z; c[3] += v.w;
     }
 #pragma unroll
@@ -122,7 +82,6 @@ __global__ void __launch_bounds__(256) k_vad_final(VadParams p) {
 }
 
 void launch_vad(const VadParams& p, cudaStream_t st) {
-  launch_k(k_vad_partial, dim3((p.M + kVadRowsPerCta - 1) / kVadRowsPerCta), dim3(256), 0, st, true, p.logits, p.M, p.w1t, p.part);
   launch_k(k_vad_final, dim3(p.B * 2), dim3(256), 0, st, true, p);
 }
 

@@ -19,6 +19,7 @@ constexpr int kBins = 257;       // n_fft/2 + 1
 constexpr int kC = 256;          // BN_dim: residual-stream channels (= kBins - 1, DC dropped)
 constexpr int kH = 512;          // H_dim: depthwise hidden channels
 constexpr int kLogitStride = 576;  // row pitch of the frame-major logits buffer (514 padded to 3 x 192)
+constexpr int kVadCol0 = 516;      // logits columns 516..555: the 2 x 20 partial products of VAD.common.conv1_1 (16 B aligned)
 constexpr int kMaxSegs = 72;     // max utterance segments touched by one 128-row tile (T >= 2)
 
 // Per-utterance GroupNorm statistics accumulators: {sum, sum of squares} in double.

@@ -141,12 +141,10 @@ extern long long* g_tl_conv1;
 cudaError_t tc_gemm_setup();  // opt-in shared memory attributes; call once per device
 // backend.cu
 struct VadParams {
-  const float* logits;   // [M,576]
+  const float* logits;   // [M,576]; columns kVadCol0 + s*20 + k*4 + j hold the conv1_1 partial products (out conv)
   int M, T, B;
-  const float* w1t;      // [5 k][4 j][257 f] folded conv1_1 weights
   float b1[4]; float slope; float g[4]; float be[4];
   float w2[12]; float b2;  // output_layer_vad [4 j][3 k]
-  float* part;           // [M, 2, 20] per-row partial products of conv1_1 (scratch)
   float* c4;             // [B*2*T, 4] scratch
   float* prob;           // [B,2,T]
   float* smooth;         // [B,2,T]

@@ -52,7 +52,7 @@ struct septfa_handle {
   const float* ln_g = nullptr; const float* ln_b = nullptr;
   float out_a = 0.f; const float* out_g = nullptr; const float* out_be = nullptr;
   const __half* out_img = nullptr; const __half* out_img_lo = nullptr; const float* out_wt = nullptr; const float* out_bias = nullptr;
-  const float* vad_w1t = nullptr; float vad_b1[4]{}; float vad_a = 0.f; float vad_g[4]{}; float vad_be[4]{};
+  float vad_b1[4]{}; float vad_a = 0.f; float vad_g[4]{}; float vad_be[4]{};
   float vad_w2[12]{}; float vad_b2 = 0.f;
   float act_k[9]{}; float act_b = 0.f; float act_a = 0.f;
   const float* win_fwd = nullptr; const float* win_inv = nullptr; const float2* twiddle = nullptr;
@@ -209,7 +209,7 @@ std::vector<__half> pack_image(const std::vector<double>& w, int nvalid, int kdi
 const std::vector<float>& T_(septfa_handle* h, const std::string& k) { return h->host.at(k); }
 
 struct Workspace {
-  float2* S; float* part; float* w; float* dcg; float* p; float* racc; float* rowsum; float* gt; float* logits;
+  float2* S; float* w; float* dcg; float* p; float* racc; float* rowsum; float* gt; float* logits;
   float* ra; float* rb; float* gf; float* c4; float* prob; float* smooth;
   uint8_t* zero_begin; size_t zero_bytes;
   Stat2* st0; Stat2* st_blk; Stat2* st_o; Stat2* st_vad; double* colsum;
@@ -226,7 +226,6 @@ Workspace carve(const septfa_handle* h, void* base, int B, int64_t L) {
     return p;
   };
   w.S = (float2*)take(M * kBins * sizeof(float2));
-  w.part = (float*)take(M * 40 * sizeof(float));
   w.w = (float*)take(M * kC * sizeof(float));
   w.dcg = (float*)take(M * sizeof(float));
   w.p = (float*)take(M * kC * sizeof(float));
@@ -557,27 +556,42 @@ int septfa_commit_weights(septfa_handle* h) {
   // output layer 256 -> 514 (padded to 576 = 3 x 192)
   {
     h->out_a = T_(h, "TCN.output.0.weight")[0];
-    const auto w = fold_wn(T_(h, "TCN.output.2.weight_g"), T_(h, "TCN.output.2.weight_v"), kBins * 2);
+    auto w = fold_wn(T_(h, "TCN.output.2.weight_g"), T_(h, "TCN.output.2.weight_v"), kBins * 2);
     std::vector<float> wt((size_t)kC * kLogitStride, 0.f), bias(kLogitStride, 0.f);
+    for (int n = 0; n < kBins * 2; ++n) bias[n] = T_(h, "TCN.output.2.bias")[n];
+    int nvalid = kBins * 2;
+    if (c.final_vad) {
+      // VAD.common.conv1_1 (257 -> 4, k5) applied to the logits is linear in them, so its 2 x 20 per-frame partial
+      // products  part[s][k][j] = sum_f w1[j][f][k] logit[s*257 + f]  are 40 more outputs of THIS contraction with the
+      // composite weights W1 * Wo (and bias W1 * bo). They live in the padding columns kVadCol0 .. +39 of the 576-wide
+      // logits rows: no extra pass over the logits (the former k_vad_partial: 118 us, LSU-bound), no extra GEMM tile.
+      const auto w1 = fold_wn(T_(h, "vad.common.conv1_1.weight_g"), T_(h, "vad.common.conv1_1.weight_v"), 4);  // [4][257][5]
+      nvalid = kVadCol0 + 40;
+      w.resize((size_t)nvalid * kC, 0.0);
+      for (int s2 = 0; s2 < 2; ++s2)
+        for (int k = 0; k < 5; ++k)
+          for (int j = 0; j < 4; ++j) {
+            const int n = kVadCol0 + s2 * 20 + k * 4 + j;
+            double bacc = 0.0;
+            for (int f = 0; f < kBins; ++f) {
+              const double w1v = w1[((size_t)j * kBins + f) * 5 + k];
+              bacc += w1v * (double)bias[s2 * kBins + f];
+              for (int kc = 0; kc < kC; ++kc) w[(size_t)n * kC + kc] += w1v * w[(size_t)(s2 * kBins + f) * kC + kc];
+            }
+            bias[n] = (float)bacc;
+          }
+    }
     std::vector<double> w_lo(w.size());   // low part of the 2-term fp16 split used by the tcgen05 output conv
     for (size_t i = 0; i < w.size(); ++i) w_lo[i] = (double)((float)w[i] - __half2float(__float2half((float)w[i])));
-    for (int n = 0; n < kBins * 2; ++n) {
-      bias[n] = T_(h, "TCN.output.2.bias")[n];
+    for (int n = 0; n < nvalid; ++n)
       for (int k = 0; k < kC; ++k) wt[(size_t)k * kLogitStride + n] = (float)w[(size_t)n * kC + k];
-    }
     if (upload(h, T_(h, "TCN.output.1.weight"), &h->out_g) || upload(h, T_(h, "TCN.output.1.bias"), &h->out_be) ||
-        upload(h, pack_image(w, kBins * 2, kC, 3, 192), &h->out_img) || upload(h, pack_image(w_lo, kBins * 2, kC, 3, 192), &h->out_img_lo) ||
+        upload(h, pack_image(w, nvalid, kC, 3, 192), &h->out_img) || upload(h, pack_image(w_lo, nvalid, kC, 3, 192), &h->out_img_lo) ||
         upload(h, wt, &h->out_wt) ||
         upload(h, bias, &h->out_bias))
       return SEPTFA_E_CUDA;
   }
   if (c.final_vad) {
-    const auto w1 = fold_wn(T_(h, "vad.common.conv1_1.weight_g"), T_(h, "vad.common.conv1_1.weight_v"), 4);  // [4][257][5]
-    std::vector<float> w1t((size_t)5 * 4 * kBins);
-    for (int j = 0; j < 4; ++j)
-      for (int f = 0; f < kBins; ++f)
-        for (int k = 0; k < 5; ++k) w1t[((size_t)k * 4 + j) * kBins + f] = (float)w1[((size_t)j * kBins + f) * 5 + k];
-    if (upload(h, w1t, &h->vad_w1t)) return SEPTFA_E_CUDA;
     const auto w2 = fold_wn(T_(h, "vad.output_layer_vad.weight_g"), T_(h, "vad.output_layer_vad.weight_v"), 1);  // [1][4][3]
     for (int j = 0; j < 4; ++j) {
       h->vad_b1[j] = T_(h, "vad.common.conv1_1.bias")[j];
@@ -686,11 +700,11 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   const float* gate = nullptr;
   if (c.final_vad) {
     VadParams vp{};
-    vp.logits = ws.logits; vp.M = M; vp.T = T; vp.B = B; vp.w1t = h->vad_w1t;
+    vp.logits = ws.logits; vp.M = M; vp.T = T; vp.B = B;
     std::memcpy(vp.b1, h->vad_b1, sizeof(vp.b1)); vp.slope = h->vad_a;
     std::memcpy(vp.g, h->vad_g, sizeof(vp.g)); std::memcpy(vp.be, h->vad_be, sizeof(vp.be));
     std::memcpy(vp.w2, h->vad_w2, sizeof(vp.w2)); vp.b2 = h->vad_b2;
-    vp.part = ws.part; vp.c4 = ws.c4; vp.prob = ws.prob; vp.smooth = ws.smooth;
+    vp.c4 = ws.c4; vp.prob = ws.prob; vp.smooth = ws.smooth;
     vp.thr = use_kw ? kw->threshold_activated_vad : 0.f;
     vp.do_smooth = use_kw ? 1 : 0;
     launch_vad(vp, st);
