@@ -122,6 +122,17 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
 int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L, const septfa_infer_kw* kw,
                         float* out_wav_host, float* out_vad_host);
 
+/* Batch streams (only_inference.py's loop over files, model/model.py:402 per batch): the same from/to HOST forward,
+ * split into an asynchronous submit and a wait so that successive batches overlap - while batch n computes, the
+ * results of batch n-1 travel device->host and the input of batch n+1 host->device (copy engines and SMs all busy).
+ * Two independent slots (0, 1), each with its own stream, device buffers and workspace; a slot holds one batch in
+ * flight: submit(slot) -> wait(slot) -> submit(slot) ... The host buffers must be page-locked (cudaHostAlloc /
+ * cudaHostRegister / torch pin_memory) and stay valid and untouched until wait(slot) returns. */
+#define SEPTFA_HOST_SLOTS 2
+int septfa_forward_host_submit(septfa_handle* h, int slot, const float* x_host, int B, int64_t L, const septfa_infer_kw* kw,
+                               float* out_wav_host, float* out_vad_host);
+int septfa_forward_host_wait(septfa_handle* h, int slot);
+
 /* Number of GPU kernels launched by the last forward / online step on this handle. */
 int septfa_last_launch_count(const septfa_handle* h);
 

@@ -61,6 +61,12 @@ struct septfa_handle {
   cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
   cudaEvent_t hev_in[8] = {}, hev_done[8] = {};
   int host_chunks = 0;  // 0 = automatic
+  struct HostSlot {      // septfa_forward_host_submit / _wait
+    cudaStream_t stream = nullptr;
+    float* x = nullptr; float* out = nullptr; float* vad = nullptr; void* ws = nullptr;
+    size_t cap_x = 0, cap_out = 0, cap_vad = 0, cap_ws = 0;
+    bool busy = false;
+  } slots[SEPTFA_HOST_SLOTS];
   int fused_resid = 1;  // cluster-resident gate + residual kernel when the utterance fits a cluster
   float* hx_dev = nullptr; float* hout_dev = nullptr; float* hvad_dev = nullptr; void* hws = nullptr; void* hws_b = nullptr;
   float* hx_pin = nullptr; float* hout_pin = nullptr; float* hvad_pin = nullptr;
@@ -326,6 +332,10 @@ void septfa_destroy(septfa_handle* h) {
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
   cudaFree(h->hx_dev); cudaFree(h->hout_dev); cudaFree(h->hvad_dev); cudaFree(h->hws); cudaFree(h->hws_b); cudaFree(h->pit_acc);
+  for (auto& sl : h->slots) {
+    if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+    cudaFree(sl.x); cudaFree(sl.out); cudaFree(sl.vad); cudaFree(sl.ws);
+  }
   cudaFreeHost(h->hx_pin); cudaFreeHost(h->hout_pin); cudaFreeHost(h->hvad_pin);
   if (h->hstream) {
     cudaStreamDestroy(h->hstream); cudaStreamDestroy(h->hstream_in); cudaStreamDestroy(h->hstream_out);
@@ -854,6 +864,57 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
   CUDA_TRY(h, cudaStreamSynchronize(h->hstream_in));
   if (!pin_out) std::memcpy(out_wav_host, h->hout_pin, nout);
   if (want_vad && !pin_vad) std::memcpy(out_vad_host, h->hvad_pin, nvad);
+  return 0;
+}
+
+int septfa_forward_host_submit(septfa_handle* h, int slot, const float* x_host, int B, int64_t L, const septfa_infer_kw* kw,
+                               float* out_wav_host, float* out_vad_host) {
+  if (int rc = check_forward_args(h, B, L)) return rc;
+  if (slot < 0 || slot >= SEPTFA_HOST_SLOTS) return fail(h, SEPTFA_E_INVALID, "slot must be 0 or 1");
+  if (!x_host || !out_wav_host) return fail(h, SEPTFA_E_INVALID, "null host buffer");
+  auto& sl = h->slots[slot];
+  if (sl.busy) return fail(h, SEPTFA_E_STATE, "slot has a batch in flight: call septfa_forward_host_wait first");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const bool want_vad = h->cfg.final_vad && out_vad_host != nullptr;
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  if (!is_pinned(x_host) || !is_pinned(out_wav_host) || (want_vad && !is_pinned(out_vad_host)))
+    return fail(h, SEPTFA_E_INVALID, "septfa_forward_host_submit needs page-locked host buffers");
+  if (!sl.stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+  const int64_t T = septfa_num_frames(L);
+  const size_t nx = (size_t)B * L * sizeof(float), nout = nx * 2, nvad = (size_t)B * 2 * T * sizeof(float);
+  const size_t nws = septfa_workspace_bytes(h, B, L);
+  auto grow = [&](void** dev, size_t* cap, size_t need) -> cudaError_t {
+    if (*cap >= need) return cudaSuccess;
+    cudaFree(*dev); *dev = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(dev, need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+  };
+  CUDA_TRY(h, grow(reinterpret_cast<void**>(&sl.x), &sl.cap_x, nx));
+  CUDA_TRY(h, grow(reinterpret_cast<void**>(&sl.out), &sl.cap_out, nout));
+  CUDA_TRY(h, grow(reinterpret_cast<void**>(&sl.vad), &sl.cap_vad, nvad));
+  CUDA_TRY(h, grow(&sl.ws, &sl.cap_ws, nws));
+  CUDA_TRY(h, cudaMemcpyAsync(sl.x, x_host, nx, cudaMemcpyHostToDevice, sl.stream));
+  if (int rc = septfa_forward(h, sl.x, B, L, kw, sl.out, sl.vad, nullptr, nullptr, nullptr, nullptr, sl.ws, sl.cap_ws, sl.stream))
+    return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(out_wav_host, sl.out, nout, cudaMemcpyDeviceToHost, sl.stream));
+  if (want_vad) CUDA_TRY(h, cudaMemcpyAsync(out_vad_host, sl.vad, nvad, cudaMemcpyDeviceToHost, sl.stream));
+  sl.busy = true;
+  return 0;
+}
+
+int septfa_forward_host_wait(septfa_handle* h, int slot) {
+  if (!h) return SEPTFA_E_INVALID;
+  if (slot < 0 || slot >= SEPTFA_HOST_SLOTS) return fail(h, SEPTFA_E_INVALID, "slot must be 0 or 1");
+  auto& sl = h->slots[slot];
+  if (!sl.busy) return fail(h, SEPTFA_E_STATE, "slot has no batch in flight");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  sl.busy = false;
+  CUDA_TRY(h, cudaStreamSynchronize(sl.stream));
   return 0;
 }
 

@@ -77,6 +77,9 @@ _PROTOS = {
                                  C.c_void_p]),
     "septfa_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.POINTER(InferKw), C.c_void_p,
                                       C.c_void_p]),
+    "septfa_forward_host_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.POINTER(InferKw),
+                                             C.c_void_p, C.c_void_p]),
+    "septfa_forward_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "septfa_last_launch_count": (C.c_int, [C.c_void_p]),
     "septfa_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int, C.c_int]),
     "septfa_online_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),

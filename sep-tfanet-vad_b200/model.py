@@ -221,8 +221,66 @@ class SeparationModel(nn.Module):
                                            C.c_void_p(vad.data_ptr()) if vad is not None else None)
             _lib.check(h.ptr, rc)
             self.last_launch_count = h.lib.septfa_last_launch_count(h.ptr)
+        return self._host_result(out, vad, kw)
+
+    def _host_result(self, out, vad, kw):
         if not self.final_vad:
             return out, 0
         if kw is not None and kw.return_smoothed_vad:
             return out, vad.unsqueeze(2)
         return out, vad
+
+    def forward_host_submit(self, x_host: torch.Tensor, inference_kw={}, device=0, slot=0, out=None, vad=None):
+        """Asynchronous half of :meth:`forward_host` (septfa_forward_host_submit): enqueue copy-in, forward and
+        copy-out of one batch on pipeline slot 0 or 1 and return a :class:`HostBatch` whose ``result()`` waits for
+        it. Two slots let successive batches overlap their PCIe copies with each other's kernels. ``x_host`` is
+        pinned if it is not already; ``out`` / ``vad`` may be caller-provided pinned result tensors (reused across
+        batches), otherwise fresh pinned tensors are allocated."""
+        assert x_host.ndim == 2 and not x_host.is_cuda
+        kw = _lib.InferKw.from_dict(inference_kw) if (inference_kw and self.final_vad) else None
+        x_host = x_host.detach().to(torch.float32).contiguous()
+        if not x_host.is_pinned():
+            x_host = x_host.pin_memory()
+        B, L = x_host.shape
+        T = _lib.num_frames(L)
+        dev = torch.device("cuda", device)
+        with torch.cuda.device(dev):
+            h = self._handle(dev)
+            if out is None:
+                out = torch.empty((B, self.num_spk, L), dtype=torch.float32, pin_memory=True)
+            if vad is None and self.final_vad:
+                vad = torch.empty((B, self.num_spk, T), dtype=torch.float32, pin_memory=True)
+            assert tuple(out.shape) == (B, self.num_spk, L) and out.is_pinned() and out.is_contiguous()
+            rc = h.lib.septfa_forward_host_submit(h.ptr, int(slot), C.c_void_p(x_host.data_ptr()), B, L,
+                                                  C.byref(kw) if kw is not None else None, C.c_void_p(out.data_ptr()),
+                                                  C.c_void_p(vad.data_ptr()) if vad is not None else None)
+            _lib.check(h.ptr, rc)
+            self.last_launch_count = h.lib.septfa_last_launch_count(h.ptr)
+        return HostBatch(self, h, dev, int(slot), x_host, out, vad if self.final_vad else None, kw)
+
+    def forward_host_stream(self, batches, inference_kw={}, device=0):
+        """Generator over an iterable of host batches ``[B, L]`` (the loop of only_inference.py:80-100 over a data
+        loader): yields ``(out_separation, output_vad)`` per batch, in order, keeping two batches in flight."""
+        pending = []
+        for i, xb in enumerate(batches):
+            if len(pending) == 2:
+                yield pending.pop(0).result()
+            pending.append(self.forward_host_submit(xb, inference_kw, device, slot=i & 1))
+        while pending:
+            yield pending.pop(0).result()
+
+
+class HostBatch:
+    """A batch in flight on one pipeline slot (returned by :meth:`SeparationModel.forward_host_submit`)."""
+
+    def __init__(self, model, handle, dev, slot, x_host, out, vad, kw):
+        self._m, self._h, self._dev, self.slot = model, handle, dev, slot
+        self._x, self._out, self._vad, self._kw = x_host, out, vad, kw   # keeps the pinned buffers alive
+        self._done = False
+
+    def result(self):
+        if not self._done:
+            with torch.cuda.device(self._dev):
+                _lib.check(self._h.ptr, self._h.lib.septfa_forward_host_wait(self._h.ptr, self.slot))
+            self._done = True
+        return self._m._host_result(self._out, self._vad, self._kw)

@@ -219,6 +219,26 @@ def test_forward_host_equals_forward(cuda_models):
     assert (vad_h - vad_d.cpu()).abs().max().item() < 1e-3
 
 
+def test_forward_host_stream_equals_forward(cuda_models):
+    """The asynchronous two-slot host pipeline (forward_host_submit / forward_host_stream) returns, per batch and in
+    order, what the synchronous device forward returns - including ragged last batches and slot reuse."""
+    args = synth.CONFIG_WITH_VAD
+    m = cuda_models(args, 31, 0)
+    kw = dict(synth.DEFAULT_INFERENCE_KW, filter_signals_by_smo_vad=True)
+    batches = [torch.from_numpy(synth.make_mixtures(n, 20000, 900 + i)) for i, n in enumerate((3, 2, 4, 1, 3))]
+    got = list(m.forward_host_stream(batches, kw))
+    assert len(got) == len(batches)
+    for xb, (o, v) in zip(batches, got):
+        od, vd, _ = m(xb.cuda(), kw)
+        assert not o.is_cuda and o.is_pinned()
+        assert (o - od.cpu()).abs().max().item() < 5e-4 and (v - vd.cpu()).abs().max().item() < 1e-3
+    # slot protocol errors are reported, not swallowed
+    f = m.forward_host_submit(batches[0], kw, slot=0)
+    with pytest.raises(Exception):
+        m.forward_host_submit(batches[1], kw, slot=0)
+    f.result()
+
+
 def test_error_behaviour(cuda_models):
     m = cuda_models(synth.CONFIG_WITH_VAD, 33, 0)
     with pytest.raises(AssertionError):           # model/model.py:406
