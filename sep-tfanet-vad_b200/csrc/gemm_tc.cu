@@ -491,10 +491,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
           const int row = r0 + rl;
           const int sg = smap.seg(row);
           if (MODE == 0) {
-            o.x = prelu(o.x + bias4.x, p.slope); o.y = prelu(o.y + bias4.y, p.slope);
-            o.z = prelu(o.z + bias4.z, p.slope); o.w = prelu(o.w + bias4.w, p.slope);
-            const float ov[4] = {o.x, o.y, o.z, o.w};
-            ostat.add(sg, ov, seg_acc);
+            // bias + PReLU (max(x, a x) for a <= 1, min otherwise: AMAX) + statistics on the packed fp32 pipe
+            const float2 sl2 = make_float2(p.slope, p.slope);
+            const float2 x0 = __fadd2_rn(make_float2(o.x, o.y), make_float2(bias4.x, bias4.y));
+            const float2 x1 = __fadd2_rn(make_float2(o.z, o.w), make_float2(bias4.z, bias4.w));
+            const float2 a0 = __fmul2_rn(sl2, x0), a1 = __fmul2_rn(sl2, x1);
+            if constexpr (AMAX) o = make_float4(fmaxf(x0.x, a0.x), fmaxf(x0.y, a0.y), fmaxf(x1.x, a1.x), fmaxf(x1.y, a1.y));
+            else o = make_float4(fminf(x0.x, a0.x), fminf(x0.y, a0.y), fminf(x1.x, a1.x), fminf(x1.y, a1.y));
+            const float2 r0 = make_float2(o.x, o.y), r1 = make_float2(o.z, o.w);
+            const float2 sv = __fadd2_rn(r0, r1), qv = __ffma2_rn(r1, r1, __fmul2_rn(r0, r0));
+            const float s = sv.x + sv.y, q = qv.x + qv.y;
+            if (sg == 0) { ostat.s0 += s; ostat.q0 += q; }
+            else if (sg == 1) { ostat.s1 += s; ostat.q1 += q; }
+            else { atomicAdd(seg_acc + 2 * sg, s); atomicAdd(seg_acc + 2 * sg + 1, q); }
           } else if (MODE == 2) {
             o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
           } else {
@@ -578,6 +587,8 @@ cudaError_t tc_gemm_setup() {
   cudaError_t e;
   if ((e = setup_one<0, false>(s0)) != cudaSuccess) return e;
   if ((e = setup_one<0, true>(s0)) != cudaSuccess) return e;
+  if ((e = setup_one<0, false, false>(s0)) != cudaSuccess) return e;
+  if ((e = setup_one<0, true, false>(s0)) != cudaSuccess) return e;
   if ((e = setup_one<1, false>(s0 + kDconvWBytes)) != cudaSuccess) return e;
   if ((e = setup_one<1, true>(s0 + kDconvWBytes)) != cudaSuccess) return e;
   if ((e = setup_one<1, false, false>(s0 + kDconvWBytes)) != cudaSuccess) return e;
@@ -592,7 +603,11 @@ void launch_tc_conv1(const Conv1Params& c, cudaStream_t st) {
   p.bias = c.bias_f; p.slope = c.slope;
   p.out = c.p_out; p.out_stride = kC; p.st_out = c.st_p;
   p.dbg = g_tl_conv1;
-  if (c.half_io) launch_mode<0, true>(p, 1, st); else launch_mode<0, false>(p, 1, st);
+  if (c.slope <= 1.f) {
+    if (c.half_io) launch_mode<0, true, true>(p, 1, st); else launch_mode<0, false, true>(p, 1, st);
+  } else {
+    if (c.half_io) launch_mode<0, true, false>(p, 1, st); else launch_mode<0, false, false>(p, 1, st);
+  }
 }
 
 void launch_tc_dconv(const DconvParams& c, cudaStream_t st) {
