@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
     const int lq = warp & 3, ch = warp >> 2;
     float* stg = reinterpret_cast<float*>(smem) + warp * (32 * kStgPitch);  // aliases the (now idle) stage buffers
     const int my_rl = lq * 32 + lane;       // the row this thread owns in TMEM
-    float rowacc = 0.f;
+    float2 rowacc2 = make_float2(0.f, 0.f);
     SegStat2 ostat;
     constexpr int NCC = NT / 64;            // 32-column chunks per column half
     for (int cc = 0; cc < NCC; ++cc) {
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
       TLG(12 + cc * 4);
       if (MODE == 1) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) rowacc += v[i];
+        for (int i = 0; i < 16; ++i) rowacc2 = __fadd2_rn(rowacc2, make_float2(v[2 * i], v[2 * i + 1]));
       }
       __syncwarp();
 #pragma unroll
@@ -507,8 +507,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
           } else if (MODE == 2) {
             o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
           } else {
-            if (sg == 0) { cs0.x += o.x; cs0.y += o.y; cs0.z += o.z; cs0.w += o.w; }
-            else if (sg == 1) { cs1.x += o.x; cs1.y += o.y; cs1.z += o.z; cs1.w += o.w; }
+            if (sg == 0) {
+              const float2 a = __fadd2_rn(make_float2(cs0.x, cs0.y), make_float2(o.x, o.y)), b2 = __fadd2_rn(make_float2(cs0.z, cs0.w), make_float2(o.z, o.w));
+              cs0 = make_float4(a.x, a.y, b2.x, b2.y);
+            } else if (sg == 1) {
+              const float2 a = __fadd2_rn(make_float2(cs1.x, cs1.y), make_float2(o.x, o.y)), b2 = __fadd2_rn(make_float2(cs1.z, cs1.w), make_float2(o.z, o.w));
+              cs1 = make_float4(a.x, a.y, b2.x, b2.y);
+            }
             else {  // only when T < 128
               double* dst = p.colsum + (size_t)(b_first + sg) * kC + col0 + c4;
               atomicAdd(dst, (double)o.x); atomicAdd(dst + 1, (double)o.y);
@@ -548,6 +553,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
     if (MODE == 0) ostat.flush_warp(slots, warp);
     if (MODE == 1) {
       // row sums: the two column halves (warps w and w+4) own the same rows
+      const float rowacc = rowacc2.x + rowacc2.y;
       if (ch == 1) rs_x[my_rl] = rowacc;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (ch == 0 && my_rl < nrows) p.rowsum[r0 + my_rl] = rowacc + rs_x[my_rl];
