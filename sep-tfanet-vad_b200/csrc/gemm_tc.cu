@@ -482,14 +482,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (MODE != 1) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
       float4 cs0 = make_float4(0.f, 0.f, 0.f, 0.f), cs1 = cs0;   // column sums of the tile's 1st / 2nd utterance
+      // FAST: a full tile that touches at most two utterances (every tile but the tensor's last when T >= 128): no
+      // per-row bounds test and a two-way segment select, so the eight unrolled rows are straight-line code the
+      // scheduler can interleave; the guarded variant wrapped every row in its own divergence region, which serialised
+      // them (2000-2900 cycles per 32-column chunk in the clock64 timeline).
+      auto copy_out = [&](auto fast_tag) {
+      constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int i = it * 4 + (lane >> 3);
         const int rl = lq * 32 + i;
-        if (rl < nrows) {
+        if (FAST || rl < nrows) {
           float4 o = *reinterpret_cast<const float4*>(stg + i * kStgPitch + c4);
           const int row = r0 + rl;
-          const int sg = smap.seg(row);
+          const int sg = FAST ? (row >= smap.e1 ? 1 : 0) : smap.seg(row);
           if (MODE == 0) {
             // bias + PReLU (max(x, a x) for a <= 1, min otherwise: AMAX) + statistics on the packed fp32 pipe
             const float2 sl2 = make_float2(p.slope, p.slope);
@@ -502,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
             const float2 sv = __fadd2_rn(r0, r1), qv = __ffma2_rn(r1, r1, __fmul2_rn(r0, r0));
             const float s = sv.x + sv.y, q = qv.x + qv.y;
             if (sg == 0) { ostat.s0 += s; ostat.q0 += q; }
-            else if (sg == 1) { ostat.s1 += s; ostat.q1 += q; }
+            else if (FAST || sg == 1) { ostat.s1 += s; ostat.q1 += q; }
             else { atomicAdd(seg_acc + 2 * sg, s); atomicAdd(seg_acc + 2 * sg + 1, q); }
           } else if (MODE == 2) {
             o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
             if (sg == 0) {
               const float2 a = __fadd2_rn(make_float2(cs0.x, cs0.y), make_float2(o.x, o.y)), b2 = __fadd2_rn(make_float2(cs0.z, cs0.w), make_float2(o.z, o.w));
               cs0 = make_float4(a.x, a.y, b2.x, b2.y);
-            } else if (sg == 1) {
+            } else if (FAST || sg == 1) {
               const float2 a = __fadd2_rn(make_float2(cs1.x, cs1.y), make_float2(o.x, o.y)), b2 = __fadd2_rn(make_float2(cs1.z, cs1.w), make_float2(o.z, o.w));
               cs1 = make_float4(a.x, a.y, b2.x, b2.y);
             }
@@ -527,6 +533,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (int64_t)row * p.out_stride + gcol) = o;
         }
       }
+      };
+      if (nrows == kTileM && nseg <= 2) copy_out(std::true_type{}); else copy_out(std::false_type{});
       TLG(14 + cc * 4);
       if (MODE == 1) {
         // column sums: fold the 4 row groups of the warp, then one global atomic per column and utterance

@@ -343,6 +343,24 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
 // the dconv grid is still running takes SM slots away from it (measured: 5.86 ms per step with, 5.09 ms without).
 static int g_fused_pdl = 0;
 
+#ifdef SEPTFA_TIMELINE
+void resid_fused_dump_timeline() {   // bring-up: globaltimer stamps of the first 32 CTAs of the last launch
+  static unsigned long long h[32 * 128];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_fused_tl, sizeof(h));
+  for (int c = 0; c < 32; ++c) {
+    const unsigned long long* t = h + c * 128;
+    printf("cta %2d: start->pdl %6llu total %6llu |", c, t[1] - t[0], t[2] - t[0]);
+    for (int it = 0; it < 9; ++it) {
+      const unsigned long long* u = t + 8 + it * 8;
+      if (u[0] == 0) break;
+      printf(" [top@%llu gates %llu tile %llu ph1 %llu xchg %llu ph2 %llu]", u[0] - t[0], u[1] - u[0], u[2] - u[1], u[3] - u[2], u[4] - u[3], u[5] - u[4]);
+    }
+    printf("\n");
+  }
+}
+#endif
+
 int resid_fused_cluster_size(int T) {   // 0: the utterance does not fit one cluster (caller uses the streaming kernels)
   if (T > 8 * kMaxTc) return 0;
   return std::min(8, (T + 31) / 32);
