@@ -35,7 +35,7 @@ FS = 16000
 MAC_PER_FRAME = 4899657                     # algorithmic MACs per STFT frame
 DCONV_MAC_PER_FRAME = 131072 + 1536         # res_out 512->256 + depthwise k3 (the dominant kernel's share)
 CONV1_MAC_PER_FRAME = 65536
-DCONV_DRAM_BYTES_NCU = 34750208           # k_tc_gemm<1,1>, 256 x 4 s: 33.78 MB read + 0.97 MB written (profiles/r1_ncu_summary.md)
+DCONV_DRAM_BYTES_NCU = 34972160           # k_tc_gemm<1,1,1>, 256 x 4 s: 33.76 MB read + 1.21 MB written (profiles/r1_ncu_summary.md)
 
 
 def measured_peaks():
@@ -93,6 +93,31 @@ class ClockSampler:
             out = {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                    "samples": len(sm)}
         return out
+
+
+def hbm_kernels(kernels, M, B, L, peak_hbm, exports):
+    """Achieved HBM bandwidth of the bandwidth-class kernels: ALGORITHMIC bytes per step (compulsory traffic of the
+    layout in DESIGN.md section 2, stated per frame in DESIGN.md section 3) over the class's CUDA-event time."""
+    spec = 257 * 8 * M          # complex64 spectrogram
+    lg = 2 * 257 * 4 * M        # both speakers' mask logits
+    alg = {
+        # resid: read stream fp32 + accumulators fp16, write stream fp32 (24 launches)
+        "resid": 24 * M * (1024 + 512 + 1024),
+        # frontend: read x, write S and the gated dB stream (+ the optional spectrum export: read stream, write [B,257,T])
+        "frontend": B * L * 4 + spec + M * 1024 + ((M * 1024 + 257 * 4 * M) if exports else 0),
+        # istft: read logits, S and gate, write both waveforms
+        "istft": lg + spec + 2 * M * 4 + 2 * B * L * 4,
+        # export: read logits and S, write est (complex64), masks and logits in torch layout
+        "export": (lg + spec + 2 * spec + lg + lg) if exports else 0,
+    }
+    out = {}
+    for k, nbytes in alg.items():
+        ms = kernels.get(k, {}).get("ms_per_step", 0.0)
+        if ms <= 0 or nbytes == 0:
+            continue
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[k] = {"alg_bytes_per_step": int(nbytes), "ms_per_step": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak_hbm}
+    return out
 
 
 def cpu_reference_throughput(n_mix, length, repeats=1):
@@ -156,8 +181,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="mixtures per GPU per step")
     ap.add_argument("--length", type=int, default=64000, help="samples per mixture (4 s @ 16 kHz)")
-    ap.add_argument("--ref-sample", type=int, default=8, help="mixtures per step of the CPU reference arm")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="mixtures of the cpu_baseline leg")
+    ap.add_argument("--ref-sample", type=int, default=48, help="mixtures per step of the CPU reference arm (~3 s of CPU work)")
+    ap.add_argument("--cpu-sample", type=int, default=192, help="mixtures of the cpu_baseline leg (~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="skip the optional exports (est/mask/spectrum/logits)")
     ap.add_argument("--online-streams", type=int, default=1024, help="concurrent streams of the online leg (0 = skip)")
@@ -340,12 +365,13 @@ def main():
                          "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": DCONV_DRAM_BYTES_NCU if (B, L) == (256, 64000) else None,
                          "traffic_source": "profiles/r1_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one "
-                                           "k_tc_gemm<1,1> launch (ncu --set full); the other 31 MB of its 65.8 MB algorithmic "
+                                           "k_tc_gemm<1,1,1> launch (ncu --set full); the other 31 MB of its 65.8 MB algorithmic "
                                            "fp16 in/out bytes are served by / left in the 126 MB L2",
                          "peak_source": peak_src,
                          "ms_per_launch": dconv_ms, "flop_per_launch": flop_per_launch,
                          "conv1_tflops": conv1_tf},
             "kernels": kernels,
+            "hbm_kernels": hbm_kernels(kernels, M, B, L, peak_hbm, not a.lean),
             "e2e": {"value": audio_s / t_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                     "d2h_bytes_per_step": int(B * 2 * L * 4 + B * 2 * T * 4), "ms_per_step": 1e3 * t_e2e / a.steps,
                     "api": "SeparationModel.forward_host_submit / HostBatch.result (septfa_forward_host_submit / _wait), "

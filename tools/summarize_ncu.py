@@ -20,7 +20,7 @@ for r in data:
     v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
     agg.setdefault(r[ki].split("(")[0].replace("void ", "").replace("septfa::", "").replace("<unnamed>::", ""), []).append(v)
 tot = sum(sum(v) for v in agg.values())
-out.append(f"## Launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` over one forward, 256 x 4 s\n")
+out.append(f"## Launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` over four forwards of 256 x 4 s (tools/profile_round.sh)\n")
 out.append("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n")
 out.append("| kernel | launches | avg us | total ms | share |\n|---|---:|---:|---:|---:|")
 for k, v in agg.items():
