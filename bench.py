@@ -189,8 +189,11 @@ def main():
     ap.add_argument("--online-hops", type=int, default=12)
     a = ap.parse_args()
 
+    # NCCL logs (its version banner included, which WARN and VERSION both print) go to stdout by default and would
+    # precede the JSON line: send them to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout and would precede the JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
     if a.impl == "reference":
         for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
             os.environ[v] = str(os.cpu_count())  # torchrun forces OMP_NUM_THREADS=1

@@ -45,7 +45,7 @@ def run_golden(cuda_models, name, engine):
     st = meta["stride"]
     for i, kw in enumerate(meta["kws"]):
         out, vad, est = m(x, dict(kw) if kw else {})
-        assert m.last_launch_count > 75  # our kernels ran (no library / CPU path exists)
+        assert m.last_launch_count > 70  # our kernels ran (no library / CPU path exists)
         o = out.cpu().numpy()[..., ::st]
         ref = g[f"kw{i}_out"]
         assert o.shape == ref.shape
