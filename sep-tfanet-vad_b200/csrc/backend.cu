@@ -204,12 +204,16 @@ __global__ void __launch_bounds__(256) k_export(const float2* __restrict__ S, co
   pdl_wait();
   const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32, b = blockIdx.z >> 1, s = blockIdx.z & 1;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  // the spectrum-only call (before the TCN overwrites the stream in place) needs neither the logits nor S, and only
+  // its s == 0 blocks have work: it used to load 264 MB for nothing
+  const bool need_masks = mask != nullptr || logits_out != nullptr || est != nullptr;
+  if (!need_masks && s != 0) return;
   for (int i = ty; i < 32; i += 8) {
     const int t = t0 + i, f = f0 + tx;
     if (t < T && f < kBins) {
       const int64_t row = (int64_t)b * T + t;
-      tl[i][tx] = __ldg(logits + row * kLogitStride + s * kBins + f);
-      ts[i][tx] = __ldg(S + row * kBins + f);
+      if (need_masks) tl[i][tx] = __ldg(logits + row * kLogitStride + s * kBins + f);
+      if (est != nullptr) ts[i][tx] = __ldg(S + row * kBins + f);
       if (spectrum != nullptr && s == 0) tz[i][tx] = (f == 0) ? __ldg(dc_gated + row) : __ldg(z0 + row * kC + f - 1);
     }
   }
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(256) k_export(const float2* __restrict__ S, co
   for (int i = ty; i < 32; i += 8) {
     const int f = f0 + i, t = t0 + tx;
     if (t < T && f < kBins) {
-      const float lg = tl[tx][i];
+      const float lg = need_masks ? tl[tx][i] : 0.f;
       const float m = sigmoidf_fast(lg);
       const int64_t o = (((int64_t)b * 2 + s) * kBins + f) * T + t;
       if (mask != nullptr) mask[o] = m;

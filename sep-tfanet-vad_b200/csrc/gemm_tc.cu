@@ -51,9 +51,13 @@ using namespace tc;
 
 // Bring-up timeline (clock64 stamps of one CTA), compiled in only with -DSEPTFA_TIMELINE.
 #ifdef SEPTFA_TIMELINE
+__device__ unsigned long long g_cta_tl[1024 * 8];
+__device__ __forceinline__ unsigned long long gtimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CTL(k) do { if (MODE == 1 && threadIdx.x == 0 && blockIdx.x < 1024) g_cta_tl[blockIdx.x * 8 + (k)] = gtimer_ns(); } while (0)
 #define TLG(idx) do { if (p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 0 && threadIdx.x == 0 && (idx) < 64) p.dbg[idx] = clock64(); } while (0)
 #else
 #define TLG(idx) do { } while (0)
+#define CTL(k) do { } while (0)
 #endif
 
 __device__ __forceinline__ float4 ld_half4(const __half* p) {   // 4 consecutive halves (8 B) -> float4
@@ -79,9 +83,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   constexpr int OFF_W = NSPLIT * kAChunkBytes;
   constexpr uint32_t IDESC = make_idesc_f16(kTileM, NT);
 
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for the 128B swizzle; plain pointer arithmetic keeps the shared address space (LDS/STS)
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // 1024-byte alignment for the 128B swizzle. The kernel has no static shared memory, so the dynamic window starts at
+  // the CTA's (1 KB aligned) shared base; declaring the alignment lets every shared address be a compile-time offset
+  // from one base register (a run-time round-up was re-derived inside the producer loop under register pressure:
+  // S2UR CgaCtaId / LOP3 0x3f0 / IMAD chains in every chunk). Checked once instead of corrected.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0u) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE);
   uint64_t* full_a = bars;          // [kStages] producers -> MMA
   uint64_t* full_w = bars + 2;      // [kStages] bulk copy -> MMA
@@ -98,6 +105,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   float4* wB_s = wA_s + 256;                                                                  // {wz_a, wz_b, sw_a, sw_b}
   float2* wC_s = reinterpret_cast<float2*>(wB_s + 256);                                       // {c2f_a, c2f_b}
 
+  CTL(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * kTileM;
   const int nrows = min(kTileM, p.M - r0);
@@ -123,7 +131,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
     // has the shared-memory layout (consecutive c8 = consecutive 16 B: conflict-free LDS.128 across a warp)
     for (int i = threadIdx.x; i < kDconvWBytes / 16; i += kThreads) wA_s[i] = __ldg(p.wtab + i);
   }
+  CTL(1);
   pdl_wait();   // everything below reads what earlier kernels of the chain wrote
+  CTL(2);
   {
     const double inv_n = 1.0 / ((double)kC * p.T);
     for (int i = threadIdx.x; i < nseg; i += kThreads) {
@@ -144,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   TLG(0);
+  CTL(3);
 
   if (warp == 8) {
     // ------------------------------------------------------------ weight loader (TMA bulk copies)
@@ -452,6 +463,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
     // ------------------------------------------------------------ epilogue (warps 0-7)
     // warp w reads TMEM lanes 32*(w%4).. (rows) and columns (w/4)*NT/2 .. in chunks of 32.
     TLG(10);
+    CTL(4);
     mbar_wait(acc_full, 0, 500);
     tc_fence_after();
     TLG(11);
@@ -571,6 +583,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   tc_fence_before();
   __syncthreads();
   TLG(31);
+  CTL(5);
   if (warp == 9) tmem_dealloc(tmem_base, 256);
   Stat2* sdst = (MODE == 0) ? p.st_out : (MODE == 1 ? p.st_q : nullptr);
   if (sdst != nullptr && blockIdx.y == 0) seg_stats_commit(slots, 8, seg_acc, nseg, sdst + b_first);
@@ -587,6 +600,22 @@ void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
 }  // namespace
 
 long long* g_tl_conv1 = nullptr;  // bring-up timeline of one conv1 launch (SEPTFA_TIMELINE)
+
+#ifdef SEPTFA_TIMELINE
+void gemm_dump_cta_timeline(int ncta) {   // wall-clock phases of every CTA of the last dconv launch
+  static unsigned long long h[1024 * 8];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_cta_tl, sizeof(h));
+  unsigned long long t0 = ~0ull, t1 = 0;
+  for (int c = 0; c < ncta; ++c) { if (h[c * 8] < t0) t0 = h[c * 8]; if (h[c * 8 + 5] > t1) t1 = h[c * 8 + 5]; }
+  printf("dconv grid: %d CTAs, first start -> last end %llu ns\n", ncta, t1 - t0);
+  printf("cta start pre_pdl pdl_wait setup loop epilogue end\n");
+  for (int c = 0; c < ncta; c += (c < 8 || c > ncta - 9 || (c >= 296 && c < 304)) ? 1 : 37) {
+    const unsigned long long* t = h + c * 8;
+    printf("%4d %7llu %6llu %6llu %6llu %6llu %6llu %7llu\n", c, t[0] - t0, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[5] - t0);
+  }
+}
+#endif
 
 template <int MODE, bool H16, bool AMAX = true>
 cudaError_t setup_one(int smem) {

@@ -132,6 +132,7 @@ int resid_fused_cluster_size(int T);   // 0: the utterance does not fit one clus
 bool launch_resid_fused(const ResidParams& rp, const GateParams& gp, cudaStream_t st);
 #ifdef SEPTFA_TIMELINE
 void resid_fused_dump_timeline();
+void gemm_dump_cta_timeline(int ncta);
 #endif
 // gemm_tc.cu
 void launch_tc_conv1(const Conv1Params& p, cudaStream_t st);

@@ -729,6 +729,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   prof_mark(h, -1, st);
 #ifdef SEPTFA_TIMELINE
   if (getenv("SEPTFA_FUSED_TL")) resid_fused_dump_timeline();
+  if (getenv("SEPTFA_GEMM_TL")) gemm_dump_cta_timeline((M + 127) / 128);
 #endif
   if (getenv("SEPTFA_TIMELINE")) {
     long long* dptr = nullptr;
