@@ -473,6 +473,61 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
     float2 rowacc2 = make_float2(0.f, 0.f);
     SegStat2 ostat;
     constexpr int NCC = NT / 64;            // 32-column chunks per column half
+    if constexpr (MODE == 0 && H16) {
+      // conv1: the thread that owns TMEM lane (= row) my_rl finishes its 32 columns itself - bias, PReLU, statistics,
+      // fp16 pack - and parks them in a row-major tile in shared memory (pitch 528 B: conflict-free 16 B stores);
+      // when both column halves are in, one TMA bulk store per row (512 contiguous bytes) writes the tile. No fp32
+      // transpose through shared memory, no per-element segment routing (a row has ONE segment), no store instructions
+      // in the warps: the staged version spent half the CTA's lifetime in its copy-out (12 k of 24 k cycles).
+      constexpr int kRowPitch = kC * 2 + 16;
+      uint8_t* tile = smem;                                   // aliases the (now idle) stage buffers: 128 x 528 B
+      const bool valid = my_rl < nrows;
+      const float2 sl2 = make_float2(p.slope, p.slope);
+      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+      for (int cc = 0; cc < NCC; ++cc) {
+        const int col0 = ch * (NT / 2) + cc * 32;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)col0, v);
+        TLG(12 + cc * 4);
+        uint4* dst = reinterpret_cast<uint4*>(tile + my_rl * kRowPitch + col0 * 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t h[4];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int c = 8 * i + 4 * k;
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));   // same address in every lane
+            const float2 x0 = __fadd2_rn(make_float2(v[c], v[c + 1]), make_float2(b4.x, b4.y));
+            const float2 x1 = __fadd2_rn(make_float2(v[c + 2], v[c + 3]), make_float2(b4.z, b4.w));
+            const float2 a0 = __fmul2_rn(sl2, x0), a1 = __fmul2_rn(sl2, x1);
+            float2 y0, y1;
+            if constexpr (AMAX) { y0 = make_float2(fmaxf(x0.x, a0.x), fmaxf(x0.y, a0.y)); y1 = make_float2(fmaxf(x1.x, a1.x), fmaxf(x1.y, a1.y)); }
+            else { y0 = make_float2(fminf(x0.x, a0.x), fminf(x0.y, a0.y)); y1 = make_float2(fminf(x1.x, a1.x), fminf(x1.y, a1.y)); }
+            s2 = __fadd2_rn(s2, __fadd2_rn(y0, y1));
+            q2 = __ffma2_rn(y0, y0, q2);
+            q2 = __ffma2_rn(y1, y1, q2);
+            h[2 * k] = pack_half2(y0.x, y0.y);
+            h[2 * k + 1] = pack_half2(y1.x, y1.y);
+          }
+          dst[i] = make_uint4(h[0], h[1], h[2], h[3]);
+        }
+        TLG(14 + cc * 4);
+      }
+      if (valid) {
+        const int sg = smap.seg(r0 + my_rl);
+        const float sv = s2.x + s2.y, qv = q2.x + q2.y;
+        if (sg == 0) { ostat.s0 = sv; ostat.q0 = qv; }
+        else if (sg == 1) { ostat.s1 = sv; ostat.q1 = qv; }
+        else { atomicAdd(seg_acc + 2 * sg, sv); atomicAdd(seg_acc + 2 * sg + 1, qv); }
+      }
+      fence_proxy_async();                                     // our generic-proxy stores -> visible to the bulk copy
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // both column halves of every row are in the tile
+      if (ch == 0 && valid) {
+        bulk_copy_s2g(reinterpret_cast<__half*>(p.out) + (int64_t)(r0 + my_rl) * p.out_stride, tile + my_rl * kRowPitch, kC * 2);
+        bulk_commit_group();
+        bulk_wait_read_all();                                  // the tile must outlive the copy's reads
+      }
+    } else
     for (int cc = 0; cc < NCC; ++cc) {
       const int col0 = ch * (NT / 2) + cc * 32;
       float v[32];
