@@ -695,6 +695,7 @@ cudaError_t tc_gemm_setup() {
 }
 
 void launch_tc_conv1(const Conv1Params& c, cudaStream_t st) {
+  if (launch_conv1_persist(c, st)) return;   // persistent warp-specialised kernel (T >= 128, fp16 activations)
   TcParams p{};
   p.M = c.M; p.T = c.T; p.B = c.B;
   p.w_img = c.w_img; p.in = c.w_in; p.norm = c.norm;

@@ -134,6 +134,9 @@ bool launch_resid_fused(const ResidParams& rp, const GateParams& gp, cudaStream_
 void resid_fused_dump_timeline();
 void gemm_dump_cta_timeline(int ncta);
 #endif
+// gemm_conv1_persist.cu
+cudaError_t conv1_persist_setup();
+bool launch_conv1_persist(const Conv1Params& p, cudaStream_t st);   // false: not applicable, use launch_tc_conv1's kernel
 // gemm_tc.cu
 void launch_tc_conv1(const Conv1Params& p, cudaStream_t st);
 void launch_tc_dconv(const DconvParams& p, cudaStream_t st);
