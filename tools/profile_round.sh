@@ -10,10 +10,10 @@ PY="python tools/profile_step.py 256 64000 3"     # 4 forwards of 256 x 4 s; the
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${TAG}.csv $PY > $OUT/ncu_launches_${TAG}.log 2>&1
 # 2. per forward: 1 frontend, 24 x (conv1, dconv, resid), out_stats, outconv, vad_final, istft, export = 78 launches
 #    block kernels: frontend + first block of the 4th forward
-ncu --set full --clock-control none --import-source on -k regex:"k_frontend|k_tc_gemm|k_resid_persist" -s 222 -c 4 \
+ncu --set full --clock-control none --import-source on -k regex:"k_frontend|k_conv1_persist|k_tc_gemm|k_resid_persist" -s 222 -c 4 \
     -o $OUT/prof_block_${TAG} -f $PY > $OUT/ncu_block_${TAG}.log 2>&1
-#    output conv = the 49th k_tc_gemm launch of a forward
-ncu --set full --clock-control none --import-source on -k regex:"k_tc_gemm" -s 195 -c 1 \
+#    output conv = the 25th k_tc_gemm launch of a forward (24 dconv + 1; conv1 is k_conv1_persist)
+ncu --set full --clock-control none --import-source on -k regex:"k_tc_gemm" -s 99 -c 1 \
     -o $OUT/prof_outconv_${TAG} -f $PY > $OUT/ncu_outconv_${TAG}.log 2>&1
 #    back-end kernels of the 4th forward
 ncu --set full --clock-control none --import-source on -k regex:"k_out_stats|k_vad_final|k_mask_istft|k_export" -s 12 -c 4 \
