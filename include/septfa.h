@@ -102,7 +102,9 @@ const char* septfa_key_name(const septfa_handle* h, int i);
 int64_t septfa_key_numel(const septfa_handle* h, int i);
 
 /* name = "engine" (SEPTFA_ENGINE_*), "profile" (0/1), "host_chunks" (0 = automatic, 1..8: number of
- * batch chunks septfa_forward_host pipelines over its two stream lanes). */
+ * batch chunks septfa_forward_host pipelines over its two stream lanes); kernel-selection switches for
+ * cross-checks (default 1): "fused_resid" (cluster-resident gate + residual kernel), "conv1_persist"
+ * (persistent warp-specialised conv1 kernel), "pdl" (programmatic dependent launch of the kernel chain). */
 int septfa_set_option(septfa_handle* h, const char* name, int value);
 int septfa_get_option(const septfa_handle* h, const char* name);
 

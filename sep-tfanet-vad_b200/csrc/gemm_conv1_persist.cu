@@ -252,10 +252,11 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_conv1_persist(PersistParams p)
   if (warp == 13) tmem_dealloc(tmem_base, 512);
 }
 
-int g_conv1_persist = 1;
 int g_sm_count = 0;
 
 }  // namespace
+
+int g_conv1_persist = 1;   // option "conv1_persist" / SEPTFA_CONV1_PERSIST: 0 = always the one-tile-per-CTA kernel
 
 cudaError_t conv1_persist_setup() {
   if (const char* e = getenv("SEPTFA_CONV1_PERSIST")) g_conv1_persist = atoi(e);

@@ -135,6 +135,7 @@ void resid_fused_dump_timeline();
 void gemm_dump_cta_timeline(int ncta);
 #endif
 // gemm_conv1_persist.cu
+extern int g_conv1_persist;
 cudaError_t conv1_persist_setup();
 bool launch_conv1_persist(const Conv1Params& p, cudaStream_t st);   // false: not applicable, use launch_tc_conv1's kernel
 // gemm_tc.cu

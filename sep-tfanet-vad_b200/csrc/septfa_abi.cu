@@ -384,6 +384,10 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
     h->profile = value ? 1 : 0;
     return 0;
   }
+  if (std::strcmp(name, "conv1_persist") == 0) {
+    g_conv1_persist = value ? 1 : 0;   // process-wide, like "pdl"
+    return 0;
+  }
   if (std::strcmp(name, "fused_resid") == 0) {
     h->fused_resid = value ? 1 : 0;
     return 0;

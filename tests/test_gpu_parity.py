@@ -183,6 +183,29 @@ def test_fused_residual_kernel_equals_streaming_kernels(cuda_models, cfg_name, B
         assert torch.equal(o1, o2)
 
 
+@pytest.mark.parametrize("B,L", [(3, 64000), (2, 40000), (1, 200000)])
+def test_persistent_conv1_equals_one_tile_kernel(cuda_models, B, L):
+    """The persistent warp-specialised conv1 kernel (gemm_conv1_persist.cu: double-buffered TMEM, TMA bulk stores)
+    against the one-tile-per-CTA kernel (gemm_tc.cu MODE 0) on the same buffers: identical operands and accumulation,
+    only the grouping of the statistics' partial sums differs -> agreement to the fp16 operand noise level; and the
+    persistent kernel is bit-reproducible run to run."""
+    args = synth.CONFIG_WITH_VAD
+    m = cuda_models(args, 34, 0)
+    x = torch.from_numpy(synth.make_mixtures(B, L, 778)).cuda()
+    try:
+        m.set_option("conv1_persist", 0)
+        o0, v0, _ = m(x, {})
+        m.set_option("conv1_persist", 1)
+        o1, v1, _ = m(x, {})
+        o2, v2, _ = m(x, {})
+    finally:
+        m.set_option("conv1_persist", 1)
+    assert (o1 - o0).abs().max().item() < 5e-4
+    assert sisdr_db(o1.cpu().numpy(), o0.cpu().numpy()) > 60
+    assert (v1 - v0).abs().max().item() < 2e-3
+    assert torch.equal(o1, o2) and torch.equal(v1, v2)
+
+
 def test_batch_invariance_and_determinism(cuda_models):
     """Utterances are independent: item b of a batch equals the same item run alone up to the fp16
     operand noise (tiles straddle utterances differently, so the statistics' partial sums - and with
