@@ -230,6 +230,28 @@ def test_batch_invariance_and_determinism(cuda_models):
     assert (os1 - os2).abs().max().item() < 5e-4 and (vs1 - vs2).abs().max().item() < 1e-3
 
 
+def test_reproducible_under_disturbed_timing(cuda_models):
+    """Race check for the persistent / cluster kernels (mbarrier pipelines, single-buffer TMA refill, DSMEM exchange):
+    the same forward repeated while a second stream hammers the memory system must stay bit-identical."""
+    args = synth.CONFIG_WITH_VAD
+    m = cuda_models(args, 35, 0)
+    x = torch.from_numpy(np.tile(synth.make_mixtures(16, 48000, 321), (4, 1))).cuda()   # 64 x 3 s: T = 188, 6-CTA clusters
+    side = torch.cuda.Stream()
+    junk = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
+    ref = None
+    for i in range(6):
+        if i % 2 == 1:
+            with torch.cuda.stream(side):
+                for _ in range(10):
+                    junk.fill_(i)
+        out, vad, _ = m(x, {})
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = (out.clone(), vad.clone())
+        else:
+            assert torch.equal(out, ref[0]) and torch.equal(vad, ref[1]), f"run {i} differs"
+
+
 def test_forward_host_equals_forward(cuda_models):
     args = synth.CONFIG_WITH_VAD
     m = cuda_models(args, 33, 0)
