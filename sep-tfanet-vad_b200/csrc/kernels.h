@@ -143,6 +143,7 @@ void launch_tc_conv1(const Conv1Params& p, cudaStream_t st);
 void launch_tc_dconv(const DconvParams& p, cudaStream_t st);
 void launch_tc_outconv(const OutConvParams& p, cudaStream_t st);
 extern long long* g_tl_conv1;
+extern int g_dconv_late_trigger;
 cudaError_t tc_gemm_setup();  // opt-in shared memory attributes; call once per device
 // backend.cu
 struct VadParams {

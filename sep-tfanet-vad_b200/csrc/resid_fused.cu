@@ -339,9 +339,11 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
 
 }  // namespace
 
-// Programmatic early launch of the cluster kernel is OFF: a persistent grid that becomes resident while the tail of
-// the dconv grid is still running takes SM slots away from it (measured: 5.86 ms per step with, 5.09 ms without).
-static int g_fused_pdl = 0;
+// Programmatic early launch of the persistent cluster kernel: only safe because its predecessor (the dconv kernel)
+// triggers its dependents late, at the start of each CTA's epilogue. With the usual trigger at kernel entry the
+// persistent grid became resident while the dconv grid's second wave still needed the SM slots (5.86 vs 5.09 ms per
+// step); with the late trigger the early launch hides the launch latency instead (3.75 -> 3.70 ms).
+static int g_fused_pdl = 1;
 
 #ifdef SEPTFA_TIMELINE
 void resid_fused_dump_timeline() {   // bring-up: globaltimer stamps of the first 32 CTAs of the last launch
@@ -412,7 +414,7 @@ static void launch_cluster(K kernel, const FusedParams& p, int nclusters, int cs
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = (g_use_pdl && g_fused_pdl) ? 2 : 1;
+  cfg.numAttrs = (g_use_pdl && g_fused_pdl && g_dconv_late_trigger) ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kernel, p);
   ++g_launch_count;
 }
