@@ -173,6 +173,12 @@ int septfa_online_hops_done(const septfa_online* st);
 int septfa_pit_l1(septfa_handle* h, const float* a, const float* b, int S, int64_t n, int32_t* perm, double* pw_sums,
                   void* stream);
 
+/* Pre-processing of only_inference.py:81, batched on the device: per utterance
+ *   out = 1.8 * (x - min(x)) / (max(x) - min(x)) - 0.9        (float32, the reference's operation order: bit-identical
+ * to numpy; a constant signal gives NaN like the reference). x, out: device [B, L]; lengths (nullable, device int64 [B]):
+ * valid samples per utterance for ragged batches - extrema over the valid part, zeros written behind it. */
+int septfa_minmax_normalize(septfa_handle* h, const float* x, int B, int64_t L, const int64_t* lengths, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,6 +134,9 @@ bool launch_resid_fused(const ResidParams& rp, const GateParams& gp, cudaStream_
 void resid_fused_dump_timeline();
 void gemm_dump_cta_timeline(int ncta);
 #endif
+// preproc.cu
+void launch_minmax_normalize(const float* x, int B, int64_t L, const int64_t* lengths /*nullable*/, unsigned* ext /*[B][2] scratch*/,
+                             float* out, cudaStream_t st);
 // gemm_conv1_persist.cu
 extern int g_conv1_persist;
 cudaError_t conv1_persist_setup();

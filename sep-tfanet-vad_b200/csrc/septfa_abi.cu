@@ -60,6 +60,7 @@ struct septfa_handle {
   // forward_host resources
   cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
   cudaEvent_t hev_in[8] = {}, hev_done[8] = {};
+  unsigned* norm_ext = nullptr; int norm_cap = 0;   // septfa_minmax_normalize scratch
   int host_chunks = 0;  // 0 = automatic
   struct HostSlot {      // septfa_forward_host_submit / _wait
     cudaStream_t stream = nullptr;          // copies of this slot
@@ -334,6 +335,7 @@ void septfa_destroy(septfa_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
+  cudaFree(h->norm_ext);
   cudaFree(h->hx_dev); cudaFree(h->hout_dev); cudaFree(h->hvad_dev); cudaFree(h->hws); cudaFree(h->hws_b); cudaFree(h->pit_acc);
   if (h->slot_compute) { cudaStreamSynchronize(h->slot_compute); cudaStreamDestroy(h->slot_compute); }
   for (auto& sl : h->slots) {
@@ -1034,6 +1036,20 @@ int septfa_pit_l1(septfa_handle* h, const float* a, const float* b, int S, int64
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   launch_pit(a, 2 * n, n, b, 2 * n, n, S, n, h->pit_acc, perm, st);
   if (pw_sums) CUDA_TRY(h, cudaMemcpyAsync(pw_sums, h->pit_acc, (size_t)S * 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+int septfa_minmax_normalize(septfa_handle* h, const float* x, int B, int64_t L, const int64_t* lengths, float* out, void* stream) {
+  if (!h || !x || !out || B < 1 || L < 1) return fail(h, SEPTFA_E_INVALID, "bad arguments");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->norm_cap < B) {
+    cudaFree(h->norm_ext); h->norm_ext = nullptr; h->norm_cap = 0;
+    CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->norm_ext), (size_t)B * 2 * sizeof(unsigned)));
+    h->norm_cap = B;
+  }
+  launch_minmax_normalize(x, B, L, lengths, h->norm_ext, out, reinterpret_cast<cudaStream_t>(stream));
+  h->last_launches = 3;
   CUDA_TRY(h, cudaGetLastError());
   return 0;
 }

@@ -230,6 +230,25 @@ class SeparationModel(nn.Module):
             return out, vad.unsqueeze(2)
         return out, vad
 
+    def minmax_normalize(self, x: torch.Tensor, lengths=None):
+        """only_inference.py:81 on the device, batched: ``1.8 * (x - x.min()) / (x.max() - x.min()) - 0.9`` per
+        utterance of ``x [B, L]`` (float32 CUDA), bit-identical to the reference's numpy expression. ``lengths``
+        (optional int64 ``[B]``): valid samples per utterance of a zero-padded ragged batch."""
+        assert x.ndim == 2 and x.is_cuda and x.dtype == torch.float32
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        if lengths is not None:
+            lengths = torch.as_tensor(lengths, dtype=torch.int64, device=x.device).contiguous()
+            assert lengths.numel() == x.shape[0]
+        with torch.cuda.device(x.device):
+            h = self._handle(x.device)
+            rc = h.lib.septfa_minmax_normalize(h.ptr, C.c_void_p(x.data_ptr()), x.shape[0], x.shape[1],
+                                               C.c_void_p(lengths.data_ptr()) if lengths is not None else None,
+                                               C.c_void_p(out.data_ptr()),
+                                               C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+            _lib.check(h.ptr, rc)
+        return out
+
     def forward_host_submit(self, x_host: torch.Tensor, inference_kw={}, device=0, slot=0, out=None, vad=None):
         """Asynchronous half of :meth:`forward_host` (septfa_forward_host_submit): enqueue copy-in, forward and
         copy-out of one batch on pipeline slot 0 or 1 and return a :class:`HostBatch` whose ``result()`` waits for

@@ -284,6 +284,34 @@ def test_forward_host_stream_equals_forward(cuda_models):
     f.result()
 
 
+def test_minmax_normalize_bit_exact(cuda_models):
+    """Device pre-processing: the min-max normalisation of only_inference.py:81, batched,
+    against the reference's own numpy expression - bit-exact, including ragged batches and the constant-signal NaN."""
+    m = cuda_models(synth.CONFIG_WITH_VAD, 31, 0)
+    rng = np.random.default_rng(7)
+    B, L = 5, 50021
+    x = (rng.standard_normal((B, L)) * rng.uniform(0.01, 30.0, (B, 1))).astype(np.float32)
+    x[1] = -np.abs(x[1]) - 3.0            # all-negative utterance
+    x[2] = np.round(x[2] * 100.0)         # int16-like magnitudes, as scipy.io.wavfile.read yields
+    ref = np.stack([1.8 * (a - a.min()) / (a.max() - a.min()) - 0.9 for a in x])     # only_inference.py:81 verbatim
+    got = m.minmax_normalize(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, ref.astype(np.float32))
+    assert got.min() == np.float32(-0.9) and abs(got.max() - 0.9) < 1e-6
+    # ragged: extrema over the valid part only, zeros behind it
+    lens = np.array([L, 1234, 40000, 7, L - 1])
+    xr = x.copy()
+    for b, n in enumerate(lens):
+        xr[b, n:] = 1e9                   # garbage in the padding must not matter
+    got = m.minmax_normalize(torch.from_numpy(xr).cuda(), lens).cpu().numpy()
+    for b, n in enumerate(lens):
+        a = x[b, :n]
+        assert np.array_equal(got[b, :n], (1.8 * (a - a.min()) / (a.max() - a.min()) - 0.9).astype(np.float32))
+        assert not got[b, n:].any()
+    # constant signal: 0 / 0 like the reference
+    c = torch.full((1, 1000), 0.25, device="cuda")
+    assert torch.isnan(m.minmax_normalize(c)).all()
+
+
 def test_error_behaviour(cuda_models):
     m = cuda_models(synth.CONFIG_WITH_VAD, 33, 0)
     with pytest.raises(AssertionError):           # model/model.py:406
