@@ -179,6 +179,12 @@ int septfa_pit_l1(septfa_handle* h, const float* a, const float* b, int S, int64
  * valid samples per utterance for ragged batches - extrema over the valid part, zeros written behind it. */
 int septfa_minmax_normalize(septfa_handle* h, const float* x, int B, int64_t L, const int64_t* lengths, float* out, void* stream);
 
+/* calc_sisdr (model/combined_loss.py:16-56): SI-SDR in dB of `rows` pairs preds[rows, n] / target[rows, n] (device,
+ * float32, contiguous) in one pass; out_db device [rows]; scratch: device, rows * 5 doubles; rows <= 65535. Runs on the
+ * current device (no handle). The online drivers use it for the online-vs-offline quality report of test.py:223-269. */
+int septfa_sisdr(const float* preds, const float* target, int64_t rows, int64_t n, int zero_mean, float* out_db, double* scratch,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

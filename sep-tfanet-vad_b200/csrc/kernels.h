@@ -137,6 +137,8 @@ void gemm_dump_cta_timeline(int ncta);
 // preproc.cu
 void launch_minmax_normalize(const float* x, int B, int64_t L, const int64_t* lengths /*nullable*/, unsigned* ext /*[B][2] scratch*/,
                              float* out, cudaStream_t st);
+void launch_sisdr(const float* p, const float* t, int64_t rows, int64_t n, int zero_mean, double* scratch /*[rows][5]*/, float* out,
+                  cudaStream_t st);
 // gemm_conv1_persist.cu
 extern int g_conv1_persist;
 cudaError_t conv1_persist_setup();

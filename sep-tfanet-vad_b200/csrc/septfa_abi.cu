@@ -1054,4 +1054,11 @@ int septfa_minmax_normalize(septfa_handle* h, const float* x, int B, int64_t L, 
   return 0;
 }
 
+int septfa_sisdr(const float* preds, const float* target, int64_t rows, int64_t n, int zero_mean, float* out_db, double* scratch,
+                 void* stream) {
+  if (!preds || !target || !out_db || !scratch || rows < 1 || rows > 65535 || n < 1) return SEPTFA_E_INVALID;
+  launch_sisdr(preds, target, rows, n, zero_mean, scratch, out_db, reinterpret_cast<cudaStream_t>(stream));
+  return cudaGetLastError() == cudaSuccess ? 0 : SEPTFA_E_CUDA;
+}
+
 }  // extern "C"

@@ -28,6 +28,20 @@ def calc_sisdr(preds, target, zero_mean=True):
     if preds.shape != target.shape:
         raise RuntimeError(f"Predictions and targets are expected to have the same shape, pred has shape of "
                            f"{preds.shape} and target has shape of {target.shape}")
+    if (preds.is_cuda and target.is_cuda and preds.dtype == torch.float32 and target.dtype == torch.float32
+            and preds.ndim >= 1 and 0 < preds.numel() // preds.shape[-1] <= 65535):
+        # one fused pass on the device (septfa_sisdr: five moments per row in double), ~1e-3 dB from the element-wise form
+        n = preds.shape[-1]
+        p2, t2 = preds.detach().reshape(-1, n).contiguous(), target.detach().reshape(-1, n).contiguous()
+        out = torch.empty(p2.shape[0], dtype=torch.float32, device=preds.device)
+        scratch = torch.empty(p2.shape[0] * 5, dtype=torch.float64, device=preds.device)
+        with torch.cuda.device(preds.device):
+            rc = _lib.load().septfa_sisdr(C.c_void_p(p2.data_ptr()), C.c_void_p(t2.data_ptr()), p2.shape[0], n, int(bool(zero_mean)),
+                                          C.c_void_p(out.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                          C.c_void_p(torch.cuda.current_stream(preds.device).cuda_stream))
+        if rc != 0:
+            raise _lib.SeptfaError(f"septfa_sisdr failed ({rc})")
+        return out.reshape(preds.shape[:-1])
     eps = torch.finfo(preds.dtype).eps
     if zero_mean:
         target = target - torch.mean(target, dim=-1, keepdim=True)

@@ -312,6 +312,34 @@ def test_minmax_normalize_bit_exact(cuda_models):
     assert torch.isnan(m.minmax_normalize(c)).all()
 
 
+def test_sisdr_kernel_matches_reference_formula(cuda_models):
+    """septfa_sisdr (one-pass moments in double) against calc_sisdr of model/combined_loss.py:16-56 evaluated
+    element-wise in float64 on the host, over 0 .. 60 dB, both zero_mean settings; and the docstring example."""
+    from septfa_b200.pit import calc_sisdr
+    rng = np.random.default_rng(11)
+    n = 48000
+    tgt = rng.standard_normal((6, 2, n)).astype(np.float32) * 0.1 + 0.02
+    noise = rng.standard_normal((6, 2, n)).astype(np.float32) * 0.1
+    snr = np.array([0.0, 10.0, 20.0, 30.0, 45.0, 60.0])[:, None, None]
+    est = (0.7 * tgt + noise * 10.0 ** (-snr / 20.0)).astype(np.float32)
+
+    def ref_formula(p, t, zero_mean):
+        p, t = p.astype(np.float64), t.astype(np.float64)
+        eps = np.finfo(np.float32).eps
+        if zero_mean:
+            p, t = p - p.mean(-1, keepdims=True), t - t.mean(-1, keepdims=True)
+        alpha = ((p * t).sum(-1, keepdims=True) + eps) / ((t ** 2).sum(-1, keepdims=True) + eps)
+        ts = alpha * t
+        return 10 * np.log10(((ts ** 2).sum(-1) + eps) / (((ts - p) ** 2).sum(-1) + eps))
+
+    for zm in (True, False):
+        got = calc_sisdr(torch.from_numpy(est).cuda(), torch.from_numpy(tgt).cuda(), zero_mean=zm).cpu().numpy()
+        assert got.shape == (6, 2)
+        assert np.abs(got - ref_formula(est, tgt, zm)).max() < 1e-2, (zm, got, ref_formula(est, tgt, zm))
+    ex = calc_sisdr(torch.tensor([2.5, 0.0, 2.0, 8.0]).cuda(), torch.tensor([3.0, -0.5, 2.0, 7.0]).cuda(), zero_mean=False)
+    assert abs(ex.item() - 18.4030) < 1e-3            # the example in the reference's docstring
+
+
 def test_error_behaviour(cuda_models):
     m = cuda_models(synth.CONFIG_WITH_VAD, 33, 0)
     with pytest.raises(AssertionError):           # model/model.py:406
