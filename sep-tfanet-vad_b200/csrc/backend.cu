@@ -86,12 +86,12 @@ void launch_vad(const VadParams& p, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Mask application + inverse STFT + overlap-add. One CTA = 7 consecutive 256-sample output blocks of one utterance,
+// Mask application + inverse STFT + overlap-add. One CTA = 15 consecutive 256-sample output blocks of one utterance,
 // BOTH speakers: the two Hermitian spectra share one complex FFT (Z = E0 + i E1 -> z = e0 + i e1). The 8 frames the
 // blocks need are transformed four at a time by the CTA's four 64-thread groups (radix-8 FFT, fft512.cuh).
 //   E_s[f] = S[t,f] * sigmoid(logit[s,f,t]) * gate[s,t]                    (model.py:429-437,452-455)
 //   out[256 j + n] = (w[256+n] fr_j[256+n] + w[n] fr_{j+1}[n]) / (w[256+n]^2 + w[n]^2)        (:460)
-constexpr int kIstftBlocks = 7;
+constexpr int kIstftBlocks = 15;   // output blocks per CTA = 16 frames in 4 rounds of 4 FFTs (one frame of overlap with the neighbour CTA: 6 % redundant)
 
 __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S, const float* __restrict__ logits,
                                                     const float* __restrict__ gate, const float* __restrict__ window,
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S
   float* out0 = out + ((int64_t)b * 2) * L;
   float* out1 = out0 + L;
   const int t_last = min(j0 + kIstftBlocks, T - 1);   // frames j0 .. t_last
-  for (int round = 0; round < 2; ++round) {
+  for (int round = 0; round < (kIstftBlocks + 1) / 4; ++round) {
     const int tbase = j0 + round * 4;
     if (tbase > t_last) break;                        // uniform
     const int t = tbase + grp;                        // this group's frame
