@@ -36,7 +36,8 @@ constexpr int kEpiWarpBytes = 32 * kEpiPitch; // 16896 B per epilogue warp
 constexpr int kOffA = 0;
 constexpr int kOffW = kOffA + kAStages * kABytes;
 constexpr int kOffEpi = kOffW + kWStages * kWBytes;
-constexpr int kOffBar = kOffEpi + 4 * kEpiWarpBytes;
+constexpr int kOffBias = kOffEpi + 4 * kEpiWarpBytes;   // [256] fp32 bias (broadcast LDS instead of 8 uniform LDG per 32 columns)
+constexpr int kOffBar = kOffBias + 1024;
 constexpr int kSmemBytes = kOffBar + 256;
 constexpr int kThreadsP = 14 * 32;
 
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_conv1_persist(PersistParams p)
   uint64_t* acc_full = bars + 10;             // [2] MMA commit
   uint64_t* acc_empty = bars + 12;            // [2] 128 epilogue arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
   constexpr uint32_t IDESC = make_idesc_f16(kTileM, 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_conv1_persist(PersistParams p)
     fence_mbar_init();
   }
   if (warp == 13) tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x < kC) bias_s[threadIdx.x] = __ldg(p.bias + threadIdx.x);   // static weights: before the dependency wait
   pdl_launch_dependents();
   pdl_wait();
   tc_fence_before();
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_conv1_persist(PersistParams p)
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const int c = 8 * i + 4 * k;
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));   // same address in every lane
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + c);   // same address in every lane: broadcast
             const float2 x0 = __fadd2_rn(make_float2(v[c], v[c + 1]), make_float2(b4.x, b4.y));
             const float2 x1 = __fadd2_rn(make_float2(v[c + 2], v[c + 3]), make_float2(b4.z, b4.w));
             const float2 a0 = __fmul2_rn(sl2, x0), a1 = __fmul2_rn(sl2, x1);
