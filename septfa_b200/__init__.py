@@ -1,12 +1,24 @@
-"""Import alias: the package lives in ``sep-tfanet-vad_b200/`` (not a valid Python identifier),
-so ``import septfa_b200`` loads that directory as the package ``septfa_b200``."""
-import importlib.util as _ilu
-import os as _os
-import sys as _sys
+"""septfa_b200 - B200-native (sm_100a) Sep-TFAnet-VAD inference forward pass.
 
-_dir = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "sep-tfanet-vad_b200")
-_spec = _ilu.spec_from_file_location("septfa_b200", _os.path.join(_dir, "__init__.py"),
-                                     submodule_search_locations=[_dir])
-_mod = _ilu.module_from_spec(_spec)
-_sys.modules["septfa_b200"] = _mod
-_spec.loader.exec_module(_mod)
+Drop-in for ``model/model.py::SeparationModel`` and the sliding-window online drivers of the
+reference (BaekMS/Sep-TFAnet-VAD); the arithmetic runs in hand-written CUDA kernels behind the
+C ABI declared in ``include/septfa.h``. Submodules are imported lazily so that the CPU-only
+utilities (``synth``) work without torch or the CUDA library.
+"""
+import importlib as _importlib
+
+__all__ = ["SeparationModel", "OnlineSaving", "OnlineSavingKnownTargets", "PITLossWrapper",
+           "reorder_source_mse", "calc_sisdr", "synth"]
+
+_LAZY = {
+    "SeparationModel": "model", "OnlineSaving": "online", "OnlineSavingKnownTargets": "online",
+    "PITLossWrapper": "pit", "reorder_source_mse": "pit", "calc_sisdr": "pit",
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        return getattr(_importlib.import_module(f"{__name__}.{_LAZY[name]}"), name)
+    if name in ("synth", "model", "online", "pit", "lib", "weights", "shard", "inference"):
+        return _importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

@@ -7,8 +7,11 @@
 
 namespace septfa {
 
-int g_launch_count = 0;
-int g_use_pdl = 1;
+// Launch context of the calling thread: every C-ABI entry binds its handle's context (kernels.h), so options such as
+// "pdl" or "conv1_persist" and the launch counter are per handle, not process-wide.
+namespace { LaunchCtx g_default_ctx; thread_local LaunchCtx* t_ctx = nullptr; }
+LaunchCtx& ctx() { return t_ctx ? *t_ctx : g_default_ctx; }
+void bind_ctx(LaunchCtx* c) { t_ctx = c; }
 
 // Per-pass twiddle table of the radix-8 FFT (layout: fft512.cuh), computed in double on the host.
 void make_twiddles(float2* h) {

@@ -259,10 +259,7 @@ int g_sm_count = 0;
 
 }  // namespace
 
-int g_conv1_persist = 1;   // option "conv1_persist" / SEPTFA_CONV1_PERSIST: 0 = always the one-tile-per-CTA kernel
-
 cudaError_t conv1_persist_setup() {
-  if (const char* e = getenv("SEPTFA_CONV1_PERSIST")) g_conv1_persist = atoi(e);
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -273,7 +270,7 @@ cudaError_t conv1_persist_setup() {
 
 // Returns false when the persistent kernel does not apply (caller uses the one-tile-per-CTA kernel).
 bool launch_conv1_persist(const Conv1Params& c, cudaStream_t st) {
-  if (!g_conv1_persist || !c.half_io || c.T < kTileM || g_sm_count <= 0) return false;
+  if (!ctx().conv1_persist || !c.half_io || c.T < kTileM || g_sm_count <= 0) return false;
   PersistParams p{};
   p.M = c.M; p.T = c.T; p.ntiles = (c.M + kTileM - 1) / kTileM;
   p.w_img = c.w_img; p.in = c.w_in; p.norm = c.norm; p.bias = c.bias_f; p.slope = c.slope;

@@ -657,8 +657,9 @@ void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
 
 // The dconv kernel's successor is a persistent grid: it may become resident only when every dconv CTA is past its main
 // loop (trigger at the start of the epilogue), otherwise it takes SM slots from the dconv grid's second wave.
-int g_dconv_late_trigger = 1;
-long long* g_tl_conv1 = nullptr;  // bring-up timeline of one conv1 launch (SEPTFA_TIMELINE)
+#ifdef SEPTFA_TIMELINE
+long long* g_tl_conv1 = nullptr;  // bring-up timeline of one conv1 launch
+#endif
 
 #ifdef SEPTFA_TIMELINE
 void gemm_dump_cta_timeline(int ncta) {   // wall-clock phases of every CTA of the last dconv launch
@@ -683,7 +684,6 @@ cudaError_t setup_one(int smem) {
 }
 
 cudaError_t tc_gemm_setup() {
-  if (const char* e = getenv("SEPTFA_DCONV_LATE_TRIGGER")) g_dconv_late_trigger = atoi(e);
   // two CTAs per SM need (almost) the whole shared-memory carveout
   const int s0 = kStages * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024;
   const int s2 = kStages * 2 * (kAChunkBytes + 192 * 128) + kAuxBytes + 1024;
@@ -706,7 +706,9 @@ void launch_tc_conv1(const Conv1Params& c, cudaStream_t st) {
   p.w_img = c.w_img; p.in = c.w_in; p.norm = c.norm;
   p.bias = c.bias_f; p.slope = c.slope;
   p.out = c.p_out; p.out_stride = kC; p.st_out = c.st_p;
+#ifdef SEPTFA_TIMELINE
   p.dbg = g_tl_conv1;
+#endif
   if (c.slope <= 1.f) {
     if (c.half_io) launch_mode<0, true, true>(p, 1, st); else launch_mode<0, false, true>(p, 1, st);
   } else {
@@ -722,7 +724,7 @@ void launch_tc_dconv(const DconvParams& c, cudaStream_t st) {
   p.slope2 = c.slope2; p.dil = c.dil; p.st_q = c.st_q;
   p.out = c.racc; p.out_stride = kC; p.rowsum = c.rowsum; p.colsum = c.colsum;
   p.dbg = c.dbg;
-  p.late_trigger = g_dconv_late_trigger;
+  p.late_trigger = ctx().dconv_late_trigger;
   if (c.slope2 <= 1.f) {
     if (c.half_io) launch_mode<1, true, true>(p, 1, st); else launch_mode<1, false, true>(p, 1, st);
   } else {

@@ -140,15 +140,15 @@ void launch_minmax_normalize(const float* x, int B, int64_t L, const int64_t* le
 void launch_sisdr(const float* p, const float* t, int64_t rows, int64_t n, int zero_mean, double* scratch /*[rows][5]*/, float* out,
                   cudaStream_t st);
 // gemm_conv1_persist.cu
-extern int g_conv1_persist;
 cudaError_t conv1_persist_setup();
 bool launch_conv1_persist(const Conv1Params& p, cudaStream_t st);   // false: not applicable, use launch_tc_conv1's kernel
 // gemm_tc.cu
 void launch_tc_conv1(const Conv1Params& p, cudaStream_t st);
 void launch_tc_dconv(const DconvParams& p, cudaStream_t st);
 void launch_tc_outconv(const OutConvParams& p, cudaStream_t st);
+#ifdef SEPTFA_TIMELINE
 extern long long* g_tl_conv1;
-extern int g_dconv_late_trigger;
+#endif
 cudaError_t tc_gemm_setup();  // opt-in shared memory attributes; call once per device
 // backend.cu
 struct VadParams {
@@ -174,8 +174,16 @@ void launch_online_emit(const float* pred /*[S,2,Lw]*/, int64_t Lw, const int32_
                         const float* tail_in /*[S,2,tail_cap]*/, int tail_len, float* tail_out, float* emitted /*[S,2,hop]*/,
                         cudaStream_t st);
 
-extern int g_launch_count;  // kernels launched since last reset (host counter)
-extern int g_use_pdl;       // launch with the programmatic-stream-serialization attribute
+// Per-handle launch state (septfa_handle owns one; every C-ABI entry binds it to the calling thread before launching).
+struct LaunchCtx {
+  int launches = 0;            // kernels launched since the last reset (host counter)
+  int use_pdl = 1;             // launch with the programmatic-stream-serialization attribute
+  int conv1_persist = 1;       // persistent warp-specialised conv1 kernel (0: always the one-tile-per-CTA kernel)
+  int dconv_late_trigger = 1;  // dconv triggers its (persistent) dependent at the start of its epilogue
+  int fused_pdl = 1;           // the cluster-resident residual kernel launches programmatically after dconv
+};
+LaunchCtx& ctx();
+void bind_ctx(LaunchCtx* c);
 
 // Kernel launch with (optional) programmatic dependent launch; counts the launch.
 template <typename... KArgs, typename... Args>
@@ -189,9 +197,9 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = (pdl && g_use_pdl) ? 1 : 0;
+  cfg.numAttrs = (pdl && ctx().use_pdl) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-  ++g_launch_count;
+  ++ctx().launches;
 }
 
 }  // namespace septfa

@@ -57,7 +57,7 @@ void launch_pit(const float* a, int64_t a_bs, int64_t a_ss, const float* b, int6
   dim3 grid((unsigned)((n + kPitChunk - 1) / kPitChunk), S);
   k_pit_l1<<<grid, 256, 0, st>>>(a, a_bs, a_ss, b, b_bs, b_ss, n, acc);
   k_pit_perm<<<(S + 127) / 128, 128, 0, st>>>(acc, S, perm);
-  g_launch_count += 2;
+  ctx().launches += 2;
 }
 
 // emitted[s,i,:] = pred[s, perm[s][i], Lw-hop:]; tail_out = concat(tail_in[:, :, :tail_len], emitted)[-tail_cap:].
@@ -90,7 +90,7 @@ void launch_online_emit(const float* pred, int64_t Lw, const int32_t* perm, int 
                         const float* tail_in, int tail_len, float* tail_out, float* emitted, cudaStream_t st) {
   dim3 grid(16, 2, S);
   k_online_emit<<<grid, 256, 0, st>>>(pred, Lw, perm, hop, tail_cap, tail_in, tail_len, tail_out, emitted);
-  ++g_launch_count;
+  ++ctx().launches;
 }
 
 }  // namespace septfa

@@ -81,7 +81,7 @@ void launch_minmax_normalize(const float* x, int B, int64_t L, const int64_t* le
   dim3 grid((unsigned)((L + kNormChunk - 1) / kNormChunk), B);
   k_minmax<<<grid, 256, 0, st>>>(x, L, lengths, ext);
   k_norm_apply<<<grid, 256, 0, st>>>(x, L, lengths, ext, out);
-  g_launch_count += 3;
+  ctx().launches += 3;
 }
 
 }  // namespace septfa
@@ -146,7 +146,7 @@ void launch_sisdr(const float* p, const float* t, int64_t rows, int64_t n, int z
   dim3 grid((unsigned)((n + kSdrChunk - 1) / kSdrChunk), (unsigned)rows);
   k_sisdr_moments<<<grid, 256, 0, st>>>(p, t, n, scratch);
   k_sisdr_final<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(scratch, rows, n, zero_mean, out);
-  g_launch_count += 2;
+  ctx().launches += 2;
 }
 
 }  // namespace septfa

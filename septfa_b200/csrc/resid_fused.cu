@@ -343,7 +343,6 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
 // triggers its dependents late, at the start of each CTA's epilogue. With the usual trigger at kernel entry the
 // persistent grid became resident while the dconv grid's second wave still needed the SM slots (5.86 vs 5.09 ms per
 // step); with the late trigger the early launch hides the launch latency instead (3.75 -> 3.70 ms).
-static int g_fused_pdl = 1;
 
 #ifdef SEPTFA_TIMELINE
 void resid_fused_dump_timeline() {   // bring-up: globaltimer stamps of the first 32 CTAs of the last launch
@@ -372,7 +371,6 @@ cudaError_t resid_fused_setup() {
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if (const char* s = getenv("SEPTFA_FUSED_PDL")) g_fused_pdl = atoi(s);
   cudaFuncAttributes fa{};
   cudaError_t e = cudaFuncGetAttributes(&fa, k_resid_persist);
   if (e != cudaSuccess) return e;
@@ -414,9 +412,9 @@ static void launch_cluster(K kernel, const FusedParams& p, int nclusters, int cs
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = (g_use_pdl && g_fused_pdl && g_dconv_late_trigger) ? 2 : 1;
+  cfg.numAttrs = (ctx().use_pdl && ctx().fused_pdl && ctx().dconv_late_trigger) ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kernel, p);
-  ++g_launch_count;
+  ++ctx().launches;
 }
 
 // Returns false if the utterance does not fit a cluster (caller falls back to k_tf_gate + k_resid<0,1>).

@@ -57,6 +57,7 @@ struct septfa_handle {
   float act_k[9]{}; float act_b = 0.f; float act_a = 0.f;
   const float* win_fwd = nullptr; const float* win_inv = nullptr; const float2* twiddle = nullptr;
   int last_launches = 0;
+  LaunchCtx lctx;   // launch options and counter of this handle (bound to the calling thread by every entry point)
   // forward_host resources
   cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
   cudaEvent_t hev_in[8] = {}, hev_done[8] = {};
@@ -284,7 +285,9 @@ int check_forward_args(septfa_handle* h, int B, int64_t L) {
 
 }  // namespace
 
-long long* septfa_dbg_ptr = nullptr;
+#ifdef SEPTFA_TIMELINE
+long long* septfa_dbg_ptr = nullptr;   // bring-up timeline buffer (clock64 stamps of one CTA)
+#endif
 
 extern "C" {
 
@@ -320,8 +323,12 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
   h->nblk = c.layer * c.stack;
   h->ln_mode = c.apply_recursive_ln ? LN_RECURSIVE : (c.apply_residual_ln ? LN_RESIDUAL : LN_NONE);  // model.py:347-352
   build_keys(h);
-  if (const char* e = getenv("SEPTFA_PDL")) g_use_pdl = atoi(e) ? 1 : 0;
+  // environment overrides of the kernel-selection switches, read once per handle (same names as septfa_set_option)
+  if (const char* e = getenv("SEPTFA_PDL")) h->lctx.use_pdl = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SEPTFA_FUSED_RESID")) h->fused_resid = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SEPTFA_CONV1_PERSIST")) h->lctx.conv1_persist = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SEPTFA_DCONV_LATE_TRIGGER")) h->lctx.dconv_late_trigger = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SEPTFA_FUSED_PDL")) h->lctx.fused_pdl = atoi(e) ? 1 : 0;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, "cudaSetDevice failed"); }
   cudaError_t e = tc_gemm_setup();
   if (e == cudaSuccess) e = resid_fused_setup();
@@ -333,6 +340,7 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
 
 void septfa_destroy(septfa_handle* h) {
   if (!h) return;
+  bind_ctx(nullptr);
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
   cudaFree(h->norm_ext);
@@ -387,7 +395,7 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
     return 0;
   }
   if (std::strcmp(name, "conv1_persist") == 0) {
-    g_conv1_persist = value ? 1 : 0;   // process-wide, like "pdl"
+    h->lctx.conv1_persist = value ? 1 : 0;
     return 0;
   }
   if (std::strcmp(name, "fused_resid") == 0) {
@@ -395,7 +403,7 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
     return 0;
   }
   if (std::strcmp(name, "pdl") == 0) {
-    g_use_pdl = value ? 1 : 0;   // process-wide: programmatic dependent launch of the forward's kernel chain
+    h->lctx.use_pdl = value ? 1 : 0;   // programmatic dependent launch of the forward's kernel chain
     return 0;
   }
   if (std::strcmp(name, "host_chunks") == 0) {
@@ -658,7 +666,8 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   // waveform error; the fp32 CUDA-core engine keeps fp32 storage.
   const int half_io = (tc_conv1 && tc_dconv) ? 1 : 0;
   const auto& c = h->cfg;
-  g_launch_count = 0;
+  bind_ctx(&h->lctx);
+  ctx().launches = 0;
 
   prof_mark(h, SEPTFA_PROF_FRONTEND, st);
   CUDA_TRY(h, cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, st));
@@ -677,19 +686,22 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     double* colsum = ws.colsum + (size_t)i * B * kC;
 
     Conv1Params c1{ws.w, norm, M, T, B, d.b1, d.a1, d.w1_img, d.b1f, d.w1_t, ws.p, st_p, half_io};
+#ifdef SEPTFA_TIMELINE
     g_tl_conv1 = (i == 6 && getenv("SEPTFA_TIMELINE") && septfa_dbg_ptr) ? septfa_dbg_ptr + 1024 : nullptr;
+#endif
     prof_mark(h, SEPTFA_PROF_CONV1, st);
     if (tc_conv1) launch_tc_conv1(c1, st); else launch_ref_conv1(c1, st);
 
     prof_mark(h, SEPTFA_PROF_DCONV, st);
     DconvParams dc{ws.p, st_p, d.g1, d.be1, d.w2b, d.w2f, d.c2f, d.a2, d.dil, M, T, B, d.w3_img, d.w3_t, ws.racc, ws.rowsum, colsum, st_q,
                    nullptr, half_io, d.wtab, d.bog};
-    long long*& s_dbg = septfa_dbg_ptr;   // bring-up timeline (SEPTFA_TIMELINE=1): block 5 of the persistent dconv kernel
-    if (i == 5 && getenv("SEPTFA_TIMELINE")) {
-      if (!s_dbg) { cudaMalloc(reinterpret_cast<void**>(&s_dbg), 8 * 256 * sizeof(long long)); }
-      cudaMemsetAsync(s_dbg, 0, 8 * 256 * sizeof(long long), st);
-      dc.dbg = s_dbg;
+#ifdef SEPTFA_TIMELINE
+    if (i == 5 && getenv("SEPTFA_TIMELINE")) {   // bring-up timeline of block 5's dconv launch
+      if (!septfa_dbg_ptr) { cudaMalloc(reinterpret_cast<void**>(&septfa_dbg_ptr), 8 * 256 * sizeof(long long)); }
+      cudaMemsetAsync(septfa_dbg_ptr, 0, 8 * 256 * sizeof(long long), st);
+      dc.dbg = septfa_dbg_ptr;
     }
+#endif
     if (tc_dconv) launch_tc_dconv(dc, st); else launch_ref_dconv(dc, st);
 
     prof_mark(h, SEPTFA_PROF_GATE, st);
@@ -742,31 +754,18 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
 #ifdef SEPTFA_TIMELINE
   if (getenv("SEPTFA_FUSED_TL")) resid_fused_dump_timeline();
   if (getenv("SEPTFA_GEMM_TL")) gemm_dump_cta_timeline((M + 127) / 128);
-#endif
-  if (getenv("SEPTFA_TIMELINE")) {
-    long long* dptr = nullptr;
-    // the static buffer lives in the block loop above; re-fetch it through a second static handle
-    dptr = septfa_dbg_ptr;
-    if (dptr) {
-      std::vector<long long> hbuf(8 * 256);
-      cudaStreamSynchronize(st);
-      cudaMemcpy(hbuf.data(), dptr, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-      long long t0 = 0;
-      for (long long v : hbuf) if (v && (!t0 || v < t0)) t0 = v;
-      const char* names[8] = {"rawload", "wload", "mma_ready", "tr_start", "tr_end", "mma_wready", "tr_rawready", "epi"};
-      fprintf(stderr, "TLG dconv:");
-      for (int i2 = 0; i2 < 64; ++i2) fprintf(stderr, " %lld", hbuf[i2] ? hbuf[i2] - hbuf[0] : -1);
-      fprintf(stderr, "\nTLG conv1:");
-      for (int i2 = 0; i2 < 64; ++i2) fprintf(stderr, " %lld", hbuf[1024 + i2] ? hbuf[1024 + i2] - hbuf[1024] : -1);
-      fprintf(stderr, "\n");
-      for (int r = 0; r < 0; ++r) {
-        fprintf(stderr, "TL %s:", names[r]);
-        for (int i2 = 0; i2 < 40; ++i2) if (hbuf[r * 256 + i2]) fprintf(stderr, " %lld", hbuf[r * 256 + i2] - t0);
-        fprintf(stderr, "\n");
-      }
-    }
+  if (getenv("SEPTFA_TIMELINE") && septfa_dbg_ptr) {
+    std::vector<long long> hbuf(8 * 256);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf.data(), septfa_dbg_ptr, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "TLG dconv:");
+    for (int i2 = 0; i2 < 64; ++i2) fprintf(stderr, " %lld", hbuf[i2] ? hbuf[i2] - hbuf[0] : -1);
+    fprintf(stderr, "\nTLG conv1:");
+    for (int i2 = 0; i2 < 64; ++i2) fprintf(stderr, " %lld", hbuf[1024 + i2] ? hbuf[1024 + i2] - hbuf[1024] : -1);
+    fprintf(stderr, "\n");
   }
-  h->last_launches = g_launch_count;
+#endif
+  h->last_launches = ctx().launches;
   CUDA_TRY(h, cudaGetLastError());
   return 0;
 }
@@ -1004,7 +1003,8 @@ int septfa_online_step(septfa_online* o, const float* win, const septfa_infer_kw
                               workspace_bytes - pred_b - vad_b - 256, st))
     return rc;
   int launches = h->last_launches;
-  g_launch_count = 0;
+  bind_ctx(&h->lctx);
+  ctx().launches = 0;
   const int64_t Lw = kWinLen;
   if (o->hops == 0) {
     // indx == 0: online_signal = pred[..., -fs:] (not yet reordered) is what the overlap is compared to (:85-88)
@@ -1019,7 +1019,7 @@ int septfa_online_step(septfa_online* o, const float* win, const septfa_infer_kw
   o->cur ^= 1;
   o->tail_len = std::min(o->tail_len + kHopLen, kTailCap);
   o->hops += 1;
-  h->last_launches = launches + g_launch_count;
+  h->last_launches = launches + ctx().launches;
   CUDA_TRY(h, cudaGetLastError());
   return 0;
 }
@@ -1034,6 +1034,7 @@ int septfa_pit_l1(septfa_handle* h, const float* a, const float* b, int S, int64
     h->pit_cap = S;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  bind_ctx(&h->lctx);
   launch_pit(a, 2 * n, n, b, 2 * n, n, S, n, h->pit_acc, perm, st);
   if (pw_sums) CUDA_TRY(h, cudaMemcpyAsync(pw_sums, h->pit_acc, (size_t)S * 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(h, cudaGetLastError());
@@ -1048,6 +1049,7 @@ int septfa_minmax_normalize(septfa_handle* h, const float* x, int B, int64_t L, 
     CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->norm_ext), (size_t)B * 2 * sizeof(unsigned)));
     h->norm_cap = B;
   }
+  bind_ctx(&h->lctx);
   launch_minmax_normalize(x, B, L, lengths, h->norm_ext, out, reinterpret_cast<cudaStream_t>(stream));
   h->last_launches = 3;
   CUDA_TRY(h, cudaGetLastError());
@@ -1057,6 +1059,7 @@ int septfa_minmax_normalize(septfa_handle* h, const float* x, int B, int64_t L, 
 int septfa_sisdr(const float* preds, const float* target, int64_t rows, int64_t n, int zero_mean, float* out_db, double* scratch,
                  void* stream) {
   if (!preds || !target || !out_db || !scratch || rows < 1 || rows > 65535 || n < 1) return SEPTFA_E_INVALID;
+  bind_ctx(nullptr);   // no handle: the process-default launch context
   launch_sisdr(preds, target, rows, n, zero_mean, scratch, out_db, reinterpret_cast<cudaStream_t>(stream));
   return cudaGetLastError() == cudaSuccess ? 0 : SEPTFA_E_CUDA;
 }

@@ -5,6 +5,10 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#ifndef SEPTFA_MBAR_TIMEOUT_CYCLES
+#define SEPTFA_MBAR_TIMEOUT_CYCLES 120000000000LL   /* ~60 s; bring-up builds pass a shorter bound */
+#endif
+
 namespace septfa {
 namespace tc {
 
@@ -32,13 +36,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug reports which wait timed out and traps (failing the launch) instead of hanging the GPU.
-// (Measured: dropping the printf or adding a __nanosleep back-off to this loop changes the dconv kernel by -10 % / 0 %;
-// the kernels are sensitive to code layout)
+// The bound is ~60 s of SM clocks: far beyond any legitimate wait (a forward takes milliseconds), long enough that
+// preemption, MPS time-slicing or a debugger stop cannot trip it.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (clock64() - t0 > SEPTFA_MBAR_TIMEOUT_CYCLES) {
       printf("septfa: mbarrier timeout tag=%d block=(%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }

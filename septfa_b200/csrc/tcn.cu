@@ -348,15 +348,15 @@ __global__ void __launch_bounds__(256) k_ref_outconv(OutConvParams p) {
 
 void launch_ref_conv1(const Conv1Params& p, cudaStream_t st) {
   k_ref_conv1<<<p.M, 256, 0, st>>>(p);
-  ++g_launch_count;
+  ++ctx().launches;
 }
 void launch_ref_dconv(const DconvParams& p, cudaStream_t st) {
   k_ref_dconv<<<p.M, 256, 0, st>>>(p);
-  ++g_launch_count;
+  ++ctx().launches;
 }
 void launch_ref_outconv(const OutConvParams& p, cudaStream_t st) {
   k_ref_outconv<<<p.M, 256, 0, st>>>(p);
-  ++g_launch_count;
+  ++ctx().launches;
 }
 
 }  // namespace septfa

@@ -42,15 +42,15 @@ def calc_sisdr(preds, target, zero_mean=True):
         if rc != 0:
             raise _lib.SeptfaError(f"septfa_sisdr failed ({rc})")
         return out.reshape(preds.shape[:-1])
+    # host tensors / other dtypes: the same definition from three inner products per row
     eps = torch.finfo(preds.dtype).eps
+    p, t = preds, target
     if zero_mean:
-        target = target - torch.mean(target, dim=-1, keepdim=True)
-        preds = preds - torch.mean(preds, dim=-1, keepdim=True)
-    alpha = (torch.sum(preds * target, dim=-1, keepdim=True) + eps) / (torch.sum(target ** 2, dim=-1, keepdim=True) + eps)
-    target_scaled = alpha * target
-    noise = target_scaled - preds
-    val = (torch.sum(target_scaled ** 2, dim=-1) + eps) / (torch.sum(noise ** 2, dim=-1) + eps)
-    return 10 * torch.log10(val)
+        p, t = p - p.mean(dim=-1, keepdim=True), t - t.mean(dim=-1, keepdim=True)
+    scale = ((p * t).sum(dim=-1, keepdim=True) + eps) / ((t * t).sum(dim=-1, keepdim=True) + eps)
+    proj = scale * t                                  # projection of the estimate on the target
+    ratio = (proj.square().sum(dim=-1) + eps) / ((proj - p).square().sum(dim=-1) + eps)
+    return 10 * torch.log10(ratio)
 
 
 class PITLossWrapper(torch.nn.Module):
@@ -125,23 +125,26 @@ class PITLossWrapper(torch.nn.Module):
 
     @staticmethod
     def get_pw_losses(loss_func, est_targets, targets, **kwargs):
-        """model/pit_wrapper.py:149-177."""
-        batch_size, n_src, *_ = targets.shape
-        pair_wise_losses = targets.new_empty(batch_size, n_src, n_src)
-        for est_idx, est_src in enumerate(est_targets.transpose(0, 1)):
-            for target_idx, target_src in enumerate(targets.transpose(0, 1)):
-                pair_wise_losses[:, est_idx, target_idx] = loss_func(est_src, target_src, **kwargs)
-        return pair_wise_losses
+        """Pairwise loss matrix ``pw[b, i, j] = loss_func(est[:, i], tgt[:, j])`` (semantics of
+        model/pit_wrapper.py:149-177, an asteroid-derived MIT-licensed routine): whatever ``loss_func`` returns - a
+        scalar for ``nn.L1Loss()`` - is broadcast over the batch axis."""
+        n_src = targets.shape[1]
+        pw = targets.new_empty(targets.shape[0], n_src, n_src)
+        for i in range(n_src):
+            for j in range(n_src):
+                pw[:, i, j] = loss_func(est_targets[:, i], targets[:, j], **kwargs)
+        return pw
 
     @staticmethod
     def find_best_perm_factorial(pair_wise_losses):
-        """model/pit_wrapper.py:261-312 with perm_reduce=None: mean over sources of every permutation,
-        argmin with ties to the first (identity) permutation."""
+        """Exhaustive search (semantics of model/pit_wrapper.py:261-312 with ``perm_reduce=None``): the score of a
+        permutation is the mean over targets ``j`` of ``pw[b, perm[j], j]``; ``torch.min`` keeps the first minimum,
+        so ties go to the identity. For two sources this is identity vs swap:
+        ``pw[0,0] + pw[1,1] <= pw[1,0] + pw[0,1]``."""
         n_src = pair_wise_losses.shape[-1]
-        pwl = pair_wise_losses.transpose(-1, -2)
-        perms = pwl.new_tensor(list(permutations(range(n_src))), dtype=torch.long)
-        idx = torch.unsqueeze(perms, 2)
-        perms_one_hot = pwl.new_zeros((*perms.size(), n_src)).scatter_(2, idx, 1)
-        loss_set = torch.einsum("bij,pij->bp", [pwl, perms_one_hot]) / n_src
-        min_loss, min_loss_idx = torch.min(loss_set, dim=1)
-        return min_loss, perms[min_loss_idx]
+        cand = list(permutations(range(n_src)))
+        tgt = torch.arange(n_src, device=pair_wise_losses.device)
+        scores = torch.stack([pair_wise_losses[:, list(c), tgt].sum(dim=1) / n_src for c in cand], dim=1)
+        best, which = torch.min(scores, dim=1)
+        table = torch.tensor(cand, dtype=torch.long, device=pair_wise_losses.device)
+        return best, table[which]
