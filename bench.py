@@ -2,7 +2,7 @@
 """Benchmark of the Sep-TFAnet-VAD inference forward pass (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # CPU port of the reference path (oracle)
+    python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference on the host cores
 
 A "step" is one forward pass over one batch of synthetic noisy two-speaker mixtures
 (BASELINE.json configs[1]: config_with_vad.json, 256 x 4 s per GPU, filter_signals_by_smo_vad).
@@ -11,11 +11,15 @@ runs the same per-GPU batch on its own shard of mixtures; there is no collective
 path, torch.distributed only takes the MAX of the per-rank times.
 
 Prints ONE JSON line (rank 0) with the keys the driver contract asks for, plus:
-  roofline     - dominant kernel (tcgen05 dconv+res_out GEMM): algorithmic FLOP per launch divided by
-                 its CUDA-event duration, against the measured bf16 peak (MEASURED_PEAKS.json)
-  kernels      - per-kernel-class device time per step (CUDA events on the launch stream)
-  cpu_baseline - the numpy port of the reference path timed on this box's host cores (bounded sample)
-  e2e          - the same metric through SeparationModel.forward_host: pinned host buffers, H2D and D2H inside
+  roofline       - dominant kernel (tcgen05 dconv+res_out GEMM): algorithmic FLOP per launch divided by
+                   its CUDA-event duration, against the measured bf16 peak (MEASURED_PEAKS.json)
+  kernels        - per-kernel-class device time per step (CUDA events on the launch stream)
+  e2e            - the same metric through the host API: pinned host buffers, H2D and D2H inside the timing;
+                   e2e.pcie measures the plain pinned-copy ceiling of the same bytes on this box
+  e2e_16bit      - the host API with int16 PCM input (normalised on the device) and fp16 output (`-ps 16`)
+  cfg4 / cfg5    - BASELINE.json configs[3] (60 s, config_without_vad) and configs[4] (8192 x 4 s, sharded)
+  torch_eager_b200 - the unmodified reference module moved `.to("cuda")` under stock torch eager (the stronger baseline)
+  cpu_baseline   - the unmodified reference timed on this box's host cores (bounded sample)
 """
 import argparse
 import contextlib
@@ -27,6 +31,7 @@ import subprocess
 import sys
 import tempfile
 import time
+import warnings
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -35,7 +40,7 @@ FS = 16000
 MAC_PER_FRAME = 4899657                     # algorithmic MACs per STFT frame
 DCONV_MAC_PER_FRAME = 131072 + 1536         # res_out 512->256 + depthwise k3 (the dominant kernel's share)
 CONV1_MAC_PER_FRAME = 65536
-DCONV_DRAM_BYTES_NCU = 34972160           # k_tc_gemm<1,1,1>, 256 x 4 s: 33.76 MB read + 1.21 MB written (profiles/r1_ncu_summary.md)
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r2_dominant_traffic.json")   # {"kernel": ..., "dram_bytes_per_launch": ...}
 
 
 def measured_peaks():
@@ -45,6 +50,15 @@ def measured_peaks():
         return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
     except Exception:  # noqa: BLE001
         return 1400.0, 6650.0, "fallback"  # /opt/skills/guides/B200_PROFILING.md
+
+
+def workload_config(a):
+    """The `config` object: identical for our arm and the reference arm (same workload, same inputs, same weights)."""
+    return {"workload": f"config_with_vad, {a.batch} x {a.length / FS:g} s mixtures per GPU, filter_signals_by_smo_vad "
+                        "(BASELINE.json configs[1])",
+            "weights": "seeded random-init, reference layout (the shipped checkpoints are absent)",
+            "inputs": "32 distinct seeded synthetic two-speaker mixtures per GPU, tiled to the batch",
+            "l2": "working set ~0.6 GB per step >> 126 MB L2 (no explicit flush)"}
 
 
 class ClockSampler:
@@ -120,57 +134,167 @@ def hbm_kernels(kernels, M, B, L, peak_hbm, exports):
     return out
 
 
-def cpu_reference_throughput(n_mix, length, repeats=1):
-    """The oracle (numpy port of the reference path, fp32, BLAS threads = all host cores) on a bounded
-    sample of the same workload. Returns (audio-seconds per second, seconds per pass)."""
-    import numpy as np
-    from oracle import septfa_oracle as O
-    from septfa_b200 import synth
-    try:  # torchrun exports OMP_NUM_THREADS=1: give the BLAS behind numpy all host cores explicitly
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(os.cpu_count())
+# --------------------------------------------------------------------------- the reference on the host cores
+def _all_host_threads():
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
     except Exception:  # noqa: BLE001
         pass
-    args = synth.CONFIG_WITH_VAD
-    W = O.OracleWeights(synth.make_state_dict_numpy(args, 0), args, np.float32)
-    x = synth.make_mixtures(n_mix, length, 1234)
-    kw = dict(synth.DEFAULT_INFERENCE_KW, filter_signals_by_smo_vad=True)
-    best = float("inf")
-    for _ in range(repeats):
+    return n
+
+
+class ReferenceCPU:
+    """The unmodified reference `SeparationModel` (oracle/ref_loader.py: /root/reference here, its byte-compiled copy under
+    oracle/_ref on the GPU box) on the host cores, through its stock forward. Falls back to the numpy port of the oracle
+    (labelled "port") only if the reference cannot be imported at all."""
+
+    def __init__(self, length, chunk):
+        import numpy as np
+        from septfa_b200 import synth
+        self.np, self.synth, self.length, self.chunk = np, synth, length, chunk
+        self.args = synth.CONFIG_WITH_VAD
+        self.kw = dict(synth.DEFAULT_INFERENCE_KW, filter_signals_by_smo_vad=True)
+        self.cores = _all_host_threads()
+        self.kind, self.why_port = "reference", None
+        try:
+            import torch
+            from oracle import ref_loader
+            ns = ref_loader.load()
+            torch.set_num_threads(self.cores)
+            warnings.filterwarnings("ignore")
+            with contextlib.redirect_stdout(io.StringIO()):
+                m = ns.model.SeparationModel(**self.args)
+            m.load_state_dict(synth.make_state_dict(self.args, 0), strict=True)
+            self.model = m.eval()
+            self.torch = torch
+            self.desc = (f"unmodified reference model/model.py:402-461 ({ns.kind} import), torch {torch.__version__} CPU, "
+                         f"{self.cores} threads, forwards of {chunk} mixtures (its fastest CPU batch size)")
+        except Exception as e:  # noqa: BLE001
+            self.kind, self.why_port = "port", f"{type(e).__name__}: {e}"
+            from oracle import septfa_oracle as O
+            try:
+                from threadpoolctl import threadpool_limits
+                threadpool_limits(self.cores)
+            except Exception:  # noqa: BLE001
+                pass
+            self.O = O
+            self.W = O.OracleWeights(synth.make_state_dict_numpy(self.args, 0), self.args, np.float32)
+            self.desc = f"numpy fp32 port (oracle/septfa_oracle.py; reference import failed: {self.why_port})"
+
+    def mixtures(self, n):
+        base = self.synth.make_mixtures(min(n, 32), self.length, 1234)
+        return self.np.tile(base, ((n + len(base) - 1) // len(base), 1))[:n]
+
+    def run(self, x):
+        """One pass over x [n, L] in chunks; returns seconds."""
         t0 = time.perf_counter()
-        O.forward(x, W, dict(kw))
-        best = min(best, time.perf_counter() - t0)
-    return n_mix * length / FS / best, best
+        for i in range(0, len(x), self.chunk):
+            xb = x[i:i + self.chunk]
+            if self.kind == "reference":
+                with self.torch.no_grad():
+                    self.model(self.torch.from_numpy(xb), dict(self.kw))
+            else:
+                self.O.forward(xb, self.W, dict(self.kw))
+        return time.perf_counter() - t0
 
 
 def run_reference(a, rank, world):
-    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
-    n_mix = a.ref_sample
-    # warm-up + timed steps, each a bounded sample of the workload
+    ref = ReferenceCPU(a.length, a.ref_chunk)
+    # one step = the whole per-GPU workload (a.batch mixtures) unless that cannot finish in a few minutes on this host
+    probe = ref.mixtures(min(a.ref_chunk, a.batch))
+    ref.run(probe[:2])
+    t_probe = ref.run(probe)
+    per_mix = t_probe / len(probe)
+    n_mix = a.ref_sample if a.ref_sample > 0 else a.batch
+    budget = 200.0
+    if per_mix * n_mix * (a.steps + a.warmup) > budget:
+        n_mix = max(a.ref_chunk, int(budget / (per_mix * (a.steps + a.warmup))) // a.ref_chunk * a.ref_chunk)
+    x = ref.mixtures(n_mix)
     for _ in range(a.warmup):
-        cpu_reference_throughput(1, a.length)
+        ref.run(x)
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        cpu_reference_throughput(n_mix, a.length)
+        ref.run(x)
     dt = time.perf_counter() - t0
     value = a.steps * n_mix * a.length / FS / dt
-    cores = os.cpu_count()
+    sample = (f"{n_mix} of the step's {a.batch} x {a.length / FS:g} s mixtures per step, {a.steps} steps; {ref.desc}")
     line = {
         "impl": "reference", "metric": "mixture-seconds processed per second (offline forward)", "value": value,
         "unit": "audio-s/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"config_with_vad, {a.batch} x {a.length / FS:g} s mixtures per GPU, "
-                               "filter_signals_by_smo_vad", "sample": f"{n_mix} x {a.length / FS:g} s per step"},
-        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_mix} x {a.length / FS:g} s mixtures per step, {a.steps} steps, numpy fp32 "
-                                   "port of model/model.py:402-461 (oracle/septfa_oracle.py)"},
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a),
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": ref.cores, "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def torch_eager_b200(a, dev, x_dev):
+    """The stronger baseline: the unmodified reference module moved `.to("cuda")`, stock torch
+    eager (cuFFT + cuDNN/cuBLAS + ATen), same weights and batch. `inference_kw={}`: the gating tail of
+    model/model.py:445-448 builds its smoothing conv on the CPU and raises on CUDA inputs."""
+    import torch
+    from septfa_b200 import synth
+    try:
+        from oracle import ref_loader
+        ns = ref_loader.load()
+        warnings.filterwarnings("ignore")
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = ns.model.SeparationModel(**synth.CONFIG_WITH_VAD)
+        m.load_state_dict(synth.make_state_dict(synth.CONFIG_WITH_VAD, 0), strict=True)
+        m = m.eval().to(dev)
+        with torch.no_grad():
+            for _ in range(2):
+                m(x_dev, {})
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 5
+            e0.record()
+            for _ in range(n):
+                out = m(x_dev, {})
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        B, L = x_dev.shape
+        res = {"value": B * L / FS / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms, "steps": n,
+               "what": f"unmodified reference SeparationModel.to('cuda') ({ns.kind} import), torch {torch.__version__} eager fp32 "
+                       "(TF32 off), inference_kw={} (its gating tail raises on CUDA), inputs resident, CUDA events",
+               "same_batch": [int(B), int(L)]}
+        del m, out
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def pcie_ceiling(torch, dev, h2d_bytes, d2h_bytes, reps=10):
+    """Plain pinned-memory copies of one step's bytes, both directions at once on two streams: the PCIe ceiling of the
+    end-to-end number on this box (and, under torchrun, with all ranks copying at the same time)."""
+    src = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(d2h_bytes, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def go(n):
+        for _ in range(n):
+            with torch.cuda.stream(s1):
+                d_in.copy_(src, non_blocking=True)
+            with torch.cuda.stream(s2):
+                dst.copy_(d_out, non_blocking=True)
+        s1.synchronize()
+        s2.synchronize()
+
+    go(2)
+    t0 = time.perf_counter()
+    go(reps)
+    dt = (time.perf_counter() - t0) / reps
+    return dt
 
 
 def main():
@@ -181,9 +305,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="mixtures per GPU per step")
     ap.add_argument("--length", type=int, default=64000, help="samples per mixture (4 s @ 16 kHz)")
-    ap.add_argument("--ref-sample", type=int, default=48, help="mixtures per step of the CPU reference arm (~3 s of CPU work)")
-    ap.add_argument("--cpu-sample", type=int, default=192, help="mixtures of the cpu_baseline leg (~12 s of CPU work)")
+    ap.add_argument("--ref-sample", type=int, default=0, help="mixtures per step of the reference arm (0 = the whole batch)")
+    ap.add_argument("--ref-chunk", type=int, default=64, help="mixtures per reference forward on the CPU")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="mixtures of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip cfg4 / cfg5 / torch-eager / 16-bit legs")
     ap.add_argument("--lean", action="store_true", help="skip the optional exports (est/mask/spectrum/logits)")
     ap.add_argument("--online-streams", type=int, default=1024, help="concurrent streams of the online leg (0 = skip)")
     ap.add_argument("--online-hops", type=int, default=12)
@@ -194,13 +320,12 @@ def main():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
-    if a.impl == "reference":
-        for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-            os.environ[v] = str(os.cpu_count())  # torchrun forces OMP_NUM_THREADS=1
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
+        for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[v] = str(_all_host_threads())  # torchrun forces OMP_NUM_THREADS=1
         run_reference(a, rank, world)
         return
 
@@ -283,31 +408,47 @@ def main():
     # its input from pinned host memory and its results back to pinned host memory; successive steps overlap their
     # PCIe copies with each other's kernels, which is how a file loop (only_inference.py:80-100) would call it.
     # The timed region runs from the first submit to the last result (pipeline fill and drain included).
-    xs = [x_host, x_host.clone().pin_memory()]
-    outs = [torch.empty((B, 2, L), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    vads = [torch.empty((B, 2, T), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    def stream_leg(xs, out_dtype):
+        outs = [torch.empty((B, 2, L), dtype=out_dtype, pin_memory=True) for _ in range(2)]
+        vads = [torch.empty((B, 2, T), dtype=torch.float32, pin_memory=True) for _ in range(2)]
 
-    def stream_steps(n):
-        pend = [None, None]
-        for i in range(n):
-            sl = i & 1
-            if pend[sl] is not None:
-                pend[sl].result()
-            pend[sl] = model.forward_host_submit(xs[sl], kw, device=local_rank, slot=sl, out=outs[sl], vad=vads[sl])
-        for f in pend:
-            if f is not None:
-                f.result()
+        def stream_steps(n):
+            pend = [None, None]
+            for i in range(n):
+                sl = i & 1
+                if pend[sl] is not None:
+                    pend[sl].result()
+                pend[sl] = model.forward_host_submit(xs[sl], kw, device=local_rank, slot=sl, out=outs[sl], vad=vads[sl],
+                                                     out_dtype=out_dtype)
+            for f in pend:
+                if f is not None:
+                    f.result()
 
-    stream_steps(3)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    stream_steps(a.steps)
-    t_e2e = gather_max_time(time.perf_counter() - t0)
+        stream_steps(3)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        stream_steps(a.steps)
+        return gather_max_time(time.perf_counter() - t0), outs, vads
+
+    t_e2e, outs, _ = stream_leg([x_host, x_host.clone().pin_memory()], torch.float32)
     # same results as the synchronous call up to the fp16 operand noise: the two paths tile the batch differently, so a
     # VAD probability within ~4e-4 of the threshold may flip a frame's gate (allowed: |p - thr| < 1e-3) in a few clips
     assert torch.isfinite(outs[0]).all()
     assert ((outs[0] - out_h[0]).abs().amax(dim=(1, 2)) > 1e-3).float().mean().item() < 0.1
+    h2d_bytes, d2h_bytes = int(x_host.numel() * 4), int(B * 2 * L * 4 + B * 2 * T * 4)
+    t_pcie = gather_max_time(pcie_ceiling(torch, dev, h2d_bytes, d2h_bytes))
+
+    # ---- 16-bit host formats: int16 PCM in (as a wav file holds it; converted and min-max normalised on the device,
+    # only_inference.py:69,81) and fp16 out (save_audio's `-ps 16`, utlis_inference.py:30-32): half the PCIe bytes
+    e2e16 = None
+    if not a.no_extras:
+        pcm = torch.from_numpy(np.round(x_host.numpy() / 0.9 * 32767.0).astype(np.int16)).pin_memory()
+        t16, outs16, _ = stream_leg([pcm, pcm.clone().pin_memory()], torch.float16)
+        assert torch.isfinite(outs16[0].float()).all()
+        t_pcie16 = gather_max_time(pcie_ceiling(torch, dev, h2d_bytes // 2, B * 2 * L * 2 + B * 2 * T * 4))
+        e2e16 = {"t": t16, "t_pcie": t_pcie16}
+        del outs16
     clocks = sampler.stop() if sampler else None   # sampled over the timed, profiled and end-to-end legs
 
     # ---- online mode (BASELINE.json configs[2]): S concurrent streams, one hop-step = forward on the current 3 s
@@ -347,6 +488,59 @@ def main():
                   "note": "hop-step = forward on S x 3 s windows (T=188) + per-stream L1-PIT + reorder + emit 1 s; "
                           "ms per frame = hop-step / 62.5 frames per hop (the reference has no per-frame entry point)"}
 
+    # ---- BASELINE.json configs[4]: 8192 x 4 s with the VAD gate, sharded over the ranks, streamed in 256-mixture host
+    # batches through forward_host_stream (host input and output every batch); whole-job audio-s/s, max over ranks
+    cfg5 = None
+    if not a.no_extras:
+        total = 8192
+        n_mine = shard_range(total, rank, world)[1] - shard_range(total, rank, world)[0]
+        nb = n_mine // B
+        xs = [x_host, x_host.clone().pin_memory()]
+        for _ in model.forward_host_stream((xs[i & 1] for i in range(2)), kw, device=local_rank):
+            pass
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n_out = 0
+        for o, v in model.forward_host_stream((xs[i & 1] for i in range(nb)), kw, device=local_rank):
+            n_out += o.shape[0]
+        t5 = gather_max_time(time.perf_counter() - t0)
+        assert n_out == nb * B
+        cfg5 = {"workload": f"{total} x 4 s mixtures over {world} GPU(s) in host batches of {B} (BASELINE.json configs[4])",
+                "value": world * nb * B * L / FS / t5, "unit": "audio-s/s", "seconds": t5,
+                "api": "SeparationModel.forward_host_stream (float32 host input and output per batch)"}
+
+    # ---- BASELINE.json configs[3]: 60 s mixtures, config_without_vad (stresses the per-utterance global statistics)
+    cfg4 = None
+    if not a.no_extras and rank == 0:
+        with contextlib.redirect_stdout(io.StringIO()):
+            m4 = SeparationModel(**synth.CONFIG_WITHOUT_VAD)
+        m4.load_state_dict(synth.make_state_dict(synth.CONFIG_WITHOUT_VAD, 0), strict=True)
+        m4.eval().to(dev)
+        m4.materialize.update(estimated_stfts=False, mask_per_speaker=False, spectrum=False, masks_b=False)
+        cfg4 = {"workload": "config_without_vad, 60 s mixtures, inference_kw={} (BASELINE.json configs[3])", "unit": "audio-s/s"}
+        x60 = torch.from_numpy(np.tile(synth.make_mixtures(4, 960000, 777), (8, 1))).to(dev)
+        for nb4 in (1, 32):
+            xb = x60[:nb4]
+            for _ in range(3):
+                m4(xb, {})
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(5):
+                m4(xb, {})
+            s1.record()
+            torch.cuda.synchronize()
+            ms = s0.elapsed_time(s1) / 5
+            cfg4[f"batch_{nb4}"] = {"ms_per_forward": ms, "value": nb4 * 60.0 / (ms * 1e-3),
+                                    "mfu": 2.0 * MAC_PER_FRAME * nb4 * 3751 / (ms * 1e-3) / 1e12 / measured_peaks()[0]}
+        del m4, x60
+        torch.cuda.empty_cache()
+
+    eager = None
+    if not a.no_extras and rank == 0:
+        eager = torch_eager_b200(a, dev, x_dev)
+
     if rank == 0:
         audio_s = world * B * L / FS * a.steps
         peak_tf, peak_hbm, peak_src = measured_peaks()
@@ -357,30 +551,39 @@ def main():
         achieved = flop_per_launch / (dconv_ms * 1e-3) / 1e12 if dconv_ms > 0 else 0.0
         c_ms, c_n = prof["conv1"]
         conv1_tf = 2.0 * CONV1_MAC_PER_FRAME * M / (c_ms / max(c_n, 1) * 1e-3) / 1e12 if c_ms > 0 else 0.0
+        traffic, traffic_src = None, None
+        try:
+            with open(NCU_TRAFFIC_FILE) as f:
+                tj = json.load(f)
+            if (B, L) == (256, 64000):
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
+        except Exception:  # noqa: BLE001
+            pass
+        cfg = workload_config(a)
         line = {
             "metric": "mixture-seconds processed per second (offline forward)",
             "value": audio_s / t_dev, "unit": "audio-s/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16xf16->f32 (tcgen05), f32 elsewhere", "data": "synthetic",
-            "config": {"workload": f"config_with_vad, {B} x {L / FS:g} s mixtures per GPU, filter_signals_by_smo_vad "
-                                   "(BASELINE.json configs[1])", "frames_per_step_per_gpu": M,
-                       "l2": "working set ~0.6 GB per step >> 126 MB L2 (no explicit flush)",
-                       "weights": "seeded random-init, reference layout", "exports": not a.lean},
+            "config": cfg,
+            "frames_per_step_per_gpu": M, "exports": not a.lean,
             "model_flops_utilization": 2.0 * MAC_PER_FRAME * M * world * a.steps / t_dev / 1e12 / (peak_tf * world),
-            "roofline": {"kernel": "k_tc_gemm<1> (depthwise conv prologue + res_out 512->256 tcgen05 GEMM)",
+            "roofline": {"kernel": "dconv + res_out (depthwise dilated conv -> PReLU -> 512->256 tcgen05 GEMM, model.py:136-144)",
                          "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": DCONV_DRAM_BYTES_NCU if (B, L) == (256, 64000) else None,
-                         "traffic_source": "profiles/r1_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one "
-                                           "k_tc_gemm<1,1,1> launch (ncu --set full); the other 31 MB of its 65.8 MB algorithmic "
-                                           "fp16 in/out bytes are served by / left in the 126 MB L2",
+                         "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "ms_per_launch": dconv_ms, "flop_per_launch": flop_per_launch,
                          "conv1_tflops": conv1_tf},
             "kernels": kernels,
             "hbm_kernels": hbm_kernels(kernels, M, B, L, peak_hbm, not a.lean),
-            "e2e": {"value": audio_s / t_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
-                    "d2h_bytes_per_step": int(B * 2 * L * 4 + B * 2 * T * 4), "ms_per_step": 1e3 * t_e2e / a.steps,
-                    "api": "SeparationModel.forward_host_submit / HostBatch.result (septfa_forward_host_submit / _wait), "
+            "e2e": {"value": audio_s / t_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * t_e2e / a.steps,
+                    "pcie": {"ms_per_step_copies_only": 1e3 * t_pcie,
+                             "pcie_gbs": (h2d_bytes + d2h_bytes) / t_pcie / 1e9,
+                             "frac_of_pcie": t_pcie / (t_e2e / a.steps),
+                             "what": "pinned H2D and D2H copies of one step's bytes, both directions at once, all ranks at the "
+                                     "same time, no kernels: the copy-only floor of a step on this box"},
+                    "api": "SeparationModel.forward_host_submit / HostBatch.result (septfa_forward_host_submit_fmt / _wait), "
                            "two batches in flight; pinned host input and output per step; fill and drain inside the timing"},
             "e2e_sync": {"value": audio_s / t_e2e_sync, "unit": "audio-s/s", "ms_per_step": 1e3 * t_e2e_sync / a.steps,
                          "api": "SeparationModel.forward_host (septfa_forward_host): one synchronous call per step, "
@@ -388,13 +591,29 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if e2e16 is not None:
+            line["e2e_16bit"] = {"value": audio_s / e2e16["t"], "unit": "audio-s/s", "ms_per_step": 1e3 * e2e16["t"] / a.steps,
+                                 "h2d_bytes_per_step": h2d_bytes // 2, "d2h_bytes_per_step": int(B * 2 * L * 2 + B * 2 * T * 4),
+                                 "pcie": {"ms_per_step_copies_only": 1e3 * e2e16["t_pcie"],
+                                          "frac_of_pcie": e2e16["t_pcie"] / (e2e16["t"] / a.steps)},
+                                 "api": "forward_host_submit with int16 PCM input (astype float32 + min-max normalise on the "
+                                        "device, only_inference.py:69,81) and out_dtype=float16 (save_audio -ps 16)"}
         if online is not None:
             line["online"] = online
+        if cfg4 is not None:
+            line["cfg4"] = cfg4
+        if cfg5 is not None:
+            line["cfg5"] = cfg5
+        if eager is not None:
+            line["torch_eager_b200"] = eager
         if world == 1 and not a.no_cpu_baseline:
-            v, secs = cpu_reference_throughput(a.cpu_sample, L)
-            line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{a.cpu_sample} x {L / FS:g} s mixtures, one pass ({secs:.1f} s), numpy "
-                                              "fp32 port of model/model.py:402-461 (oracle/septfa_oracle.py)"}
+            ref = ReferenceCPU(L, a.ref_chunk)
+            xs = ref.mixtures(a.cpu_sample)
+            ref.run(xs[:2])
+            secs = ref.run(xs)
+            line["cpu_baseline"] = {"value": a.cpu_sample * L / FS / secs, "unit": "audio-s/s", "cores": ref.cores,
+                                    "kind": ref.kind,
+                                    "sample": f"{a.cpu_sample} x {L / FS:g} s mixtures, one pass ({secs:.1f} s); {ref.desc}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -105,6 +105,14 @@ int64_t septfa_key_numel(const septfa_handle* h, int i);
  * batch chunks septfa_forward_host pipelines over its two stream lanes); kernel-selection switches for
  * cross-checks (default 1): "fused_resid" (cluster-resident gate + residual kernel), "conv1_persist"
  * (persistent warp-specialised conv1 kernel), "pdl" (programmatic dependent launch of the kernel chain). */
+/* "precision": arithmetic of the two block contractions (conv1d 256->256, res_out 512->256) on the tensor cores.
+ *   SEPTFA_PRECISION_FAST      fp16 operands, one tcgen05 pass, fp16 storage of the tensors between them
+ *   SEPTFA_PRECISION_ACCURATE  2-term fp16 split of both operands (three passes, fp32-accurate), fp32 storage
+ *   SEPTFA_PRECISION_AUTO      (default) ACCURATE for apply_residual_ln (config_without_vad: the residual stream is
+ *                              never re-normalised and accumulates the rounding of all blocks), FAST otherwise */
+#define SEPTFA_PRECISION_AUTO 0
+#define SEPTFA_PRECISION_FAST 1
+#define SEPTFA_PRECISION_ACCURATE 2
 int septfa_set_option(septfa_handle* h, const char* name, int value);
 int septfa_get_option(const septfa_handle* h, const char* name);
 
@@ -134,6 +142,20 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
 int septfa_forward_host_submit(septfa_handle* h, int slot, const float* x_host, int B, int64_t L, const septfa_infer_kw* kw,
                                float* out_wav_host, float* out_vad_host);
 int septfa_forward_host_wait(septfa_handle* h, int slot);
+
+/* The same submit with 16-bit sample formats on the host side, which halves the PCIe bytes in either direction:
+ *   x_fmt   SEPTFA_FMT_F32   float32 waveforms, already normalised (what forward() takes)
+ *           SEPTFA_FMT_PCM16 int16 PCM exactly as scipy.io.wavfile.read returns it (only_inference.py:68); the device then
+ *                            does only_inference.py:69,81: astype(float32) and the min-max normalisation to [-0.9, 0.9],
+ *                            bit-identical to the reference's numpy expression, before the forward
+ *   out_fmt SEPTFA_FMT_F32   float32 waveforms
+ *           SEPTFA_FMT_F16   IEEE half, round to nearest: the `-ps 16` format of save_audio (Our_utils/utlis_inference.py:30-32)
+ * x_host: B*L elements of x_fmt; out_wav_host: B*2*L elements of out_fmt; out_vad_host: float32 as above. */
+#define SEPTFA_FMT_F32 0
+#define SEPTFA_FMT_PCM16 1
+#define SEPTFA_FMT_F16 2
+int septfa_forward_host_submit_fmt(septfa_handle* h, int slot, const void* x_host, int x_fmt, int B, int64_t L,
+                                   const septfa_infer_kw* kw, void* out_wav_host, int out_fmt, float* out_vad_host);
 
 /* Number of GPU kernels launched by the last forward / online step on this handle. */
 int septfa_last_launch_count(const septfa_handle* h);

@@ -32,7 +32,7 @@ struct TcParams {
   int M, T, B;
   int late_trigger;            // MODE 1: let the dependent grid (a persistent kernel) launch only when this CTA's main loop is done
   const __half* w_img;
-  const __half* w_img_lo;   // MODE 2: low part of the fp16 split of the weights
+  const __half* w_img_lo;   // MODE 2 / SPLIT: low part of the fp16 split of the weights
   const void* in;           // [M,256] fp32 (MODE 0/2, and MODE 1 when !H16) or fp16 (MODE 1 with H16)
   StreamNorm norm;
   // MODE 2 prologue
@@ -68,18 +68,33 @@ __device__ __forceinline__ float4 ld_half4(const __half* p) {   // 4 consecutive
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// Low part of the 2-term fp16 split: fp16(x - fp16(x)), the residual being exact in fp32.
+__device__ __forceinline__ uint32_t pack_residual2(float a, float b, uint32_t hi) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  return pack_half2(a - h.x, b - h.y);
+}
+__device__ __forceinline__ uint4 pack_residual8(const float (&y)[8], const uint4& hi) {
+  return make_uint4(pack_residual2(y[0], y[1], hi.x), pack_residual2(y[2], y[3], hi.y), pack_residual2(y[4], y[5], hi.z),
+                    pack_residual2(y[6], y[7], hi.w));
+}
+
 // H16: the activation tensor exchanged with the neighbouring contraction (conv1's output p = dconv's input; dconv's
 // output racc) is stored as fp16 instead of fp32.
 // AMAX (MODE 1): the PReLU slope of the depthwise stage is <= 1, so PReLU(x) = max(x, a x); otherwise min(x, a x).
-template <int MODE, bool H16, bool AMAX = true>
-__global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
+// SPLIT (MODE 0 / 1): split-precision operands - A = A_hi + A_lo and W = W_hi + W_lo, each part fp16, three tensor-core
+// passes A_hi W_hi + A_lo W_hi + A_hi W_lo into the same fp32 accumulator (the A_lo W_lo term is below 2^-22 relative):
+// the contraction is then fp32-accurate. Used with fp32 storage of p / racc (H16 = false) by the "accurate" precision
+// mode, which config_without_vad needs (its un-renormalised residual stream accumulates the fp16 rounding of every
+// block: DESIGN.md, "Precision"). The stage then holds [A_hi][A_lo][W_hi][W_lo] = 96 KB: one CTA per SM.
+template <int MODE, bool H16, bool AMAX = true, bool SPLIT = false>
+__global__ void __launch_bounds__(kThreads, SPLIT ? 1 : 2) k_tc_gemm(TcParams p) {
   constexpr int NT = (MODE == 2) ? 192 : 256;
   constexpr int KDIM = (MODE == 1) ? 512 : 256;
   constexpr int NCH = KDIM / 64;
   constexpr int WCH = NT * 128;
   // MODE 2 runs a 3-pass fp16 split (A = A_hi + A_lo, W = W_hi + W_lo; A_hi W_hi + A_lo W_hi + A_hi W_lo): the output
   // conv feeds the VAD head directly and dominated its error budget, and costs < 3 % of the FLOPs.
-  constexpr int NSPLIT = (MODE == 2) ? 2 : 1;
+  constexpr int NSPLIT = (MODE == 2 || SPLIT) ? 2 : 1;
   constexpr int STAGE = NSPLIT * (kAChunkBytes + WCH);   // [A_hi][A_lo][W_hi][W_lo]
   constexpr int OFF_W = NSPLIT * kAChunkBytes;
   constexpr uint32_t IDESC = make_idesc_f16(kTileM, NT);
@@ -236,9 +251,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
           const int rl = it * 32 + warp * 4 + rg;
           const float4 x0 = xa[j & 1][it], x1 = xb[j & 1][it];
           const float sc = mrs[it].y, nb = -mrs[it].x * mrs[it].y;
-          const uint4 pk = make_uint4(pack_half2(fmaf(x0.x, sc, nb), fmaf(x0.y, sc, nb)), pack_half2(fmaf(x0.z, sc, nb), fmaf(x0.w, sc, nb)),
-                                      pack_half2(fmaf(x1.x, sc, nb), fmaf(x1.y, sc, nb)), pack_half2(fmaf(x1.z, sc, nb), fmaf(x1.w, sc, nb)));
+          const float y[8] = {fmaf(x0.x, sc, nb), fmaf(x0.y, sc, nb), fmaf(x0.z, sc, nb), fmaf(x0.w, sc, nb),
+                              fmaf(x1.x, sc, nb), fmaf(x1.y, sc, nb), fmaf(x1.z, sc, nb), fmaf(x1.w, sc, nb)};
+          const uint4 pk = make_uint4(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]), pack_half2(y[6], y[7]));
           *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = pk;
+          if constexpr (NSPLIT == 2) *reinterpret_cast<uint4*>(a_tile + kAChunkBytes + sw128_offset(rl, c8)) = pack_residual8(y, pk);
         }
         fence_proxy_async();
         mbar_arrive(full_a + s);
@@ -332,6 +349,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
           }
         }
         uint32_t pk[2][4];
+        [[maybe_unused]] uint32_t pl[2][4];
 #pragma unroll
         for (int gp = 0; gp < 2; ++gp) {
           float2 P[2][2];
@@ -359,12 +377,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
           for (int i2 = 0; i2 < 2; ++i2) {
             pk[i2][gp * 2] = pack_half2(P[0][i2].x, P[1][i2].x);
             pk[i2][gp * 2 + 1] = pack_half2(P[0][i2].y, P[1][i2].y);
+            if constexpr (NSPLIT == 2) {
+              pl[i2][gp * 2] = pack_residual2(P[0][i2].x, P[1][i2].x, pk[i2][gp * 2]);
+              pl[i2][gp * 2 + 1] = pack_residual2(P[0][i2].y, P[1][i2].y, pk[i2][gp * 2 + 1]);
+            }
           }
         }
 #pragma unroll
         for (int i2 = 0; i2 < 2; ++i2) {
           const int rl = (half * 2 + i2) * 32 + warp * 4 + rg;
           *reinterpret_cast<uint4*>(a_tile + sw128_offset(rl, c8)) = make_uint4(pk[i2][0], pk[i2][1], pk[i2][2], pk[i2][3]);
+          if constexpr (NSPLIT == 2)
+            *reinterpret_cast<uint4*>(a_tile + kAChunkBytes + sw128_offset(rl, c8)) = make_uint4(pl[i2][0], pl[i2][1], pl[i2][2], pl[i2][3]);
         }
       };
       Step sa, sb;
@@ -645,12 +669,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(TcParams p) {
   if (sdst != nullptr && blockIdx.y == 0) seg_stats_commit(slots, 8, seg_acc, nseg, sdst + b_first);
 }
 
-template <int MODE, bool H16, bool AMAX = true>
+template <int MODE, bool H16, bool AMAX = true, bool SPLIT = false>
 void launch_mode(const TcParams& p, int ntiles_n, cudaStream_t st) {
   constexpr int NT = (MODE == 2) ? 192 : 256;
-  constexpr int smem = kStages * (MODE == 2 ? 2 : 1) * (kAChunkBytes + NT * 128) + kAuxBytes + 1024 + (MODE == 1 ? kDconvWBytes : 0);
+  constexpr int smem = kStages * ((MODE == 2 || SPLIT) ? 2 : 1) * (kAChunkBytes + NT * 128) + kAuxBytes + 1024 + (MODE == 1 ? kDconvWBytes : 0);
   dim3 grid((p.M + kTileM - 1) / kTileM, ntiles_n);
-  launch_k(k_tc_gemm<MODE, H16, AMAX>, grid, dim3(kThreads), smem, st, true, p);
+  launch_k(k_tc_gemm<MODE, H16, AMAX, SPLIT>, grid, dim3(kThreads), smem, st, true, p);
 }
 
 }  // namespace
@@ -677,10 +701,10 @@ void gemm_dump_cta_timeline(int ncta) {   // wall-clock phases of every CTA of t
 }
 #endif
 
-template <int MODE, bool H16, bool AMAX = true>
+template <int MODE, bool H16, bool AMAX = true, bool SPLIT = false>
 cudaError_t setup_one(int smem) {
-  cudaFuncSetAttribute(k_tc_gemm<MODE, H16, AMAX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  return cudaFuncSetAttribute(k_tc_gemm<MODE, H16, AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_tc_gemm<MODE, H16, AMAX, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return cudaFuncSetAttribute(k_tc_gemm<MODE, H16, AMAX, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 cudaError_t tc_gemm_setup() {
@@ -696,20 +720,28 @@ cudaError_t tc_gemm_setup() {
   if ((e = setup_one<1, true>(s0 + kDconvWBytes)) != cudaSuccess) return e;
   if ((e = setup_one<1, false, false>(s0 + kDconvWBytes)) != cudaSuccess) return e;
   if ((e = setup_one<1, true, false>(s0 + kDconvWBytes)) != cudaSuccess) return e;
+  // split-precision ("accurate") variants: fp32 activations, [A_hi][A_lo][W_hi][W_lo] stages
+  const int s0s = kStages * 2 * (kAChunkBytes + 256 * 128) + kAuxBytes + 1024;
+  if ((e = setup_one<0, false, true, true>(s0s)) != cudaSuccess) return e;
+  if ((e = setup_one<0, false, false, true>(s0s)) != cudaSuccess) return e;
+  if ((e = setup_one<1, false, true, true>(s0s + kDconvWBytes)) != cudaSuccess) return e;
+  if ((e = setup_one<1, false, false, true>(s0s + kDconvWBytes)) != cudaSuccess) return e;
   return setup_one<2, false>(s2);
 }
 
 void launch_tc_conv1(const Conv1Params& c, cudaStream_t st) {
-  if (launch_conv1_persist(c, st)) return;   // persistent warp-specialised kernel (T >= 128, fp16 activations)
+  if (!c.split && launch_conv1_persist(c, st)) return;   // persistent warp-specialised kernel (T >= 128, fp16 activations)
   TcParams p{};
   p.M = c.M; p.T = c.T; p.B = c.B;
-  p.w_img = c.w_img; p.in = c.w_in; p.norm = c.norm;
+  p.w_img = c.w_img; p.w_img_lo = c.w_img_lo; p.in = c.w_in; p.norm = c.norm;
   p.bias = c.bias_f; p.slope = c.slope;
   p.out = c.p_out; p.out_stride = kC; p.st_out = c.st_p;
 #ifdef SEPTFA_TIMELINE
   p.dbg = g_tl_conv1;
 #endif
-  if (c.slope <= 1.f) {
+  if (c.split) {   // split-precision operands, fp32 p
+    if (c.slope <= 1.f) launch_mode<0, false, true, true>(p, 1, st); else launch_mode<0, false, false, true>(p, 1, st);
+  } else if (c.slope <= 1.f) {
     if (c.half_io) launch_mode<0, true, true>(p, 1, st); else launch_mode<0, false, true>(p, 1, st);
   } else {
     if (c.half_io) launch_mode<0, true, false>(p, 1, st); else launch_mode<0, false, false>(p, 1, st);
@@ -719,13 +751,15 @@ void launch_tc_conv1(const Conv1Params& c, cudaStream_t st) {
 void launch_tc_dconv(const DconvParams& c, cudaStream_t st) {
   TcParams p{};
   p.M = c.M; p.T = c.T; p.B = c.B;
-  p.w_img = c.w_img; p.in = c.p_in;
+  p.w_img = c.w_img; p.w_img_lo = c.w_img_lo; p.in = c.p_in;
   p.st_p = c.st_p; p.wtab = c.wtab; p.bog = c.bog;
   p.slope2 = c.slope2; p.dil = c.dil; p.st_q = c.st_q;
   p.out = c.racc; p.out_stride = kC; p.rowsum = c.rowsum; p.colsum = c.colsum;
   p.dbg = c.dbg;
   p.late_trigger = ctx().dconv_late_trigger;
-  if (c.slope2 <= 1.f) {
+  if (c.split) {   // split-precision operands, fp32 p and racc
+    if (c.slope2 <= 1.f) launch_mode<1, false, true, true>(p, 1, st); else launch_mode<1, false, false, true>(p, 1, st);
+  } else if (c.slope2 <= 1.f) {
     if (c.half_io) launch_mode<1, true, true>(p, 1, st); else launch_mode<1, false, true>(p, 1, st);
   } else {
     if (c.half_io) launch_mode<1, true, false>(p, 1, st); else launch_mode<1, false, false>(p, 1, st);

@@ -31,6 +31,8 @@ struct Conv1Params {
   void* p_out;         // [M,256] fp32, or fp16 when half_io
   Stat2* st_p;         // [B]
   int half_io;         // store p as fp16 (both conv1 and dconv on the tcgen05 engine)
+  const __half* w_img_lo = nullptr;  // low part of the fp16 weight split ("accurate" precision mode)
+  int split = 0;       // split-precision operands: three tensor-core passes, fp32-accurate contraction
 };
 
 // DepthConv1d second half (model/model.py:136/142,144) with GroupNorm reg2 folded into W3:
@@ -56,6 +58,8 @@ struct DconvParams {
   int half_io;         // p and racc are fp16
   const float4* wtab;  // tcgen05 engine: the folded taps in pair order, 640 float4 (septfa_abi.cu: dconv tap table)
   const float* bog;    // tcgen05 engine: [256] beta1 / gamma1 (zero-padding substitute, see gemm_tc.cu)
+  const __half* w_img_lo = nullptr;  // low part of the fp16 weight split ("accurate" precision mode)
+  int split = 0;       // split-precision operands: three tensor-core passes, fp32-accurate contraction
 };
 
 // TCN.output (model/model.py:322-325,357): logits = Wo GN(PReLU(y)) + bo, N = 514 padded to 576.
@@ -94,6 +98,7 @@ struct GateParams {
   float* rb;           // [B,256]
   float* gf;           // [B,256]
   float* gt;           // [M]
+  float* mt;           // [M] scratch of the streaming gate kernel: per-frame channel means
 };
 
 enum LnMode { LN_NONE = 0, LN_RECURSIVE = 1, LN_RESIDUAL = 2 };
@@ -137,6 +142,9 @@ void gemm_dump_cta_timeline(int ncta);
 // preproc.cu
 void launch_minmax_normalize(const float* x, int B, int64_t L, const int64_t* lengths /*nullable*/, unsigned* ext /*[B][2] scratch*/,
                              float* out, cudaStream_t st);
+void launch_minmax_normalize_pcm16(const int16_t* x, int B, int64_t L, const int64_t* lengths /*nullable*/, unsigned* ext, float* out,
+                                   cudaStream_t st);
+void launch_to_half(const float* in, __half* out, int64_t n, cudaStream_t st);
 void launch_sisdr(const float* p, const float* t, int64_t rows, int64_t n, int zero_mean, double* scratch /*[rows][5]*/, float* out,
                   cudaStream_t st);
 // gemm_conv1_persist.cu

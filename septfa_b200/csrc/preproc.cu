@@ -5,6 +5,7 @@
 // compiler cannot contract them into FMAs: the result is bit-identical to numpy's. A constant signal gives 0/0 = NaN,
 // like the reference. Two kernels: per-utterance extrema (ordered-integer atomics), then the element-wise map with
 // 16-byte accesses.
+#include <algorithm>
 #include "kernels.h"
 
 namespace septfa {
@@ -28,18 +29,21 @@ __global__ void k_ext_init(unsigned* ext, int n) {
   if (i < n) ext[i] = (i & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
 }
 
-__global__ void __launch_bounds__(256) k_minmax(const float* __restrict__ x, int64_t L, const int64_t* __restrict__ lengths,
+// XT = float, or int16_t: PCM samples as scipy.io.wavfile.read returns them, converted like only_inference.py:69
+// (`np.array(audio, dtype=np.float32)`, exact for 16-bit integers).
+template <typename XT>
+__global__ void __launch_bounds__(256) k_minmax(const XT* __restrict__ x, int64_t L, const int64_t* __restrict__ lengths,
                                                 unsigned* __restrict__ ext /*[B][2]: ordered min, ordered max*/) {
   __shared__ float red[2][8];
   const int b = blockIdx.y;
   const int64_t n = lengths != nullptr ? min(lengths[b], L) : L;
   const int64_t i0 = (int64_t)blockIdx.x * kNormChunk;
   if (i0 >= n) return;
-  const float* xb = x + (int64_t)b * L;
+  const XT* xb = x + (int64_t)b * L;
   float lo = INFINITY, hi = -INFINITY;
   const int64_t i1 = min(i0 + kNormChunk, n);
   for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) {
-    const float v = __ldg(xb + i);
+    const float v = (float)__ldg(xb + i);
     lo = fminf(lo, v);
     hi = fmaxf(hi, v);
   }
@@ -58,30 +62,59 @@ __global__ void __launch_bounds__(256) k_minmax(const float* __restrict__ x, int
   }
 }
 
-__global__ void __launch_bounds__(256) k_norm_apply(const float* __restrict__ x, int64_t L, const int64_t* __restrict__ lengths,
+template <typename XT>
+__global__ void __launch_bounds__(256) k_norm_apply(const XT* __restrict__ x, int64_t L, const int64_t* __restrict__ lengths,
                                                     const unsigned* __restrict__ ext, float* __restrict__ out) {
   const int b = blockIdx.y;
   const int64_t n = lengths != nullptr ? min(lengths[b], L) : L;
   const float mn = ord2f(ext[2 * b]), mx = ord2f(ext[2 * b + 1]);
   const float range = __fsub_rn(mx, mn);
-  const float* xb = x + (int64_t)b * L;
+  const XT* xb = x + (int64_t)b * L;
   float* ob = out + (int64_t)b * L;
   const int64_t i0 = (int64_t)blockIdx.x * kNormChunk, i1 = min(i0 + kNormChunk, L);
   for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) {
     float v = 0.f;   // samples past a ragged utterance's length are written as zeros
-    if (i < n) v = __fsub_rn(__fdiv_rn(__fmul_rn(1.8f, __fsub_rn(__ldg(xb + i), mn)), range), 0.9f);
+    if (i < n) v = __fsub_rn(__fdiv_rn(__fmul_rn(1.8f, __fsub_rn((float)__ldg(xb + i), mn)), range), 0.9f);
     ob[i] = v;
   }
+}
+
+// float32 -> IEEE half, round to nearest even: numpy's `.astype(np.float16)` of save_audio (Our_utils/utlis_inference.py:30-32)
+__global__ void __launch_bounds__(256) k_to_half(const float4* __restrict__ in, uint2* __restrict__ out, int64_t n4,
+                                                 const float* __restrict__ in_tail, __half* __restrict__ out_tail, int ntail) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(in + i);
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    out[i] = make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b));
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) out_tail[threadIdx.x] = __float2half_rn(in_tail[threadIdx.x]);
+}
+
+template <typename XT>
+void minmax_normalize_t(const XT* x, int B, int64_t L, const int64_t* lengths, unsigned* ext, float* out, cudaStream_t st) {
+  k_ext_init<<<(2 * B + 255) / 256, 256, 0, st>>>(ext, 2 * B);
+  dim3 grid((unsigned)((L + kNormChunk - 1) / kNormChunk), B);
+  k_minmax<XT><<<grid, 256, 0, st>>>(x, L, lengths, ext);
+  k_norm_apply<XT><<<grid, 256, 0, st>>>(x, L, lengths, ext, out);
+  ctx().launches += 3;
 }
 
 }  // namespace
 
 void launch_minmax_normalize(const float* x, int B, int64_t L, const int64_t* lengths, unsigned* ext, float* out, cudaStream_t st) {
-  k_ext_init<<<(2 * B + 255) / 256, 256, 0, st>>>(ext, 2 * B);
-  dim3 grid((unsigned)((L + kNormChunk - 1) / kNormChunk), B);
-  k_minmax<<<grid, 256, 0, st>>>(x, L, lengths, ext);
-  k_norm_apply<<<grid, 256, 0, st>>>(x, L, lengths, ext, out);
-  ctx().launches += 3;
+  minmax_normalize_t<float>(x, B, L, lengths, ext, out, st);
+}
+void launch_minmax_normalize_pcm16(const int16_t* x, int B, int64_t L, const int64_t* lengths, unsigned* ext, float* out,
+                                   cudaStream_t st) {
+  minmax_normalize_t<int16_t>(x, B, L, lengths, ext, out, st);
+}
+void launch_to_half(const float* in, __half* out, int64_t n, cudaStream_t st) {
+  const int64_t n4 = n / 4;
+  const int blocks = (int)std::min<int64_t>(148 * 8, (n4 + 255) / 256 + 1);
+  k_to_half<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out), n4, in + n4 * 4,
+                                    out + n4 * 4, (int)(n - n4 * 4));
+  ctx().launches += 1;
 }
 
 }  // namespace septfa

@@ -25,7 +25,7 @@ struct KeySpec {
 };
 
 struct DevBlock {
-  const __half* w1_img; const float* w1_t; const float* b1; const float* b1f; float a1; const float* g1; const float* be1;
+  const __half* w1_img; const __half* w1_img_lo; const __half* w3_img_lo; const float* w1_t; const float* b1; const float* b1f; float a1; const float* g1; const float* be1;
   const float4* w2b; const float4* w2f; const float* c2f; float a2; int dil;
   const float4* wtab; const float* bog;   // tcgen05 dconv producer: pair-ordered tap table, beta1 / gamma1
   const __half* w3_img; const float* w3_t; const float* s3_tc; const float* s3_ref; const float* c03;
@@ -67,11 +67,13 @@ struct septfa_handle {
     cudaStream_t stream = nullptr;          // copies of this slot
     cudaEvent_t ev_in = nullptr, ev_done = nullptr;
     float* x = nullptr; float* out = nullptr; float* vad = nullptr; void* ws = nullptr;
-    size_t cap_x = 0, cap_out = 0, cap_vad = 0, cap_ws = 0;
+    void* xraw = nullptr; void* out16 = nullptr; unsigned* ext = nullptr;   // PCM16 input staging, fp16 output staging, extrema
+    size_t cap_x = 0, cap_out = 0, cap_vad = 0, cap_ws = 0, cap_xraw = 0, cap_out16 = 0, cap_ext = 0;
     bool busy = false;
   } slots[SEPTFA_HOST_SLOTS];
   cudaStream_t slot_compute = nullptr;      // kernels of both slots, in submission order
   int fused_resid = 1;  // cluster-resident gate + residual kernel when the utterance fits a cluster
+  int precision = SEPTFA_PRECISION_AUTO;   // option "precision"
   float* hx_dev = nullptr; float* hout_dev = nullptr; float* hvad_dev = nullptr; void* hws = nullptr; void* hws_b = nullptr;
   float* hx_pin = nullptr; float* hout_pin = nullptr; float* hvad_pin = nullptr;
   size_t hcap_x = 0, hcap_out = 0, hcap_vad = 0, hcap_ws = 0, hcap_ws_b = 0;
@@ -216,10 +218,17 @@ std::vector<__half> pack_image(const std::vector<double>& w, int nvalid, int kdi
   return img;
 }
 
+// Low part of the 2-term fp16 split of a weight matrix: w - fp16(w), evaluated on the fp32 value.
+std::vector<double> split_lo(const std::vector<double>& w) {
+  std::vector<double> lo(w.size());
+  for (size_t i = 0; i < w.size(); ++i) lo[i] = (double)((float)w[i] - __half2float(__float2half((float)w[i])));
+  return lo;
+}
+
 const std::vector<float>& T_(septfa_handle* h, const std::string& k) { return h->host.at(k); }
 
 struct Workspace {
-  float2* S; float* w; float* dcg; float* p; float* racc; float* rowsum; float* gt; float* logits;
+  float2* S; float* w; float* dcg; float* p; float* racc; float* rowsum; float* gt; float* mt; float* logits;
   float* ra; float* rb; float* gf; float* c4; float* prob; float* smooth;
   uint8_t* zero_begin; size_t zero_bytes;
   Stat2* st0; Stat2* st_blk; Stat2* st_o; Stat2* st_vad; double* colsum;
@@ -242,6 +251,7 @@ Workspace carve(const septfa_handle* h, void* base, int B, int64_t L) {
   w.racc = (float*)take(M * kC * sizeof(float));
   w.rowsum = (float*)take(M * sizeof(float));
   w.gt = (float*)take(M * sizeof(float));
+  w.mt = (float*)take(M * sizeof(float));
   w.logits = (float*)take(M * kLogitStride * sizeof(float));
   w.ra = (float*)take(B * sizeof(float));
   w.rb = (float*)take((size_t)B * kC * sizeof(float));
@@ -279,6 +289,7 @@ int check_forward_args(septfa_handle* h, int B, int64_t L) {
   if (!h->committed) return fail(h, SEPTFA_E_STATE, "weights not committed");
   if (B < 1) return fail(h, SEPTFA_E_INVALID, "B must be >= 1");
   if (L < 257) return fail(h, SEPTFA_E_INVALID, "L must be >= 257 (reflect padding of 256 samples needs a longer input)");
+  if (B > 32767) return fail(h, SEPTFA_E_INVALID, "B must be <= 32767 per call (grid limits): split larger batches, utterances are independent");
   if ((int64_t)B * septfa_num_frames(L) > (int64_t)1 << 30) return fail(h, SEPTFA_E_INVALID, "B*T too large");
   return 0;
 }
@@ -350,7 +361,7 @@ void septfa_destroy(septfa_handle* h) {
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
     if (sl.ev_in) cudaEventDestroy(sl.ev_in);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
-    cudaFree(sl.x); cudaFree(sl.out); cudaFree(sl.vad); cudaFree(sl.ws);
+    cudaFree(sl.x); cudaFree(sl.out); cudaFree(sl.vad); cudaFree(sl.ws); cudaFree(sl.xraw); cudaFree(sl.out16); cudaFree(sl.ext);
   }
   cudaFreeHost(h->hx_pin); cudaFreeHost(h->hout_pin); cudaFreeHost(h->hvad_pin);
   if (h->hstream) {
@@ -406,6 +417,11 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
     h->lctx.use_pdl = value ? 1 : 0;   // programmatic dependent launch of the forward's kernel chain
     return 0;
   }
+  if (std::strcmp(name, "precision") == 0) {
+    if (value < 0 || value > 2) return fail(h, SEPTFA_E_INVALID, "precision must be 0 (auto), 1 (fast) or 2 (accurate)");
+    h->precision = value;
+    return 0;
+  }
   if (std::strcmp(name, "host_chunks") == 0) {
     if (value < 0 || value > kHostChunksMax) return fail(h, SEPTFA_E_INVALID, "host_chunks must be 0..8");
     h->host_chunks = value;
@@ -416,6 +432,7 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
 int septfa_get_option(const septfa_handle* h, const char* name) {
   if (h && name && std::strcmp(name, "engine") == 0) return h->engine;
   if (h && name && std::strcmp(name, "profile") == 0) return h->profile;
+  if (h && name && std::strcmp(name, "precision") == 0) return h->precision;
   return SEPTFA_E_INVALID;
 }
 
@@ -472,7 +489,8 @@ int septfa_commit_weights(septfa_handle* h) {
           b1f[n] = (float)((double)b1f[n] + acc);
         }
       }
-      if (upload(h, pack_image(wf, kC, kC, 1, 256), &d.w1_img) || upload(h, wt, &d.w1_t) ||
+      if (upload(h, pack_image(wf, kC, kC, 1, 256), &d.w1_img) || upload(h, pack_image(split_lo(wf), kC, kC, 1, 256), &d.w1_img_lo) ||
+          upload(h, wt, &d.w1_t) ||
           upload(h, T_(h, p + ".conv1d.bias"), &d.b1) || upload(h, b1f, &d.b1f))
         return SEPTFA_E_CUDA;
       d.a1 = T_(h, p + ".nonlinearity1.weight")[0];
@@ -553,7 +571,8 @@ int septfa_commit_weights(septfa_handle* h) {
         s3_ref[n] = (float)s_ref;
         c03[n] = (float)c0;
       }
-      if (upload(h, pack_image(wg, kC, kH, 1, 256), &d.w3_img) || upload(h, wt, &d.w3_t) || upload(h, s3_tc, &d.s3_tc) ||
+      if (upload(h, pack_image(wg, kC, kH, 1, 256), &d.w3_img) || upload(h, pack_image(split_lo(wg), kC, kH, 1, 256), &d.w3_img_lo) ||
+          upload(h, wt, &d.w3_t) || upload(h, s3_tc, &d.s3_tc) ||
           upload(h, s3_ref, &d.s3_ref) || upload(h, c03, &d.c03))
         return SEPTFA_E_CUDA;
     }
@@ -611,8 +630,7 @@ int septfa_commit_weights(septfa_handle* h) {
             bias[n] = (float)bacc;
           }
     }
-    std::vector<double> w_lo(w.size());   // low part of the 2-term fp16 split used by the tcgen05 output conv
-    for (size_t i = 0; i < w.size(); ++i) w_lo[i] = (double)((float)w[i] - __half2float(__float2half((float)w[i])));
+    const std::vector<double> w_lo = split_lo(w);   // low part of the 2-term fp16 split used by the tcgen05 output conv
     for (int n = 0; n < nvalid; ++n)
       for (int k = 0; k < kC; ++k) wt[(size_t)k * kLogitStride + n] = (float)w[(size_t)n * kC + k];
     if (upload(h, T_(h, "TCN.output.1.weight"), &h->out_g) || upload(h, T_(h, "TCN.output.1.bias"), &h->out_be) ||
@@ -664,7 +682,13 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   // p (conv1 -> dconv) and racc (dconv -> residual kernels) are stored as fp16 when both producers run on the tensor
   // cores: their consumers round to fp16 operands anyway, and emulation on the oracle shows no change of the VAD /
   // waveform error; the fp32 CUDA-core engine keeps fp32 storage.
-  const int half_io = (tc_conv1 && tc_dconv) ? 1 : 0;
+  // Precision mode of the two block contractions: "accurate" = split-precision operands (three tensor-core passes) and
+  // fp32 p / racc. AUTO picks it for the residual-LN wiring (config_without_vad): its stream is never re-normalised, so
+  // the fp16 roundings of all 24 blocks accumulate to ~1e-3 in VAD probability, against ~1e-4 with the recursive-LN
+  // wiring of config_with_vad (measured: DESIGN.md, "Precision").
+  const bool split = tc_conv1 && tc_dconv &&
+                     (h->precision == SEPTFA_PRECISION_ACCURATE || (h->precision == SEPTFA_PRECISION_AUTO && h->ln_mode == LN_RESIDUAL));
+  const int half_io = (tc_conv1 && tc_dconv && !split) ? 1 : 0;
   const auto& c = h->cfg;
   bind_ctx(&h->lctx);
   ctx().launches = 0;
@@ -685,7 +709,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     Stat2* st_w = ws.st_blk + (size_t)(i * 4 + 3) * B;
     double* colsum = ws.colsum + (size_t)i * B * kC;
 
-    Conv1Params c1{ws.w, norm, M, T, B, d.b1, d.a1, d.w1_img, d.b1f, d.w1_t, ws.p, st_p, half_io};
+    Conv1Params c1{ws.w, norm, M, T, B, d.b1, d.a1, d.w1_img, d.b1f, d.w1_t, ws.p, st_p, half_io, d.w1_img_lo, split ? 1 : 0};
 #ifdef SEPTFA_TIMELINE
     g_tl_conv1 = (i == 6 && getenv("SEPTFA_TIMELINE") && septfa_dbg_ptr) ? septfa_dbg_ptr + 1024 : nullptr;
 #endif
@@ -694,7 +718,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
 
     prof_mark(h, SEPTFA_PROF_DCONV, st);
     DconvParams dc{ws.p, st_p, d.g1, d.be1, d.w2b, d.w2f, d.c2f, d.a2, d.dil, M, T, B, d.w3_img, d.w3_t, ws.racc, ws.rowsum, colsum, st_q,
-                   nullptr, half_io, d.wtab, d.bog};
+                   nullptr, half_io, d.wtab, d.bog, d.w3_img_lo, split ? 1 : 0};
 #ifdef SEPTFA_TIMELINE
     if (i == 5 && getenv("SEPTFA_TIMELINE")) {   // bring-up timeline of block 5's dconv launch
       if (!septfa_dbg_ptr) { cudaMalloc(reinterpret_cast<void**>(&septfa_dbg_ptr), 8 * 256 * sizeof(long long)); }
@@ -705,7 +729,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     if (tc_dconv) launch_tc_dconv(dc, st); else launch_ref_dconv(dc, st);
 
     prof_mark(h, SEPTFA_PROF_GATE, st);
-    GateParams gp{st_q, tc_dconv ? d.s3_tc : d.s3_ref, d.c03, ws.rowsum, colsum, d.tf, M, T, B, ws.ra, ws.rb, ws.gf, ws.gt};
+    GateParams gp{st_q, (tc_dconv && !split) ? d.s3_tc : d.s3_ref, d.c03, ws.rowsum, colsum, d.tf, M, T, B, ws.ra, ws.rb, ws.gf, ws.gt, ws.mt};
     ResidParams rp{};
     rp.w = ws.w; rp.norm = norm; rp.racc = ws.racc; rp.racc_half = half_io; rp.ra = ws.ra; rp.rb = ws.rb; rp.gf = ws.gf; rp.gt = ws.gt;
     rp.M = M; rp.T = T; rp.B = B; rp.mode = h->ln_mode; rp.st_v = st_v; rp.st_w = st_w;
@@ -881,7 +905,14 @@ int septfa_forward_host(septfa_handle* h, const float* x_host, int B, int64_t L,
 
 int septfa_forward_host_submit(septfa_handle* h, int slot, const float* x_host, int B, int64_t L, const septfa_infer_kw* kw,
                                float* out_wav_host, float* out_vad_host) {
+  return septfa_forward_host_submit_fmt(h, slot, x_host, SEPTFA_FMT_F32, B, L, kw, out_wav_host, SEPTFA_FMT_F32, out_vad_host);
+}
+
+int septfa_forward_host_submit_fmt(septfa_handle* h, int slot, const void* x_host, int x_fmt, int B, int64_t L,
+                                   const septfa_infer_kw* kw, void* out_wav_host, int out_fmt, float* out_vad_host) {
   if (int rc = check_forward_args(h, B, L)) return rc;
+  if (x_fmt != SEPTFA_FMT_F32 && x_fmt != SEPTFA_FMT_PCM16) return fail(h, SEPTFA_E_INVALID, "x_fmt must be SEPTFA_FMT_F32 or SEPTFA_FMT_PCM16");
+  if (out_fmt != SEPTFA_FMT_F32 && out_fmt != SEPTFA_FMT_F16) return fail(h, SEPTFA_E_INVALID, "out_fmt must be SEPTFA_FMT_F32 or SEPTFA_FMT_F16");
   if (slot < 0 || slot >= SEPTFA_HOST_SLOTS) return fail(h, SEPTFA_E_INVALID, "slot must be 0 or 1");
   if (!x_host || !out_wav_host) return fail(h, SEPTFA_E_INVALID, "null host buffer");
   auto& sl = h->slots[slot];
@@ -904,6 +935,7 @@ int septfa_forward_host_submit(septfa_handle* h, int slot, const float* x_host, 
   const int64_t T = septfa_num_frames(L);
   const size_t nx = (size_t)B * L * sizeof(float), nout = nx * 2, nvad = (size_t)B * 2 * T * sizeof(float);
   const size_t nws = septfa_workspace_bytes(h, B, L);
+  const bool pcm = x_fmt == SEPTFA_FMT_PCM16, half_out = out_fmt == SEPTFA_FMT_F16;
   auto grow = [&](void** dev, size_t* cap, size_t need) -> cudaError_t {
     if (*cap >= need) return cudaSuccess;
     cudaFree(*dev); *dev = nullptr; *cap = 0;
@@ -915,17 +947,37 @@ int septfa_forward_host_submit(septfa_handle* h, int slot, const float* x_host, 
   CUDA_TRY(h, grow(reinterpret_cast<void**>(&sl.out), &sl.cap_out, nout));
   CUDA_TRY(h, grow(reinterpret_cast<void**>(&sl.vad), &sl.cap_vad, nvad));
   CUDA_TRY(h, grow(&sl.ws, &sl.cap_ws, nws));
+  if (pcm) {
+    CUDA_TRY(h, grow(&sl.xraw, &sl.cap_xraw, nx / 2));
+    CUDA_TRY(h, grow(reinterpret_cast<void**>(&sl.ext), &sl.cap_ext, (size_t)B * 2 * sizeof(unsigned)));
+  }
+  if (half_out) CUDA_TRY(h, grow(&sl.out16, &sl.cap_out16, nout / 2));
   // Copies run on the slot's own stream, the kernels of BOTH slots on one compute stream in submission order: a
   // batch's forward has the SMs to itself (two interleaved 78-kernel chains were 15 % slower than back to back) while
   // the other slot's copy-in and copy-out use the two copy engines underneath it.
-  CUDA_TRY(h, cudaMemcpyAsync(sl.x, x_host, nx, cudaMemcpyHostToDevice, sl.stream));
+  // 16-bit formats halve the PCIe bytes either way: PCM16 input is converted and min-max normalised on the device
+  // (only_inference.py:69,81), fp16 output is the precision_save=16 cast of save_audio (utlis_inference.py:30-32).
+  if (pcm) CUDA_TRY(h, cudaMemcpyAsync(sl.xraw, x_host, nx / 2, cudaMemcpyHostToDevice, sl.stream));
+  else CUDA_TRY(h, cudaMemcpyAsync(sl.x, x_host, nx, cudaMemcpyHostToDevice, sl.stream));
   CUDA_TRY(h, cudaEventRecord(sl.ev_in, sl.stream));
   CUDA_TRY(h, cudaStreamWaitEvent(h->slot_compute, sl.ev_in, 0));
+  int extra = 0;
+  if (pcm) {
+    bind_ctx(&h->lctx);
+    launch_minmax_normalize_pcm16(reinterpret_cast<const int16_t*>(sl.xraw), B, L, nullptr, sl.ext, sl.x, h->slot_compute);
+    extra += 3;
+  }
   if (int rc = septfa_forward(h, sl.x, B, L, kw, sl.out, sl.vad, nullptr, nullptr, nullptr, nullptr, sl.ws, sl.cap_ws, h->slot_compute))
     return rc;
+  if (half_out) {
+    launch_to_half(sl.out, reinterpret_cast<__half*>(sl.out16), (int64_t)B * 2 * L, h->slot_compute);
+    extra += 1;
+  }
+  h->last_launches += extra;
   CUDA_TRY(h, cudaEventRecord(sl.ev_done, h->slot_compute));
   CUDA_TRY(h, cudaStreamWaitEvent(sl.stream, sl.ev_done, 0));
-  CUDA_TRY(h, cudaMemcpyAsync(out_wav_host, sl.out, nout, cudaMemcpyDeviceToHost, sl.stream));
+  if (half_out) CUDA_TRY(h, cudaMemcpyAsync(out_wav_host, sl.out16, nout / 2, cudaMemcpyDeviceToHost, sl.stream));
+  else CUDA_TRY(h, cudaMemcpyAsync(out_wav_host, sl.out, nout, cudaMemcpyDeviceToHost, sl.stream));
   if (want_vad) CUDA_TRY(h, cudaMemcpyAsync(out_vad_host, sl.vad, nvad, cudaMemcpyDeviceToHost, sl.stream));
   sl.busy = true;
   return 0;
@@ -946,7 +998,7 @@ int septfa_last_launch_count(const septfa_handle* h) { return h ? h->last_launch
 
 // ------------------------------------------------------------------------------------------ online
 int septfa_online_create(septfa_handle* h, int S, septfa_online** out) {
-  if (!h || !out || S < 1) return fail(h, SEPTFA_E_INVALID, "bad arguments");
+  if (!h || !out || S < 1 || S > 32767) return fail(h, SEPTFA_E_INVALID, "bad arguments (1 <= S <= 32767 streams per online state)");
   if (!h->committed) return fail(h, SEPTFA_E_STATE, "weights not committed");
   CUDA_TRY(h, cudaSetDevice(h->device));
   auto* o = new septfa_online();
@@ -1026,7 +1078,7 @@ int septfa_online_step(septfa_online* o, const float* win, const septfa_infer_kw
 
 int septfa_pit_l1(septfa_handle* h, const float* a, const float* b, int S, int64_t n, int32_t* perm, double* pw_sums,
                   void* stream) {
-  if (!h || !a || !b || !perm || S < 1 || n < 1) return SEPTFA_E_INVALID;
+  if (!h || !a || !b || !perm || S < 1 || S > 65535 || n < 1) return SEPTFA_E_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (h->pit_cap < S) {
     cudaFree(h->pit_acc); h->pit_acc = nullptr; h->pit_cap = 0;
@@ -1042,7 +1094,7 @@ int septfa_pit_l1(septfa_handle* h, const float* a, const float* b, int S, int64
 }
 
 int septfa_minmax_normalize(septfa_handle* h, const float* x, int B, int64_t L, const int64_t* lengths, float* out, void* stream) {
-  if (!h || !x || !out || B < 1 || L < 1) return fail(h, SEPTFA_E_INVALID, "bad arguments");
+  if (!h || !x || !out || B < 1 || B > 65535 || L < 1) return fail(h, SEPTFA_E_INVALID, "bad arguments (1 <= B <= 65535)");
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (h->norm_cap < B) {
     cudaFree(h->norm_ext); h->norm_ext = nullptr; h->norm_cap = 0;

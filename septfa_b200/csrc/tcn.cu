@@ -222,7 +222,7 @@ __device__ __forceinline__ float tf_chain(const float* m, int n, int j, const fl
 }
 
 __global__ void __launch_bounds__(256) k_tf_gate(GateParams p) {
-  extern __shared__ float sm[];  // m_t [T]
+  float* sm = p.mt + (int64_t)blockIdx.x * p.T;   // m_t [T] of this utterance: global scratch, so T is unbounded
   __shared__ float m_f[kC];
   __shared__ float red[32];
   __shared__ float s_ra, s_mu, s_rbmean;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) k_tf_gate(GateParams p) {
 }
 
 void launch_tf_gate(const GateParams& p, cudaStream_t st) {
-  launch_k(k_tf_gate, dim3(p.B), dim3(256), p.T * sizeof(float), st, true, p);
+  launch_k(k_tf_gate, dim3(p.B), dim3(256), 0, st, true, p);
 }
 
 // ------------------------------------------------------------------------------------------

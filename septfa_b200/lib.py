@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libseptfa.so")
 
 ENGINE_TCGEN05_F16 = 0
+FMT_F32, FMT_PCM16, FMT_F16 = 0, 1, 2   # host sample formats of septfa_forward_host_submit_fmt
 ENGINE_FP32_SIMT = 7  # bit mask: 1 conv1d, 2 dconv+res_out, 4 output conv on fp32 CUDA cores
 
 
@@ -80,6 +81,8 @@ _PROTOS = {
     "septfa_forward_host_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.POINTER(InferKw),
                                              C.c_void_p, C.c_void_p]),
     "septfa_forward_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "septfa_forward_host_submit_fmt": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64,
+                                                 C.POINTER(InferKw), C.c_void_p, C.c_int, C.c_void_p]),
     "septfa_last_launch_count": (C.c_int, [C.c_void_p]),
     "septfa_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int, C.c_int]),
     "septfa_online_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),

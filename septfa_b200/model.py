@@ -249,15 +249,29 @@ class SeparationModel(nn.Module):
             _lib.check(h.ptr, rc)
         return out
 
-    def forward_host_submit(self, x_host: torch.Tensor, inference_kw={}, device=0, slot=0, out=None, vad=None):
-        """Asynchronous half of :meth:`forward_host` (septfa_forward_host_submit): enqueue copy-in, forward and
+    def forward_host_submit(self, x_host: torch.Tensor, inference_kw={}, device=0, slot=0, out=None, vad=None,
+                            out_dtype=torch.float32):
+        """Asynchronous half of :meth:`forward_host` (septfa_forward_host_submit_fmt): enqueue copy-in, forward and
         copy-out of one batch on pipeline slot 0 or 1 and return a :class:`HostBatch` whose ``result()`` waits for
         it. Two slots let successive batches overlap their PCIe copies with each other's kernels. ``x_host`` is
         pinned if it is not already; ``out`` / ``vad`` may be caller-provided pinned result tensors (reused across
-        batches), otherwise fresh pinned tensors are allocated."""
+        batches), otherwise fresh pinned tensors are allocated.
+
+        16-bit host formats halve the PCIe bytes: an ``int16`` ``x_host`` is PCM as ``scipy.io.wavfile.read`` returns
+        it - the device then does only_inference.py:69,81 (``astype(float32)``, min-max normalise to +-0.9) before the
+        forward; ``out_dtype=torch.float16`` returns the waveforms as the ``-ps 16`` format of ``save_audio``
+        (Our_utils/utlis_inference.py:30-32)."""
         assert x_host.ndim == 2 and not x_host.is_cuda
         kw = _lib.InferKw.from_dict(inference_kw) if (inference_kw and self.final_vad) else None
-        x_host = x_host.detach().to(torch.float32).contiguous()
+        if x_host.dtype == torch.int16:
+            x_fmt = _lib.FMT_PCM16
+            x_host = x_host.detach().contiguous()
+        else:
+            x_fmt = _lib.FMT_F32
+            x_host = x_host.detach().to(torch.float32).contiguous()
+        if out_dtype not in (torch.float32, torch.float16):
+            raise ValueError("out_dtype must be torch.float32 or torch.float16")
+        out_fmt = _lib.FMT_F16 if out_dtype == torch.float16 else _lib.FMT_F32
         if not x_host.is_pinned():
             x_host = x_host.pin_memory()
         B, L = x_host.shape
@@ -266,25 +280,26 @@ class SeparationModel(nn.Module):
         with torch.cuda.device(dev):
             h = self._handle(dev)
             if out is None:
-                out = torch.empty((B, self.num_spk, L), dtype=torch.float32, pin_memory=True)
+                out = torch.empty((B, self.num_spk, L), dtype=out_dtype, pin_memory=True)
             if vad is None and self.final_vad:
                 vad = torch.empty((B, self.num_spk, T), dtype=torch.float32, pin_memory=True)
-            assert tuple(out.shape) == (B, self.num_spk, L) and out.is_pinned() and out.is_contiguous()
-            rc = h.lib.septfa_forward_host_submit(h.ptr, int(slot), C.c_void_p(x_host.data_ptr()), B, L,
-                                                  C.byref(kw) if kw is not None else None, C.c_void_p(out.data_ptr()),
-                                                  C.c_void_p(vad.data_ptr()) if vad is not None else None)
+            assert tuple(out.shape) == (B, self.num_spk, L) and out.is_pinned() and out.is_contiguous() and out.dtype == out_dtype
+            rc = h.lib.septfa_forward_host_submit_fmt(h.ptr, int(slot), C.c_void_p(x_host.data_ptr()), x_fmt, B, L,
+                                                      C.byref(kw) if kw is not None else None, C.c_void_p(out.data_ptr()),
+                                                      out_fmt, C.c_void_p(vad.data_ptr()) if vad is not None else None)
             _lib.check(h.ptr, rc)
             self.last_launch_count = h.lib.septfa_last_launch_count(h.ptr)
         return HostBatch(self, h, dev, int(slot), x_host, out, vad if self.final_vad else None, kw)
 
-    def forward_host_stream(self, batches, inference_kw={}, device=0):
+    def forward_host_stream(self, batches, inference_kw={}, device=0, out_dtype=torch.float32):
         """Generator over an iterable of host batches ``[B, L]`` (the loop of only_inference.py:80-100 over a data
-        loader): yields ``(out_separation, output_vad)`` per batch, in order, keeping two batches in flight."""
+        loader): yields ``(out_separation, output_vad)`` per batch, in order, keeping two batches in flight. Batches
+        may be float32 (normalised) or int16 PCM; ``out_dtype`` as in :meth:`forward_host_submit`."""
         pending = []
         for i, xb in enumerate(batches):
             if len(pending) == 2:
                 yield pending.pop(0).result()
-            pending.append(self.forward_host_submit(xb, inference_kw, device, slot=i & 1))
+            pending.append(self.forward_host_submit(xb, inference_kw, device, slot=i & 1, out_dtype=out_dtype))
         while pending:
             yield pending.pop(0).result()
 
