@@ -19,6 +19,6 @@ _LAZY = {
 def __getattr__(name):
     if name in _LAZY:
         return getattr(_importlib.import_module(f"{__name__}.{_LAZY[name]}"), name)
-    if name in ("synth", "model", "online", "pit", "lib", "weights", "shard", "inference"):
+    if name in ("synth", "model", "online", "pit", "lib", "shard", "inference", "evaluate"):
         return _importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

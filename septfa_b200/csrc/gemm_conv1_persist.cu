@@ -47,11 +47,14 @@ struct PersistParams {
   const float* in;            // [M,256] fp32 stream
   StreamNorm norm;
   const float* bias; float slope;
-  __half* out;                // [M,256] fp16
+  __half* out;                // [M,256] fp16, or K-group planes [32][Mp][8] (PLANES)
+  int Mp;
   Stat2* st_out;              // [B]
 };
 
-template <bool AMAX>
+// PLANES: p is stored as K-group planes (kernels.h, DconvMmaParams): a lane = a row, so the 32 lanes of a warp write 512
+// contiguous bytes per plane straight from registers (full sectors: no staging, no bulk store).
+template <bool AMAX, bool PLANES>
 __global__ void __launch_bounds__(kThreadsP, 1) k_conv1_persist(PersistParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_conv1_persist(PersistParams p)
       const bool valid = rl < nrows;
       mbar_wait(acc_full + buf, (lt >> 1) & 1, 500);
       tc_fence_after();
-      bulk_wait_read_all();          // this lane's previous row piece has left the staging buffer
+      if constexpr (!PLANES) bulk_wait_read_all();   // this lane's previous row piece has left the staging buffer
       float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int cc = 0; cc < 8; ++cc) {
@@ -187,13 +190,21 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_conv1_persist(PersistParams p)
             h[2 * k] = pack_half2(y0.x, y0.y);
             h[2 * k + 1] = pack_half2(y1.x, y1.y);
           }
-          dst[i] = make_uint4(h[0], h[1], h[2], h[3]);
+          if constexpr (PLANES) {
+            if (valid)
+              *reinterpret_cast<uint4*>(p.out + ((size_t)(cc * 4 + i) * p.Mp + (size_t)(kPlaneHalo + r0 + rl)) * 8) =
+                  make_uint4(h[0], h[1], h[2], h[3]);
+          } else {
+            dst[i] = make_uint4(h[0], h[1], h[2], h[3]);
+          }
         }
       }
-      fence_proxy_async();           // this lane wrote its own row piece: no other lane's data is needed
-      if (valid) {
-        bulk_copy_s2g(p.out + (int64_t)(r0 + rl) * kC, stg, 512);
-        bulk_commit_group();
+      if constexpr (!PLANES) {
+        fence_proxy_async();           // this lane wrote its own row piece: no other lane's data is needed
+        if (valid) {
+          bulk_copy_s2g(p.out + (int64_t)(r0 + rl) * kC, stg, 512);
+          bulk_commit_group();
+        }
       }
       // statistics of this warp's 32 rows, per utterance: fixed-order shuffle trees, one double atomic pair
       const bool second = r0 + rl >= e1;
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) k_conv1_persist(PersistParams p)
         }
       }
     }
-    bulk_wait_read_all();
+    if constexpr (!PLANES) bulk_wait_read_all();
   } else if (warp == 12) {
     // ------------------------------------------------------------ weight loader
     if (lane == 0) {
@@ -263,9 +274,11 @@ cudaError_t conv1_persist_setup() {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t e = cudaFuncSetAttribute(k_conv1_persist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_conv1_persist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(k_conv1_persist<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv1_persist<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv1_persist<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv1_persist<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  return e;
 }
 
 // Returns false when the persistent kernel does not apply (caller uses the one-tile-per-CTA kernel).
@@ -274,10 +287,15 @@ bool launch_conv1_persist(const Conv1Params& c, cudaStream_t st) {
   PersistParams p{};
   p.M = c.M; p.T = c.T; p.ntiles = (c.M + kTileM - 1) / kTileM;
   p.w_img = c.w_img; p.in = c.w_in; p.norm = c.norm; p.bias = c.bias_f; p.slope = c.slope;
-  p.out = reinterpret_cast<__half*>(c.p_out); p.st_out = c.st_p;
+  p.out = reinterpret_cast<__half*>(c.p_out); p.st_out = c.st_p; p.Mp = c.Mp;
   const dim3 grid(std::min(g_sm_count, p.ntiles));
-  if (c.slope <= 1.f) launch_k(k_conv1_persist<true>, grid, dim3(kThreadsP), kSmemBytes, st, true, p);
-  else launch_k(k_conv1_persist<false>, grid, dim3(kThreadsP), kSmemBytes, st, true, p);
+  if (c.planes) {
+    if (c.slope <= 1.f) launch_k(k_conv1_persist<true, true>, grid, dim3(kThreadsP), kSmemBytes, st, true, p);
+    else launch_k(k_conv1_persist<false, true>, grid, dim3(kThreadsP), kSmemBytes, st, true, p);
+  } else {
+    if (c.slope <= 1.f) launch_k(k_conv1_persist<true, false>, grid, dim3(kThreadsP), kSmemBytes, st, true, p);
+    else launch_k(k_conv1_persist<false, false>, grid, dim3(kThreadsP), kSmemBytes, st, true, p);
+  }
   return true;
 }
 

@@ -31,6 +31,8 @@ struct Conv1Params {
   void* p_out;         // [M,256] fp32, or fp16 when half_io
   Stat2* st_p;         // [B]
   int half_io;         // store p as fp16 (both conv1 and dconv on the tcgen05 engine)
+  int planes = 0;      // store p (fp16) as K-group planes [32][Mp][8] for the tensor-core depthwise kernel (dconv_mma.cu)
+  int Mp = 0;          // slots per plane; frame r lives in slot r + kPlaneHalo
   const __half* w_img_lo = nullptr;  // low part of the fp16 weight split ("accurate" precision mode)
   int split = 0;       // split-precision operands: three tensor-core passes, fp32-accurate contraction
 };
@@ -60,6 +62,23 @@ struct DconvParams {
   const float* bog;    // tcgen05 engine: [256] beta1 / gamma1 (zero-padding substitute, see gemm_tc.cu)
   const __half* w_img_lo = nullptr;  // low part of the fp16 weight split ("accurate" precision mode)
   int split = 0;       // split-precision operands: three tensor-core passes, fp32-accurate contraction
+};
+
+// Plane layout of p for dconv_mma.cu: [32 K-groups of 8 channels][Mp slots][8 halves], frame r in slot r + kPlaneHalo;
+// the kPlaneHalo slots in front of frame 0 and the slots behind frame M - 1 are zero.
+constexpr int kPlaneHalo = 4;                      // = the largest dilation
+constexpr int kDconvTapBytes = 16 * 3 * 1024;      // [16 channel groups][3 taps][32 outputs x 16 inputs, fp16]
+struct DconvMmaParams {
+  const __half* p_planes; int Mp;
+  const Stat2* st_p;
+  const uint8_t* tap_img;   // block-diagonal tap matrices, no-swizzle K-major operand images
+  const float4* swc;        // [256] {sw[2i], sw[2i+1], c2f[2i], c2f[2i+1]}: sums of the fp16 taps, folded constants
+  const float* w16;         // [3][512] the fp16-rounded folded taps as fp32
+  const float* bog;         // [256] beta1 / gamma1
+  float slope2; int dil;
+  int M, T, B;
+  const __half* w_img;      // res_out image, as DconvParams
+  __half* racc; float* rowsum; double* colsum; Stat2* st_q;
 };
 
 // TCN.output (model/model.py:322-325,357): logits = Wo GN(PReLU(y)) + bo, N = 514 padded to 576.
@@ -150,6 +169,9 @@ void launch_sisdr(const float* p, const float* t, int64_t rows, int64_t n, int z
 // gemm_conv1_persist.cu
 cudaError_t conv1_persist_setup();
 bool launch_conv1_persist(const Conv1Params& p, cudaStream_t st);   // false: not applicable, use launch_tc_conv1's kernel
+// dconv_mma.cu
+cudaError_t dconv_mma_setup();
+void launch_dconv_mma(const DconvMmaParams& p, cudaStream_t st);
 // gemm_tc.cu
 void launch_tc_conv1(const Conv1Params& p, cudaStream_t st);
 void launch_tc_dconv(const DconvParams& p, cudaStream_t st);
@@ -189,6 +211,9 @@ struct LaunchCtx {
   int conv1_persist = 1;       // persistent warp-specialised conv1 kernel (0: always the one-tile-per-CTA kernel)
   int dconv_late_trigger = 1;  // dconv triggers its (persistent) dependent at the start of its epilogue
   int fused_pdl = 1;           // the cluster-resident residual kernel launches programmatically after dconv
+  int dconv_mma = 1;           // tensor-core depthwise + res_out kernel (dconv_mma.cu) when applicable
+  int dconv_desc_swap = 0;     // bring-up: exchange LBO / SBO of its no-swizzle descriptors
+  int dconv_cluster = 1;       // 2: clusters of two CTAs with a multicast weight stream (measured: no gain)
 };
 LaunchCtx& ctx();
 void bind_ctx(LaunchCtx* c);

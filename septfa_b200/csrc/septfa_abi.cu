@@ -28,6 +28,7 @@ struct DevBlock {
   const __half* w1_img; const __half* w1_img_lo; const __half* w3_img_lo; const float* w1_t; const float* b1; const float* b1f; float a1; const float* g1; const float* be1;
   const float4* w2b; const float4* w2f; const float* c2f; float a2; int dil;
   const float4* wtab; const float* bog;   // tcgen05 dconv producer: pair-ordered tap table, beta1 / gamma1
+  const uint8_t* tap_img; const float4* swc; const float* w16; bool mma_ok;   // tensor-core depthwise kernel (dconv_mma.cu)
   const __half* w3_img; const float* w3_t; const float* s3_tc; const float* s3_ref; const float* c03;
   TfParams tf;
   const float* lf_g; const float* lf_b; const float* ls_g; const float* ls_b;  // recursive
@@ -74,6 +75,7 @@ struct septfa_handle {
   cudaStream_t slot_compute = nullptr;      // kernels of both slots, in submission order
   int fused_resid = 1;  // cluster-resident gate + residual kernel when the utterance fits a cluster
   int precision = SEPTFA_PRECISION_AUTO;   // option "precision"
+  bool all_mma_ok = false;                 // every block's folded taps are representable for the tensor-core depthwise kernel
   float* hx_dev = nullptr; float* hout_dev = nullptr; float* hvad_dev = nullptr; void* hws = nullptr; void* hws_b = nullptr;
   float* hx_pin = nullptr; float* hout_pin = nullptr; float* hvad_pin = nullptr;
   size_t hcap_x = 0, hcap_out = 0, hcap_vad = 0, hcap_ws = 0, hcap_ws_b = 0;
@@ -247,7 +249,7 @@ Workspace carve(const septfa_handle* h, void* base, int B, int64_t L) {
   w.S = (float2*)take(M * kBins * sizeof(float2));
   w.w = (float*)take(M * kC * sizeof(float));
   w.dcg = (float*)take(M * sizeof(float));
-  w.p = (float*)take(M * kC * sizeof(float));
+  w.p = (float*)take(M * kC * sizeof(float) + (size_t)(256 + 2 * kPlaneHalo) * 512);   // also holds the fp16 plane layout (Mp slots)
   w.racc = (float*)take(M * kC * sizeof(float));
   w.rowsum = (float*)take(M * sizeof(float));
   w.gt = (float*)take(M * sizeof(float));
@@ -340,10 +342,13 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
   if (const char* e = getenv("SEPTFA_CONV1_PERSIST")) h->lctx.conv1_persist = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SEPTFA_DCONV_LATE_TRIGGER")) h->lctx.dconv_late_trigger = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SEPTFA_FUSED_PDL")) h->lctx.fused_pdl = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SEPTFA_DCONV_MMA")) h->lctx.dconv_mma = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SEPTFA_DCONV_DESC_SWAP")) h->lctx.dconv_desc_swap = atoi(e) ? 1 : 0;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, "cudaSetDevice failed"); }
   cudaError_t e = tc_gemm_setup();
   if (e == cudaSuccess) e = resid_fused_setup();
   if (e == cudaSuccess) e = conv1_persist_setup();
+  if (e == cudaSuccess) e = dconv_mma_setup();
   if (e != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, std::string("tc_gemm_setup: ") + cudaGetErrorString(e)); }
   *out = h;
   return 0;
@@ -415,6 +420,18 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "pdl") == 0) {
     h->lctx.use_pdl = value ? 1 : 0;   // programmatic dependent launch of the forward's kernel chain
+    return 0;
+  }
+  if (std::strcmp(name, "dconv_mma") == 0) {
+    h->lctx.dconv_mma = value ? 1 : 0;
+    return 0;
+  }
+  if (std::strcmp(name, "dconv_cluster") == 0) {
+    h->lctx.dconv_cluster = value == 2 ? 2 : 1;
+    return 0;
+  }
+  if (std::strcmp(name, "dconv_desc_swap") == 0) {   // bring-up switch of dconv_mma.cu
+    h->lctx.dconv_desc_swap = value ? 1 : 0;
     return 0;
   }
   if (std::strcmp(name, "precision") == 0) {
@@ -548,6 +565,38 @@ int septfa_commit_weights(septfa_handle* h) {
         if (upload(h, tab, &tptr) || upload(h, bog, &d.bog)) return SEPTFA_E_CUDA;
         d.wtab = reinterpret_cast<const float4*>(tptr);
       }
+      // dconv_mma.cu: the depthwise conv as block-diagonal tensor-core GEMMs. Group gi = input channels 16 gi .. +15 ->
+      // outputs 32 gi .. +31; per tap k a B operand [32 outputs][16 inputs] (fp16, K-major, no swizzle: core matrices of
+      // 8 rows x 16 B, the two K halves 512 B apart) with B[n][n / 2] = fp16(w[o][k] * gamma1[o / 2]) and zeros elsewhere.
+      // The kernel's affine uses the SAME rounded taps (sw = their sum, c2f = b2 + beta / gamma * sw), so the result is
+      // an exact depthwise conv with the effective weights fp16(w gamma) / gamma.
+      {
+        std::vector<uint8_t> img(kDconvTapBytes, 0);
+        std::vector<float> swc(4 * 256), w16(3 * kH);
+        bool ok = true;
+        for (int cch = 0; cch < kC; ++cch) ok = ok && std::isfinite(g1v[cch]) && std::fabs(g1v[cch]) >= 1e-3f;
+        for (int o = 0; o < kH; ++o) {
+          double sw = 0.0;
+          for (int k = 0; k < 3; ++k) {
+            const float f = (float)(w[o * 3 + k] * (double)g1v[o / 2]);
+            ok = ok && std::isfinite(f) && std::fabs(f) < 60000.f;
+            const __half hq = __float2half(f);
+            const float fq = __half2float(hq);
+            w16[k * kH + o] = fq;
+            sw += (double)fq;
+            const int gi = o / 32, n = o % 32, kk = (o / 2) % 16;
+            const size_t byte = (size_t)((gi * 3 + k) * 1024) + (size_t)(kk / 8) * 512 + (size_t)n * 16 + (size_t)(kk % 8) * 2;
+            std::memcpy(img.data() + byte, &hq, 2);
+          }
+          const double bogv = ok ? (double)be1v[o / 2] / (double)g1v[o / 2] : 0.0;
+          swc[(o / 2) * 4 + (o & 1)] = (float)sw;
+          swc[(o / 2) * 4 + 2 + (o & 1)] = (float)((double)b2[o] + bogv * sw);
+        }
+        const float* sp = nullptr;
+        if (upload(h, img, &d.tap_img) || upload(h, swc, &sp) || upload(h, w16, &d.w16)) return SEPTFA_E_CUDA;
+        d.swc = reinterpret_cast<const float4*>(sp);
+        d.mma_ok = ok;
+      }
     }
     // res_out 512 -> 256 with GroupNorm reg2 folded in:  r = rstd2 * (W3g q - mu2 * s3) + c03
     {
@@ -655,6 +704,8 @@ int septfa_commit_weights(septfa_handle* h) {
     h->act_b = T_(h, "activity_input.bias")[0];
     h->act_a = T_(h, "prelu.weight")[0];
   }
+  h->all_mma_ok = true;
+  for (const auto& d : h->blocks) h->all_mma_ok = h->all_mma_ok && d.mma_ok;
   h->committed = true;
   return 0;
 }
@@ -699,6 +750,14 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
                   ws.dcg, ws.st0, st);
   if (spectrum) launch_export(ws.S, ws.logits, nullptr, ws.w, ws.dcg, B, T, nullptr, nullptr, spectrum, nullptr, st);
 
+  // Tensor-core depthwise kernel (dconv_mma.cu): p travels as K-group planes; its halo slots must read as zeros.
+  const bool planes = half_io && T >= 128 && h->lctx.conv1_persist && h->lctx.dconv_mma && h->all_mma_ok;
+  const int Mp = (M + 255) / 256 * 256 + 2 * kPlaneHalo;   // whole tile PAIRS (dconv_mma.cu walks its tiles in pairs)
+  if (planes) {
+    uint8_t* pb = reinterpret_cast<uint8_t*>(ws.p);
+    CUDA_TRY(h, cudaMemset2DAsync(pb, (size_t)Mp * 16, 0, (size_t)kPlaneHalo * 16, 32, st));
+    CUDA_TRY(h, cudaMemset2DAsync(pb + (size_t)(M + kPlaneHalo) * 16, (size_t)Mp * 16, 0, (size_t)(Mp - M - kPlaneHalo) * 16, 32, st));
+  }
   const double inv_n = 1.0 / ((double)kC * T);
   StreamNorm norm{ws.st0, h->ln_g, h->ln_b, 1e-8f, inv_n};  // TCN.LN, model.py:333
   for (int i = 0; i < h->nblk; ++i) {
@@ -709,7 +768,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     Stat2* st_w = ws.st_blk + (size_t)(i * 4 + 3) * B;
     double* colsum = ws.colsum + (size_t)i * B * kC;
 
-    Conv1Params c1{ws.w, norm, M, T, B, d.b1, d.a1, d.w1_img, d.b1f, d.w1_t, ws.p, st_p, half_io, d.w1_img_lo, split ? 1 : 0};
+    Conv1Params c1{ws.w, norm, M, T, B, d.b1, d.a1, d.w1_img, d.b1f, d.w1_t, ws.p, st_p, half_io, planes ? 1 : 0, Mp, d.w1_img_lo, split ? 1 : 0};
 #ifdef SEPTFA_TIMELINE
     g_tl_conv1 = (i == 6 && getenv("SEPTFA_TIMELINE") && septfa_dbg_ptr) ? septfa_dbg_ptr + 1024 : nullptr;
 #endif
@@ -726,7 +785,15 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
       dc.dbg = septfa_dbg_ptr;
     }
 #endif
-    if (tc_dconv) launch_tc_dconv(dc, st); else launch_ref_dconv(dc, st);
+    if (planes) {
+      DconvMmaParams dm{reinterpret_cast<const __half*>(ws.p), Mp, st_p, d.tap_img, d.swc, d.w16, d.bog, d.a2, d.dil, M, T, B, d.w3_img,
+                        reinterpret_cast<__half*>(ws.racc), ws.rowsum, colsum, st_q};
+      launch_dconv_mma(dm, st);
+    } else if (tc_dconv) {
+      launch_tc_dconv(dc, st);
+    } else {
+      launch_ref_dconv(dc, st);
+    }
 
     prof_mark(h, SEPTFA_PROF_GATE, st);
     GateParams gp{st_q, (tc_dconv && !split) ? d.s3_tc : d.s3_ref, d.c03, ws.rowsum, colsum, d.tf, M, T, B, ws.ra, ws.rb, ws.gf, ws.gt, ws.mt};

@@ -102,6 +102,73 @@ def plot_spectrogram(masks, title, save_path):
         plt.close("all")
 
 
+def save_vad(vad_output, save_path):
+    """Our_utils/utlis_inference.py:39-46: the decisions ``p >= 0.5`` of batch item 0, one figure per speaker
+    (``estimated_vad_{spk}.png``). Without matplotlib the decisions are written as ``estimated_vad_{spk}.npy``."""
+    Path(save_path).mkdir(parents=True, exist_ok=True)
+    vad_output = vad_output.detach().cpu()
+    if vad_output.ndim == 4:            # [B, 2, 1, T] when return_smoothed_vad
+        vad_output = vad_output[:, :, 0]
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+    except ImportError:
+        plt = None
+    for spk in range(vad_output.shape[1]):
+        est_vad = torch.where(vad_output[0, spk] >= 0.5, 1, 0)
+        if plt is None:
+            np.save(os.path.join(save_path, f"estimated_vad_{spk}.npy"), est_vad.numpy())
+        else:
+            plt.plot(est_vad)
+            plt.savefig(os.path.join(save_path, f"estimated_vad_{spk}.png"))
+            plt.close()
+
+
+def separate_files(model, paths, save_dir, inference_kw=None, precision_save=32, device=0, batch=64):
+    """The file loop either side of the forward, batched: 16-bit mono 16 kHz wav files of
+    EQUAL length are grouped into batches; each batch travels to the device as int16 PCM, is converted and min-max
+    normalised there (only_inference.py:69,81, bit-identical to numpy), separated, and comes back as float32 or - for
+    ``precision_save=16`` - float16, two batches in flight (forward_host_stream). Other files (stereo, other rates or
+    sample formats) take the single-file path of :func:`read_mixture`. Writes ``<stem>_Speaker_{0,1}.wav`` into
+    ``save_dir`` (float32 wav, or 16-bit PCM for precision 16) and returns ``{path: vad [2, T]}``."""
+    from scipy.io.wavfile import read, write
+    Path(save_dir).mkdir(parents=True, exist_ok=True)
+    kw = copy.deepcopy(DEFAULT_INFERENCE_KW)
+    kw.update(inference_kw or {})
+    groups, singles = {}, []
+    for pth in paths:
+        sr, audio = read(pth)
+        if sr == 16000 and audio.ndim == 1 and audio.dtype == np.int16 and len(audio) >= 257:
+            groups.setdefault(len(audio), []).append((pth, audio))
+        else:
+            singles.append(pth)
+    out_dtype = torch.float16 if precision_save == 16 else torch.float32
+    vads = {}
+
+    def emit(pth, out, vad):
+        stem = Path(pth).stem
+        for s in range(2):
+            a = out[s].float().numpy()
+            if precision_save == 16:
+                a = np.clip(np.round(a * 32767.0), -32768, 32767).astype(np.int16)
+            write(os.path.join(save_dir, f"{stem}_Speaker_{s}.wav"), 16000, a)
+        vads[pth] = vad
+
+    for _, items in sorted(groups.items()):
+        chunks = [items[i:i + batch] for i in range(0, len(items), batch)]
+        batches = (torch.from_numpy(np.stack([a for _, a in ch])) for ch in chunks)
+        for ch, (out, vad) in zip(chunks, model.forward_host_stream(batches, kw, device=device, out_dtype=out_dtype)):
+            for i, (pth, _) in enumerate(ch):
+                emit(pth, out[i].clone(), vad[i].clone() if torch.is_tensor(vad) else None)
+    for pth in singles:
+        x = read_mixture(pth).to(torch.device("cuda", device))
+        with torch.no_grad():
+            out, vad, _ = model(x, kw)
+        emit(pth, out[0].cpu(), vad[0].cpu() if torch.is_tensor(vad) else None)
+    return vads
+
+
 def main(argv=None):
     args = argparse.ArgumentParser(description="septfa_b200 inference (flags of only_inference.py:110-134)")
     args.add_argument("-c", "--config", default="config_without_vad.json", type=str)
@@ -132,6 +199,10 @@ def main(argv=None):
         out_separation, output_vad, _ = model(x, inference_kw)                                # :90-91
     plot_spectrogram(model.mask_per_speaker, "Mask in fft domain", a.save_test_path)          # :92-94
     save_audio(x, out_separation, a.save_test_path, a.precision_save)                         # :95
+    # :96-97: `config.resume == "model_without_vad.pth"` compares a pathlib.Path with a str in the reference and is
+    # therefore never true there; the comparison is kept on the plain string the user typed
+    if a.resume == "model_without_vad.pth":
+        save_vad(output_vad, a.save_test_path)
     return out_separation, output_vad
 
 

@@ -41,7 +41,17 @@ class OnlineSaving:
         if criterion_similarity is not None:
             self.similarity = True
             self.criterion_similarity = criterion_similarity
+            self._check_similarity_criterion(criterion_similarity)
         self.last_perms = None
+
+    @staticmethod
+    def _check_similarity_criterion(crit):
+        """The stitch runs on the device as PITLossWrapper(nn.L1Loss(), pit_from='pw_pt') - the only criterion
+        only_inference.py:85-86 ever passes. Anything else would silently be replaced by it, so it is refused."""
+        lf = getattr(crit, "loss_func", None)
+        if getattr(crit, "pit_from", None) != "pw_pt" or not isinstance(lf, torch.nn.L1Loss):
+            raise NotImplementedError("septfa_b200.OnlineSaving stitches windows with PITLossWrapper(nn.L1Loss(), "
+                                      "pit_from='pw_pt') on the device; other similarity criteria are not supported")
 
     def reset(self):
         self.indx = 0
@@ -107,8 +117,12 @@ class OnlineSaving:
                     _lib.check(h.ptr, rc)
                     online[:, :, self.indx * hop:(self.indx + 1) * hop] = emitted              # :94 (cat)
                     if sample_indx < self.num_save_samples:                                   # :95-96
-                        # the reference dumps the whole reordered window; only the emitted second is kept here
-                        pass
+                        # per-window dumps of batch item 0: the model's window output (first tensor of the online
+                        # workspace, [S, 2, 48000]) reordered by this hop's permutation, and the window of the mixture
+                        base = (ws.data_ptr() + 255) // 256 * 256 - ws.data_ptr()
+                        pred0 = ws[base: base + 2 * self.max_len * self.fs * 4].view(torch.float32).view(1, 2, -1)
+                        pred0 = pred0[:, perms[self.indx][0].long()]
+                        self.save_audio(name_folder, pred0, win)
                     self.increase_indx()
                 torch.cuda.current_stream(dev).synchronize()
             finally:
@@ -134,11 +148,15 @@ class OnlineSavingKnownTargets(OnlineSaving):
     ("reference") pass (:126-145).
     """
 
-    def __init__(self, model, save_path, criterion_separation, criterion_similarity=None) -> None:
+    def __init__(self, criterion_separation, model, save_path, device=None, criterion_similarity=None) -> None:
+        # argument order of the reference's constructor (model/online_class_known_targets.py:10); `device` is accepted
+        # and ignored there too (the tensors decide)
         super().__init__(model, save_path, criterion_similarity)
         self.criterion_separation = criterion_separation
+        self.num_save_samples = 2000000                                                       # :20
 
     def calc_online(self, full_signal_mix, target_signal, name_folder, sample_indx, inference_kw=None):
+        """model/online_class_known_targets.py:85-154 (which calls the model without inference_kw: the default here)."""
         inference_kw = inference_kw or {}
         x = full_signal_mix.detach().float()
         tgt = target_signal.detach().float()

@@ -173,6 +173,15 @@ def make_mixture(index, length, base_seed=1234, fs=16000):
     return mix.astype(np.float32)
 
 
+def make_cli_wav(seed, seconds=3.0, fs=8000):
+    """A STEREO int16 wav payload [n, 2] at 8 kHz for the command-line tests: channel 0 is a synthetic mixture scaled to
+    int16, channel 1 something else entirely (the script must pick channel 0, only_inference.py:70-75)."""
+    n = int(seconds * fs)
+    a = make_mixture(0, n, 5000 + seed, fs=fs)
+    b = make_mixture(1, n, 5000 + seed, fs=fs)
+    return np.stack([np.round(a * 30000.0), np.round(b * 12000.0)], axis=1).astype(np.int16)
+
+
 def make_mixtures(n, length, base_seed=1234, first_index=0):
     """[n, length] float32 batch of :func:`make_mixture` (mixture i uses seed base_seed+first_index+i)."""
     return np.stack([make_mixture(first_index + i, length, base_seed) for i in range(n)])

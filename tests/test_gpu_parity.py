@@ -18,8 +18,9 @@ from septfa_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-TOL = {0: dict(wav=5e-4, sisdr=60.0, vad=1e-3, logits=1e-2, est=2e-2),
-       7: dict(wav=2e-5, sisdr=100.0, vad=5e-5, logits=5e-4, est=5e-4)}
+# est: |e - ref| <= 2e-3 * (1 + |ref|): 2e-3 absolute on small values, 2e-3 relative on the large ones (|S| reaches ~40)
+TOL = {0: dict(wav=5e-4, sisdr=60.0, vad=1e-3, logits=1e-2, est=2e-3),
+       7: dict(wav=2e-5, sisdr=100.0, vad=5e-5, logits=5e-4, est=1e-4)}
 
 
 def check_decisions(p, p_ref, thr):
@@ -37,35 +38,77 @@ def smoothed_from(p, thr):
     return sm
 
 
+def gate_unsure(p_ref, thr):
+    """Frames whose SMOOTHED decision may legitimately differ between two implementations that agree on every raw
+    decision outside the 1e-3 band: s[t] depends on d[t-1] and d[t+1] (on d[t] at the two edges), model.py:449-451."""
+    near = np.abs(p_ref - np.float32(thr)) < 1e-3
+    unsure = near.copy()
+    if near.shape[-1] >= 3:
+        unsure[..., 1:-1] = near[..., :-2] | near[..., 2:]
+    return unsure
+
+
+def check_outputs(out, est, p, ref_out, ref_est, p_ref, kw, tol, stride=1, wav_scale=1.0):
+    """Waveforms and estimated STFTs against the reference with the VAD gate in force. Where the smoothed gate of a
+    frame differs - allowed only if a raw decision behind it lies inside the 1e-3 band - that frame (est) and the 512
+    samples it overlaps (waveform) are left out; EVERYTHING else is compared. Nothing is skipped silently."""
+    B, S, T = p.shape
+    frame_ok = np.ones((B, S, T), dtype=bool)
+    if kw and (kw.get("filter_signals_by_smo_vad") or kw.get("filter_signals_by_unsmo_vad")):
+        thr = kw["threshold_activated_vad"]
+        diff = smoothed_from(p, thr) != smoothed_from(p_ref, thr)
+        assert not (diff & ~gate_unsure(p_ref, thr)).any(), "smoothed gate differs outside the 1e-3 band"
+        frame_ok = ~diff
+    if est is not None and ref_est is not None:
+        err = np.abs(est - ref_est) / (1.0 + np.abs(ref_est))
+        err = np.where(frame_ok[:, :, None, :], err, 0.0)
+        assert err.max() <= tol["est"], ("est", err.max())
+    L = out.shape[-1]
+    samp_ok = np.ones(out.shape, dtype=bool)
+    for b, s_, t in zip(*np.nonzero(~frame_ok)):     # frame t overlaps output samples [256 (t-1), 256 (t+1))
+        samp_ok[b, s_, max(0, 256 * (t - 1)):min(L, 256 * (t + 1))] = False
+    o, r, ok = out[..., ::stride], ref_out, samp_ok[..., ::stride]
+    assert o.shape == r.shape
+    d = np.where(ok, o - r, 0.0)
+    assert np.abs(d).max() <= tol["wav"] * wav_scale, ("wav", np.abs(d).max())
+    assert sisdr_db(np.where(ok, o, 0.0), np.where(ok, r, 0.0)) >= tol["sisdr"]
+    return int((~frame_ok).sum())
+
+
 def run_golden(cuda_models, name, engine):
     g, meta = load_golden(name)
     tol = TOL[engine]
     m = cuda_models(meta["args"], meta["weight_seed"], engine)
     x = torch.from_numpy(synth.make_mixtures(meta["n"], meta["length"], meta["base_seed"])).cuda()
     st = meta["stride"]
+    # probabilities: ours from a plain forward, the reference's from the first case that returns them
+    p_ours = m(x, {})[1].cpu().numpy() if meta["args"]["final_vad"] else None
+    i_prob = next(i for i, kw in enumerate(meta["kws"]) if not (kw and kw.get("return_smoothed_vad")))
+    p_ref = g[f"kw{i_prob}_vad"]
+    if p_ours is not None:
+        assert np.abs(p_ours - p_ref).max() < tol["vad"], np.abs(p_ours - p_ref).max()
     for i, kw in enumerate(meta["kws"]):
         out, vad, est = m(x, dict(kw) if kw else {})
         assert m.last_launch_count > 70  # our kernels ran (no library / CPU path exists)
-        o = out.cpu().numpy()[..., ::st]
-        ref = g[f"kw{i}_out"]
-        assert o.shape == ref.shape
-        assert np.abs(o - ref).max() <= tol["wav"], (name, i, np.abs(o - ref).max())
-        assert sisdr_db(o, ref) >= tol["sisdr"]
         ref_vad = g[f"kw{i}_vad"]
         if ref_vad.size:
             v = vad.cpu().numpy()
             assert v.shape == ref_vad.shape
+            thr = kw["threshold_activated_vad"] if kw else 0.5
             if kw and kw.get("return_smoothed_vad"):
-                # smoothed decisions: must equal the smoothing of OUR decisions; ours vs the reference's are
-                # compared on the probabilities of the kw0 run below
+                # the returned smoothed decisions [B,2,1,T]: exactly the smoothing of our own probabilities, and equal to
+                # the REFERENCE's smoothed decisions on every frame no in-band raw decision can influence
                 assert set(np.unique(v)) <= {0.0, 1.0}
+                assert np.array_equal(v[:, :, 0], smoothed_from(p_ours, thr))
+                assert not ((v[:, :, 0] != ref_vad[:, :, 0]) & ~gate_unsure(p_ref, thr)).any()
             else:
                 assert np.abs(v - ref_vad).max() < tol["vad"], np.abs(v - ref_vad).max()
-                check_decisions(v, ref_vad, kw["threshold_activated_vad"] if kw else 0.5)
-        if f"kw{i}_est" in g:
-            e = est.cpu().numpy()
-            assert e.dtype == np.complex64 and e.shape == g[f"kw{i}_est"].shape
-            assert np.abs(e - g[f"kw{i}_est"]).max() < tol["est"]
+                check_decisions(v, ref_vad, thr)
+        ref_est = g[f"kw{i}_est"] if f"kw{i}_est" in g else None
+        e = est.cpu().numpy()
+        if ref_est is not None:
+            assert e.dtype == np.complex64 and e.shape == ref_est.shape
+        check_outputs(out.cpu().numpy(), e if ref_est is not None else None, p_ours, g[f"kw{i}_out"], ref_est, p_ref, kw, tol, stride=st)
         if i == 0 and "logits" in g:
             assert np.abs(m.masks_b.cpu().numpy() - g["logits"]).max() < tol["logits"]
             sp = m.spectrum.cpu().numpy()
@@ -115,7 +158,7 @@ def test_smoothed_vad_is_smoothing_of_own_decisions(cuda_models):
 @pytest.mark.parametrize("cfg_name", ["with", "without"])
 @pytest.mark.parametrize("B,L", [(1, 257), (3, 1000), (2, 4099), (1, 12800)])
 def test_against_oracle_seeded(cuda_models, cfg_name, B, L):
-    """Ragged / minimum lengths against the fp64 numpy oracle (the checker, never the product)."""
+    """Ragged / minimum lengths against the fp64 numpy oracle (the checker, never the product), VAD gate on."""
     from oracle import septfa_oracle as O
     args = synth.CONFIG_WITH_VAD if cfg_name == "with" else synth.CONFIG_WITHOUT_VAD
     seed = 21
@@ -126,17 +169,49 @@ def test_against_oracle_seeded(cuda_models, cfg_name, B, L):
     ref_out, ref_vad, ref_est, _ = O.forward(x, W, dict(kw))
     out, vad, est = m(torch.from_numpy(x).cuda(), dict(kw))
     v = vad.cpu().numpy()
+    p_ref = ref_vad.astype(np.float32)
     assert np.abs(v - ref_vad).max() < 1e-3
-    check_decisions(v, ref_vad.astype(np.float32), 0.5)
-    # compare waveforms where both gate the same way (a decision inside the 1e-3 band may flip a whole frame)
-    _, sm_ref = O.smooth_vad(ref_vad, 0.5)
-    same = np.array_equal(sm_ref.astype(np.float32), smoothed_from(v, 0.5))
-    if same:
-        # very short inputs end in the ragged istft tail (division by a small window envelope), so the
-        # absolute tolerance scales with the reference's peak
-        assert np.abs(out.cpu().numpy() - ref_out).max() <= 1e-3 * max(1.0, np.abs(ref_out).max())
-        assert sisdr_db(out.cpu().numpy(), ref_out) >= 60.0
-        assert np.abs(est.cpu().numpy() - ref_est).max() <= 2e-2
+    check_decisions(v, p_ref, 0.5)
+    # very short inputs end in the ragged istft tail (division by a small window envelope), so
+    # the absolute waveform tolerance scales with the reference's peak there
+    tol = dict(TOL[0], wav=1e-3)
+    check_outputs(out.cpu().numpy(), est.cpu().numpy(), v, ref_out.astype(np.float32), ref_est.astype(np.complex64), p_ref, kw, tol,
+                  wav_scale=max(1.0, float(np.abs(ref_out).max())))
+
+
+SWEEP_SHAPES = [(1, 257), (1, 32768), (2, 32767), (3, 33000), (9, 64000), (33, 20000), (130, 4000), (2, 300000), (1, 131072),
+                (5, 65536), (300, 16000)]
+
+
+@pytest.mark.parametrize("seed", [9, 21])
+@pytest.mark.parametrize("cfg_name", ["with", "without"])
+def test_shape_sweep_against_oracle(cuda_models, cfg_name, seed):
+    """The VAD parity gate on odd shapes (tiles straddling utterances, one tile per utterance, T below / above every
+    kernel-selection threshold, ragged istft tails), two weight seeds, both configurations, default precision mode,
+    against the fp64 oracle: |dp| < 1e-3 on every frame (north_star band) - measured worst case 4e-4 - and the decision
+    rule. Batches repeat min(B, 8) distinct utterances; every copy is checked against its oracle result."""
+    from oracle import septfa_oracle as O
+    args = synth.CONFIG_WITH_VAD if cfg_name == "with" else synth.CONFIG_WITHOUT_VAD
+    m = cuda_models(args, seed, 0)
+    W = O.OracleWeights(synth.make_state_dict_numpy(args, seed), args, np.float64)
+    worst = 0.0
+    for B, L in SWEEP_SHAPES:
+        nd = min(B, 8)
+        xd = synth.make_mixtures(nd, L, 4242)
+        ref_out, ref_vad, _, _ = O.forward(xd, W, {})
+        x = torch.from_numpy(np.tile(xd, ((B + nd - 1) // nd, 1))[:B]).cuda()
+        out, vad, _ = m(x, {})
+        v, o = vad.cpu().numpy(), out.cpu().numpy()
+        assert np.isfinite(o).all()
+        idx = np.arange(B) % nd
+        dv = np.abs(v - ref_vad[idx]).max()
+        worst = max(worst, dv)
+        assert dv < 1e-3, (cfg_name, seed, B, L, dv)
+        check_decisions(v, ref_vad[idx].astype(np.float32), 0.5)
+        tail = (L % 256) if (L % 256) > 200 else 0   # samples only the last frame covers: envelope -> ~1e-8 there
+        assert np.abs(o[..., :L - tail] - ref_out[idx][..., :L - tail]).max() <= 5e-4, (cfg_name, seed, B, L)
+        assert sisdr_db(o[:nd, :, :L - tail], ref_out[..., :L - tail]) >= 60.0
+    assert worst < 7.5e-4, worst      # margin pin: the tolerance band is 1e-3
 
 
 def test_engines_agree(cuda_models):
@@ -163,6 +238,7 @@ def test_fused_residual_kernel_equals_streaming_kernels(cuda_models, cfg_name, B
     kw = dict(synth.DEFAULT_INFERENCE_KW) if cfg_name == "with" else {}
     x = torch.from_numpy(synth.make_mixtures(B, L, 777)).cuda()
     try:
+        m.set_option("precision", 1)     # the fused kernel reads fp16 accumulators: the single-pass ("fast") mode
         m.set_option("fused_resid", 0)
         o0, v0, _ = m(x, kw)
         n0 = m.last_launch_count
@@ -172,6 +248,7 @@ def test_fused_residual_kernel_equals_streaming_kernels(cuda_models, cfg_name, B
         o2, v2, _ = m(x, kw)
     finally:
         m.set_option("fused_resid", 1)
+        m.set_option("precision", 0)
     assert n1 < n0, (n0, n1)            # the fused kernel really replaced three launches per block
     assert (o1 - o0).abs().max().item() < 5e-4
     assert sisdr_db(o1.cpu().numpy(), o0.cpu().numpy()) > 60
@@ -386,27 +463,34 @@ def test_pit_kernel(cuda_models):
     assert abs(loss.item() - ref.item()) < 1e-5
 
 
-def test_full_size_batch_properties(cuda_models):
-    """cfg2 size (256 x 4 s): golden utterance embedded in the batch reproduces the golden output,
-    outputs are finite, gated frames are exactly zero."""
+def test_full_size_batch_against_oracle(cuda_models):
+    """cfg2 size (256 x 4 s, VAD gate on): the batch holds 32 distinct utterances (8 copies each, interleaved so that
+    copies sit in different tiles); EVERY one of the 256 results is compared with the oracle's result for its
+    utterance - probabilities, decisions, gated waveforms. The golden utterance of cfg1 is one of the 32."""
+    from oracle import septfa_oracle as O
     g, meta = load_golden("cfg1_with_vad_4s")
     m = cuda_models(meta["args"], meta["weight_seed"], 0)
-    B = 256
-    x = np.tile(synth.make_mixtures(8, 64000, 9000), (B // 8, 1))
-    x[137] = synth.make_mixtures(1, 64000, meta["base_seed"])[0]
+    B, nd, L = 256, 32, 64000
+    xd = synth.make_mixtures(nd, L, 9000)
+    xd[13] = synth.make_mixtures(1, L, meta["base_seed"])[0]
     kw = dict(meta["kws"][0])
+    W = O.OracleWeights(synth.make_state_dict_numpy(meta["args"], meta["weight_seed"]), meta["args"], np.float32)
+    ref_out, ref_vad, _, _ = O.forward(xd, W, dict(kw))
+    assert np.abs(ref_out[13] - g["kw0_out"][0]).max() < 2e-5 and np.abs(ref_vad[13] - g["kw0_vad"][0]).max() < 2e-5   # oracle == reference
+    idx = np.arange(B) % nd
     m.materialize.update(estimated_stfts=False, mask_per_speaker=False, spectrum=False, masks_b=False)
     try:
-        out, vad, est = m(torch.from_numpy(x).cuda(), kw)
+        out, vad, est = m(torch.from_numpy(xd[idx]).cuda(), kw)
     finally:
         m.materialize.update(estimated_stfts=True, mask_per_speaker=True, spectrum=True, masks_b=True)
     assert est is None
-    assert torch.isfinite(out).all() and torch.isfinite(vad).all()
-    o = out[137].cpu().numpy()
-    assert np.abs(o - g["kw0_out"][0]).max() <= 5e-4
-    assert np.abs(vad[137].cpu().numpy() - g["kw0_vad"][0]).max() < 1e-3
-    # periodic batch -> identical results for identical utterances (up to the order of atomic sums)
-    assert (out[0] - out[8]).abs().max().item() < 5e-4, (out[0] - out[8]).abs().max().item()
+    o, v = out.cpu().numpy(), vad.cpu().numpy()
+    assert np.isfinite(o).all() and np.isfinite(v).all()
+    assert np.abs(v - ref_vad[idx]).max() < 1e-3, np.abs(v - ref_vad[idx]).max()
+    check_decisions(v, ref_vad[idx], kw["threshold_activated_vad"])
+    skipped = check_outputs(o, None, v, ref_out[idx], None, ref_vad[idx], kw, TOL[0])
+    assert skipped <= 4, skipped      # frames whose gate legitimately differs (in-band decisions): a handful at most
+    assert np.abs(o[13] - g["kw0_out"][0]).max() <= 5e-4
 
 
 def test_online_many_streams_equals_per_stream_runs(cuda_models):
@@ -426,6 +510,157 @@ def test_online_many_streams_equals_per_stream_runs(cuda_models):
         # same permutation decisions, waveforms equal up to the fp16 batch-placement noise
         assert np.array_equal(o.last_perms.cpu().numpy()[:, 0], perms_batch[:, s])
         assert (single[0] - batch[s]).abs().max().item() < 5e-4
+
+
+def test_online_1024_streams_equal_per_stream_runs_and_oracle(cuda_models):
+    """cfg3 size: 1024 concurrent streams (16 distinct mixtures x 64 copies) driven as ONE batch for 3 hops. Every
+    stream's permutation decisions and emitted audio must equal those of its mixture driven in a 16-stream batch, and
+    two of the distinct streams are checked against the oracle's calc_online (the reference driver's semantics)."""
+    from oracle import septfa_oracle as O
+    from septfa_b200.online import OnlineSaving
+    args = synth.CONFIG_WITH_VAD
+    m = cuda_models(args, 41, 0)
+    kw = dict(synth.DEFAULT_INFERENCE_KW, filter_signals_by_smo_vad=True)
+    xd = synth.make_mixtures(16, 80000, 700)                       # 5 s -> 3 hops
+    o = OnlineSaving(m, "/tmp/septfa_online_test1024")
+    o.num_save_samples = 0
+    small = o.calc_online(torch.from_numpy(xd).cuda(), "n", 0, dict(kw)).cpu().numpy()
+    perms_small = o.last_perms.cpu().numpy()                       # [hops, 16, 2]
+    idx = np.arange(1024) % 16
+    big = o.calc_online(torch.from_numpy(xd[idx]).cuda(), "n", 0, dict(kw)).cpu().numpy()
+    perms_big = o.last_perms.cpu().numpy()
+    assert big.shape == (1024, 2, 48000) and perms_big.shape == (3, 1024, 2)
+    assert np.array_equal(perms_big, perms_small[:, idx])
+    assert np.abs(big - small[idx]).max() < 5e-4, np.abs(big - small[idx]).max()
+    W = O.OracleWeights(synth.make_state_dict_numpy(args, 41), args, np.float32)
+    ref_sig, ref_perms = O.calc_online(xd[[0, 7]], W, dict(kw))
+    assert np.array_equal(ref_perms, perms_small[:, [0, 7]])
+    assert np.abs(small[[0, 7]] - ref_sig).max() < 1e-3, np.abs(small[[0, 7]] - ref_sig).max()
+
+
+def test_precision_modes(cuda_models):
+    """Option "precision": the split-precision (three-pass) contractions reproduce the oracle to fp32 level, the
+    single-pass mode to the fp16 level; AUTO picks the split for config_without_vad (its stream is never re-normalised)."""
+    from oracle import septfa_oracle as O
+    x = synth.make_mixtures(2, 33000, 4242)
+    for args, auto_is_accurate in ((synth.CONFIG_WITH_VAD, False), (synth.CONFIG_WITHOUT_VAD, True)):
+        m = cuda_models(args, 9, 0)
+        W = O.OracleWeights(synth.make_state_dict_numpy(args, 9), args, np.float64)
+        _, ref_vad, _, _ = O.forward(x, W, {})
+        err = {}
+        try:
+            for prec in (0, 1, 2):
+                m.set_option("precision", prec)
+                err[prec] = float(np.abs(m(torch.from_numpy(x).cuda(), {})[1].cpu().numpy() - ref_vad).max())
+        finally:
+            m.set_option("precision", 0)
+        assert err[2] < 1e-4 and err[1] < 2e-3, err
+        assert (err[0] == err[2]) if auto_is_accurate else (err[0] == err[1]), err
+    with pytest.raises(Exception):
+        m.set_option("precision", 3)
+        m(torch.from_numpy(x).cuda(), {})
+    m.set_option("precision", 0)
+
+
+@pytest.mark.parametrize("B,L", [(3, 64000), (2, 40000), (1, 200000), (5, 33000)])
+def test_tensor_core_depthwise_kernel_equals_cuda_core_producer(cuda_models, B, L):
+    """dconv_mma.cu (depthwise conv as block-diagonal tcgen05 GEMMs on the plane layout of p, edge rows corrected) against
+    gemm_tc.cu MODE 1 (depthwise conv on the CUDA cores) on the same buffers: same network up to the fp16 rounding of
+    the folded taps; run-to-run bit-reproducible; and both within the band of the oracle."""
+    from oracle import septfa_oracle as O
+    args = synth.CONFIG_WITH_VAD
+    m = cuda_models(args, 34, 0)
+    xh = synth.make_mixtures(B, L, 779)
+    x = torch.from_numpy(xh).cuda()
+    try:
+        m.set_option("dconv_mma", 0)
+        o0, v0, _ = m(x, {})
+        m.set_option("dconv_mma", 1)
+        o1, v1, _ = m(x, {})
+        o2, v2, _ = m(x, {})
+    finally:
+        m.set_option("dconv_mma", 1)
+    assert (o1 - o0).abs().max().item() < 5e-4
+    assert (v1 - v0).abs().max().item() < 1e-3
+    assert torch.equal(o1, o2) and torch.equal(v1, v2)
+    W = O.OracleWeights(synth.make_state_dict_numpy(args, 34), args, np.float64)
+    _, ref_vad, _, _ = O.forward(xh, W, {})
+    assert np.abs(v1.cpu().numpy() - ref_vad).max() < 1e-3
+
+
+def test_host_16bit_formats(cuda_models):
+    """septfa_forward_host_submit_fmt: int16 PCM input (only_inference.py:68-81 on the device: astype float32 + min-max
+    normalisation, bit-identical to numpy) and fp16 output (save_audio's `-ps 16` cast, utlis_inference.py:30-32)."""
+    m = cuda_models(synth.CONFIG_WITH_VAD, 31, 0)
+    kw = dict(synth.DEFAULT_INFERENCE_KW, filter_signals_by_smo_vad=True)
+    rng = np.random.default_rng(5)
+    pcm = np.clip(np.round(synth.make_mixtures(3, 20000, 910) * 20000.0 + rng.integers(-3, 4, (3, 20000))), -32768, 32767).astype(np.int16)
+    audio = pcm.astype(np.float32)                                                     # only_inference.py:69
+    norm = np.stack([1.8 * (a - a.min()) / (a.max() - a.min()) - 0.9 for a in audio])  # only_inference.py:81
+    ref_out, ref_vad, _ = m(torch.from_numpy(norm.astype(np.float32)).cuda(), kw)
+    f = m.forward_host_submit(torch.from_numpy(pcm), kw, slot=0, out_dtype=torch.float16)
+    out16, vad = f.result()
+    assert out16.dtype == torch.float16 and out16.shape == (3, 2, 20000) and not out16.is_cuda
+    # same device arithmetic on bit-identical inputs -> identical fp32 waveforms; the output is their fp16 rounding
+    assert torch.equal(out16, ref_out.cpu().to(torch.float16))
+    assert torch.equal(vad, ref_vad.cpu())
+    # fp32 in / fp16 out and int16 in / fp32 out
+    o2, _ = m.forward_host_submit(torch.from_numpy(norm.astype(np.float32)), kw, slot=1, out_dtype=torch.float16).result()
+    assert torch.equal(o2, out16)
+    o3, _ = m.forward_host_submit(torch.from_numpy(pcm), kw, slot=0).result()
+    assert o3.dtype == torch.float32 and torch.equal(o3, ref_out.cpu())
+
+
+def test_utterance_longer_than_200_s(cuda_models):
+    """A 210 s file (T = 13126 frames): every kernel's shared memory is independent of T (the streaming gate kernel used
+    to keep its per-frame means in shared memory and failed beyond ~190 s). Checked against the oracle."""
+    from oracle import septfa_oracle as O
+    args = synth.CONFIG_WITHOUT_VAD
+    m = cuda_models(args, 4, 0)
+    L = 210 * 16000
+    x = np.tile(synth.make_mixtures(1, 160000, 31), (1, 21))[:, :L].copy()
+    W = O.OracleWeights(synth.make_state_dict_numpy(args, 4), args, np.float32)
+    ref_out, ref_vad, _, _ = O.forward(x, W, {})
+    m.materialize.update(estimated_stfts=False, mask_per_speaker=False, spectrum=False, masks_b=False)
+    try:
+        out, vad, _ = m(torch.from_numpy(x).cuda(), {})
+    finally:
+        m.materialize.update(estimated_stfts=True, mask_per_speaker=True, spectrum=True, masks_b=True)
+    assert np.abs(vad.cpu().numpy() - ref_vad).max() < 1e-3
+    assert np.abs(out.cpu().numpy() - ref_out).max() <= 5e-4
+    from septfa_b200.lib import SeptfaError
+    with pytest.raises(SeptfaError):
+        m(torch.zeros(40000, 300).cuda())          # B above the per-call limit is rejected with a clear message
+
+
+def test_unusual_weights_against_oracle(cuda_models):
+    """Weights outside the benign random-init ranges: PReLU slopes > 1 and < 0 (the min-form / general PReLU code paths),
+    a reg1 gamma that is (nearly) zero (the tensor-core depthwise kernel declines, the CUDA-core producer clamps), large
+    weight_g. Checked against the fp64 oracle; probabilities stay within the band."""
+    from oracle import septfa_oracle as O
+    from conftest import build_cuda_model
+    args = synth.CONFIG_WITH_VAD
+    sd = synth.make_state_dict(args, 55)
+    for i in range(24):
+        sd[f"TCN.TCN.{i}.nonlinearity1.weight"].fill_(1.3 if i % 3 == 0 else (-0.2 if i % 3 == 1 else 0.25))
+        sd[f"TCN.TCN.{i}.nonlinearity2.weight"].fill_(1.7 if i % 3 == 1 else (-0.1 if i % 3 == 2 else 0.3))
+    sd["TCN.TCN.5.reg1.weight"][17] = 0.0
+    sd["TCN.TCN.9.reg1.weight"][3] = 1e-6
+    sd["TCN.TCN.2.res_out.weight_g"] *= 6.0
+    sd["TCN.TCN.11.conv1d.weight_g"] *= 5.0
+    import contextlib, io
+    from septfa_b200.model import SeparationModel
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = SeparationModel(**args)
+    m.load_state_dict(sd, strict=True)
+    m.eval().cuda()
+    x = synth.make_mixtures(3, 40000, 56)
+    W = O.OracleWeights({k: v.numpy() for k, v in sd.items()}, args, np.float64)
+    ref_out, ref_vad, _, _ = O.forward(x, W, {})
+    out, vad, _ = m(torch.from_numpy(x).cuda(), {})
+    assert torch.isfinite(out).all()
+    assert np.abs(vad.cpu().numpy() - ref_vad).max() < 1e-3, np.abs(vad.cpu().numpy() - ref_vad).max()
+    assert sisdr_db(out.cpu().numpy(), ref_out) >= 60.0
 
 
 def test_known_targets_driver_runs(cuda_models):
