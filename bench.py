@@ -496,19 +496,19 @@ def main():
         n_mine = shard_range(total, rank, world)[1] - shard_range(total, rank, world)[0]
         nb = n_mine // B
         xs = [x_host, x_host.clone().pin_memory()]
-        for _ in model.forward_host_stream((xs[i & 1] for i in range(2)), kw, device=local_rank):
+        for _ in model.forward_host_stream((xs[i & 1] for i in range(4)), kw, device=local_rank, reuse_outputs=True):
             pass
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         n_out = 0
-        for o, v in model.forward_host_stream((xs[i & 1] for i in range(nb)), kw, device=local_rank):
+        for o, v in model.forward_host_stream((xs[i & 1] for i in range(nb)), kw, device=local_rank, reuse_outputs=True):
             n_out += o.shape[0]
         t5 = gather_max_time(time.perf_counter() - t0)
         assert n_out == nb * B
         cfg5 = {"workload": f"{total} x 4 s mixtures over {world} GPU(s) in host batches of {B} (BASELINE.json configs[4])",
                 "value": world * nb * B * L / FS / t5, "unit": "audio-s/s", "seconds": t5,
-                "api": "SeparationModel.forward_host_stream (float32 host input and output per batch)"}
+                "api": "SeparationModel.forward_host_stream(reuse_outputs=True): float32 pinned host input and output per batch"}
 
     # ---- BASELINE.json configs[3]: 60 s mixtures, config_without_vad (stresses the per-utterance global statistics)
     cfg4 = None
@@ -540,6 +540,36 @@ def main():
     eager = None
     if not a.no_extras and rank == 0:
         eager = torch_eager_b200(a, dev, x_dev)
+
+    # ---- small-request latency: one 4 s mixture, resident input, per-call CUDA events;
+    # the eager launch sequence (~80 kernels) against its CUDA-graph replay (SeparationModel.graphed)
+    small = None
+    if not a.no_extras and rank == 0:
+        def lat(fn, n=200):
+            for _ in range(10):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(n):
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                fn()
+                s1.record()
+                s1.synchronize()
+                ts.append(s0.elapsed_time(s1))
+            ts.sort()
+            return {"p50_ms": ts[len(ts) // 2], "p99_ms": ts[min(len(ts) - 1, int(0.99 * len(ts)))]}
+        model.materialize.update(estimated_stfts=False, mask_per_speaker=False, spectrum=False, masks_b=False)
+        x1 = x_dev[:1].contiguous()
+        small = {"workload": "one 4 s mixture per request, input resident, VAD gate on", "eager": lat(lambda: model(x1, kw))}
+        try:
+            g1 = model.graphed(1, L, kw)
+            g1.x.copy_(x1)
+            small["cuda_graph"] = dict(lat(g1.replay), nodes=g1.num_nodes)
+        except Exception as e:  # noqa: BLE001
+            small["cuda_graph"] = {"unavailable": f"{type(e).__name__}: {e}"}
+        if not a.lean:
+            model.materialize.update(estimated_stfts=True, mask_per_speaker=True, spectrum=True, masks_b=True)
 
     if rank == 0:
         audio_s = world * B * L / FS * a.steps
@@ -606,6 +636,8 @@ def main():
             line["cfg5"] = cfg5
         if eager is not None:
             line["torch_eager_b200"] = eager
+        if small is not None:
+            line["small_request_latency"] = small
         if world == 1 and not a.no_cpu_baseline:
             ref = ReferenceCPU(L, a.ref_chunk)
             xs = ref.mixtures(a.cpu_sample)

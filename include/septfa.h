@@ -157,6 +157,19 @@ int septfa_forward_host_wait(septfa_handle* h, int slot);
 int septfa_forward_host_submit_fmt(septfa_handle* h, int slot, const void* x_host, int x_fmt, int B, int64_t L,
                                    const septfa_infer_kw* kw, void* out_wav_host, int out_fmt, float* out_vad_host);
 
+/* ---- small-request serving: the forward as a CUDA graph ---------------------------
+ * A forward of one short mixture is ~80 kernels of a few microseconds each: launch-bound (0.9 ms for one 4 s mixture).
+ * septfa_graph_capture records septfa_forward for one (B, L, kw) on the caller's STATIC device buffers (x, out_wav,
+ * out_vad, workspace: same pointers at every replay) into an executable CUDA graph; septfa_graph_launch replays it on a
+ * stream (the caller refreshes x before, reads out_wav / out_vad after, stream-ordered). One graph per shape bucket.
+ * The optional exports (est_stft / mask / spectrum / logits) are not part of the graph. */
+typedef struct septfa_graph septfa_graph;
+int septfa_graph_capture(septfa_handle* h, const float* x, int B, int64_t L, const septfa_infer_kw* kw, float* out_wav,
+                         float* out_vad, void* workspace, size_t workspace_bytes, septfa_graph** out);
+int septfa_graph_launch(septfa_graph* g, void* stream);
+int septfa_graph_num_nodes(const septfa_graph* g);
+void septfa_graph_destroy(septfa_graph* g);
+
 /* Number of GPU kernels launched by the last forward / online step on this handle. */
 int septfa_last_launch_count(const septfa_handle* h);
 

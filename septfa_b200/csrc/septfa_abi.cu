@@ -90,6 +90,13 @@ struct septfa_handle {
   int prof_launches[SEPTFA_PROF_NCAT] = {0};
 };
 
+struct septfa_graph {
+  septfa_handle* h = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int nodes = 0, kernels = 0;
+};
+
 struct septfa_online {
   septfa_handle* h = nullptr;
   int S = 0;
@@ -1062,6 +1069,65 @@ int septfa_forward_host_wait(septfa_handle* h, int slot) {
 }
 
 int septfa_last_launch_count(const septfa_handle* h) { return h ? h->last_launches : 0; }
+
+// ------------------------------------------------------------------------------------------ CUDA-graph replay
+int septfa_graph_capture(septfa_handle* h, const float* x, int B, int64_t L, const septfa_infer_kw* kw, float* out_wav,
+                         float* out_vad, void* workspace, size_t workspace_bytes, septfa_graph** out) {
+  if (!out) return SEPTFA_E_INVALID;
+  *out = nullptr;
+  if (int rc = check_forward_args(h, B, L)) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  // one eager forward first: it fills the lazily initialised caches (occupancy queries) and validates the arguments
+  cudaStream_t cs = nullptr;
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  const int saved_profile = h->profile, saved_pdl = h->lctx.use_pdl;
+  h->profile = 0;
+  int rc = septfa_forward(h, x, B, L, kw, out_wav, out_vad, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, cs);
+  if (rc == 0 && cudaStreamSynchronize(cs) != cudaSuccess) rc = fail(h, SEPTFA_E_CUDA, "eager forward before the capture failed");
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  // programmatic dependent launches are captured as programmatic edges; if this driver refuses them inside a capture,
+  // the chain is captured with plain stream order instead
+  for (int attempt = 0; rc == 0 && attempt < 2 && exec == nullptr; ++attempt) {
+    h->lctx.use_pdl = attempt == 0 ? saved_pdl : 0;
+    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) { rc = fail(h, SEPTFA_E_CUDA, "cudaStreamBeginCapture failed"); break; }
+    const int frc = septfa_forward(h, x, B, L, kw, out_wav, out_vad, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, cs);
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (frc == 0 && ce == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) break;
+    cudaGetLastError();
+    if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+    exec = nullptr;
+    if (attempt == 1) rc = fail(h, SEPTFA_E_CUDA, "the forward could not be captured into a CUDA graph");
+  }
+  h->profile = saved_profile;
+  h->lctx.use_pdl = saved_pdl;
+  cudaStreamDestroy(cs);
+  if (rc != 0 || exec == nullptr) return rc != 0 ? rc : SEPTFA_E_CUDA;
+  auto* g = new septfa_graph();
+  g->h = h; g->graph = graph; g->exec = exec;
+  size_t n = 0;
+  cudaGraphGetNodes(graph, nullptr, &n);
+  g->nodes = (int)n;
+  g->kernels = h->last_launches;
+  *out = g;
+  return 0;
+}
+
+int septfa_graph_launch(septfa_graph* g, void* stream) {
+  if (!g) return SEPTFA_E_INVALID;
+  CUDA_TRY(g->h, cudaGraphLaunch(g->exec, reinterpret_cast<cudaStream_t>(stream)));
+  g->h->last_launches = g->kernels;
+  return 0;
+}
+
+int septfa_graph_num_nodes(const septfa_graph* g) { return g ? g->nodes : 0; }
+
+void septfa_graph_destroy(septfa_graph* g) {
+  if (!g) return;
+  cudaGraphExecDestroy(g->exec);
+  cudaGraphDestroy(g->graph);
+  delete g;
+}
 
 // ------------------------------------------------------------------------------------------ online
 int septfa_online_create(septfa_handle* h, int S, septfa_online** out) {

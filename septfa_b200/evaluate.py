@@ -12,19 +12,30 @@ from __future__ import annotations
 
 import torch
 
-from .pit import PITLossWrapper, calc_sisdr, reorder_source_mse
+from .pit import PITLossWrapper, calc_sisdr, reorder_source_mse, sisdr_moments
 
 
 def pairwise_neg_sisdr(est_targets, targets):
     """``PairwiseNegSDR('sisdr')`` (model/sdr.py:48-85): ``out[b, i, j] = -SI-SDR(est_i, target_j)`` in dB, zero-mean.
-    [B, n_src, n] x [B, n_src, n] -> [B, n_src, n_src]. (The reference adds its EPS = 1e-8 in slightly different
-    places than calc_sisdr; the two agree to ~1e-4 dB on signals of audio scale.)"""
+    [B, n_src, n] x [B, n_src, n] -> [B, n_src, n_src], CUDA tensors."""
     if targets.shape != est_targets.shape or targets.ndim != 3:
         raise TypeError(f"Inputs must be of shape [batch, n_src, time], got {targets.size()} and {est_targets.size()} instead")
     B, n_src, n = targets.shape
-    est = est_targets.unsqueeze(2).expand(B, n_src, n_src, n)     # [B, i, j, n] = est_i
-    tgt = targets.unsqueeze(1).expand(B, n_src, n_src, n)         # [B, i, j, n] = target_j
-    return -calc_sisdr(est.reshape(-1, n), tgt.reshape(-1, n), zero_mean=True).view(B, n_src, n_src)
+    est = est_targets.detach().float().unsqueeze(2).expand(B, n_src, n_src, n).reshape(-1, n).contiguous()   # est_i
+    tgt = targets.detach().float().unsqueeze(1).expand(B, n_src, n_src, n).reshape(-1, n).contiguous()       # target_j
+    # the reference's expression (EPS = 1e-8 added to the target energy, to the noise energy and inside the log: pairs
+    # that do not correlate saturate at +80 dB) evaluated from the five moments of one device pass
+    _, mom = sisdr_moments(est, tgt)
+    sp, st, spt, stt, spp = mom.unbind(dim=1)
+    eps = 1e-8
+    dot = spt - sp * st / n
+    tt = stt - st * st / n
+    pp = spp - sp * sp / n
+    te = tt + eps
+    proj2 = dot * dot * tt / (te * te)
+    noise2 = (pp - 2.0 * dot * dot / te + proj2).clamp_min(0.0)
+    sdr = proj2 / (noise2 + eps)
+    return (-10.0 * torch.log10(sdr + eps)).to(est_targets.dtype).view(B, n_src, n_src)
 
 
 def pit_sisdr(est_targets, targets):

@@ -80,13 +80,21 @@ def save_audio(mix_waves, separated_signals, save_path, bit16):
         write(os.path.join(save_path, name), 16000, a)
 
 
-def plot_spectrogram(masks, title, save_path):
-    """Our_utils/utlis_inference.py:9-22; skipped (with a note) when matplotlib is unavailable."""
+def _pyplot():
+    """matplotlib.pyplot with the Agg backend, or None when matplotlib is absent (or only a stub module is importable)."""
     try:
         import matplotlib
         matplotlib.use("Agg")
         import matplotlib.pyplot as plt
-    except ImportError:
+        return plt if hasattr(plt, "subplots") else None
+    except (ImportError, AttributeError):
+        return None
+
+
+def plot_spectrogram(masks, title, save_path):
+    """Our_utils/utlis_inference.py:9-22; skipped (with a note) when matplotlib is unavailable."""
+    plt = _pyplot()
+    if plt is None:
         print("matplotlib not available: mask PNGs not written")
         return
     masks = masks.cpu()
@@ -109,12 +117,7 @@ def save_vad(vad_output, save_path):
     vad_output = vad_output.detach().cpu()
     if vad_output.ndim == 4:            # [B, 2, 1, T] when return_smoothed_vad
         vad_output = vad_output[:, :, 0]
-    try:
-        import matplotlib
-        matplotlib.use("Agg")
-        import matplotlib.pyplot as plt
-    except ImportError:
-        plt = None
+    plt = _pyplot()
     for spk in range(vad_output.shape[1]):
         est_vad = torch.where(vad_output[0, spk] >= 0.5, 1, 0)
         if plt is None:
@@ -158,9 +161,9 @@ def separate_files(model, paths, save_dir, inference_kw=None, precision_save=32,
     for _, items in sorted(groups.items()):
         chunks = [items[i:i + batch] for i in range(0, len(items), batch)]
         batches = (torch.from_numpy(np.stack([a for _, a in ch])) for ch in chunks)
-        for ch, (out, vad) in zip(chunks, model.forward_host_stream(batches, kw, device=device, out_dtype=out_dtype)):
+        for ch, (out, vad) in zip(chunks, model.forward_host_stream(batches, kw, device=device, out_dtype=out_dtype, reuse_outputs=True)):
             for i, (pth, _) in enumerate(ch):
-                emit(pth, out[i].clone(), vad[i].clone() if torch.is_tensor(vad) else None)
+                emit(pth, out[i], vad[i].clone() if torch.is_tensor(vad) else None)
     for pth in singles:
         x = read_mixture(pth).to(torch.device("cuda", device))
         with torch.no_grad():

@@ -84,6 +84,11 @@ _PROTOS = {
     "septfa_forward_host_submit_fmt": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64,
                                                  C.POINTER(InferKw), C.c_void_p, C.c_int, C.c_void_p]),
     "septfa_last_launch_count": (C.c_int, [C.c_void_p]),
+    "septfa_graph_capture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.POINTER(InferKw), C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "septfa_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "septfa_graph_num_nodes": (C.c_int, [C.c_void_p]),
+    "septfa_graph_destroy": (None, [C.c_void_p]),
     "septfa_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int, C.c_int]),
     "septfa_online_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "septfa_online_destroy": (None, [C.c_void_p]),

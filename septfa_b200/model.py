@@ -201,6 +201,14 @@ class SeparationModel(nn.Module):
             output_vad = vad
         return out, output_vad, self.estimated_stfts
 
+    def graphed(self, B, L, inference_kw={}, device=None):
+        """The forward for one (B, L, inference_kw) as a replayable CUDA graph (septfa_graph_capture): for serving many
+        small requests, where ~80 kernel launches of a few microseconds each dominate (launch-bound). Returns a
+        :class:`GraphedForward`; ``g(x)`` copies ``x [B, L]`` into the graph's static input, replays the graph on the
+        current stream and returns ``(out_separation, output_vad)`` - static tensors, overwritten by the next call."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        return GraphedForward(self, int(B), int(L), inference_kw, dev)
+
     def forward_host(self, x_host: torch.Tensor, inference_kw={}, device=0, pin_outputs=True):
         """End-to-end call with HOST tensors: septfa_forward_host does the H2D copy, the forward and
         the D2H copy of (out_separation, output_vad) through pinned staging buffers."""
@@ -291,17 +299,81 @@ class SeparationModel(nn.Module):
             self.last_launch_count = h.lib.septfa_last_launch_count(h.ptr)
         return HostBatch(self, h, dev, int(slot), x_host, out, vad if self.final_vad else None, kw)
 
-    def forward_host_stream(self, batches, inference_kw={}, device=0, out_dtype=torch.float32):
+    def forward_host_stream(self, batches, inference_kw={}, device=0, out_dtype=torch.float32, reuse_outputs=False):
         """Generator over an iterable of host batches ``[B, L]`` (the loop of only_inference.py:80-100 over a data
         loader): yields ``(out_separation, output_vad)`` per batch, in order, keeping two batches in flight. Batches
-        may be float32 (normalised) or int16 PCM; ``out_dtype`` as in :meth:`forward_host_submit`."""
+        may be float32 (normalised) or int16 PCM; ``out_dtype`` as in :meth:`forward_host_submit`.
+        ``reuse_outputs=True`` recycles three sets of pinned result buffers instead of page-locking fresh memory for
+        every batch (cudaHostAlloc of 130 MB costs more than the batch's forward): a yielded result then stays valid
+        until TWO further results have been yielded - enough for a loop that writes each result out before asking for
+        the next."""
         pending = []
+        pool = {}
+
+        def buffers(i, xb):
+            if not reuse_outputs:
+                return None, None
+            B, L = xb.shape
+            key = (B, L, i % 3)
+            if key not in pool:
+                pool[key] = (torch.empty((B, self.num_spk, L), dtype=out_dtype, pin_memory=True),
+                             torch.empty((B, self.num_spk, _lib.num_frames(L)), dtype=torch.float32, pin_memory=True)
+                             if self.final_vad else None)
+            return pool[key]
+
         for i, xb in enumerate(batches):
             if len(pending) == 2:
                 yield pending.pop(0).result()
-            pending.append(self.forward_host_submit(xb, inference_kw, device, slot=i & 1, out_dtype=out_dtype))
+            o, v = buffers(i, xb)
+            pending.append(self.forward_host_submit(xb, inference_kw, device, slot=i & 1, out=o, vad=v, out_dtype=out_dtype))
         while pending:
             yield pending.pop(0).result()
+
+
+class GraphedForward:
+    """A captured forward (see :meth:`SeparationModel.graphed`). Owns its static device buffers."""
+
+    def __init__(self, model, B, L, inference_kw, dev):
+        self._m, self.B, self.L, self._dev = model, B, L, dev
+        self._kw = _lib.InferKw.from_dict(inference_kw) if (inference_kw and model.final_vad) else None
+        T = _lib.num_frames(L)
+        with torch.cuda.device(dev):
+            h = model._handle(dev)
+            self._h = h
+            need = h.lib.septfa_workspace_bytes(h.ptr, B, L)
+            if need == 0:
+                raise _lib.SeptfaError(f"unsupported input shape B={B}, L={L} (need L >= 257)")
+            self.x = torch.zeros((B, L), dtype=torch.float32, device=dev)
+            self.out = torch.empty((B, model.num_spk, L), dtype=torch.float32, device=dev)
+            self.vad = torch.empty((B, model.num_spk, T), dtype=torch.float32, device=dev)
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            self._g = C.c_void_p()
+            torch.cuda.synchronize(dev)
+            rc = h.lib.septfa_graph_capture(h.ptr, C.c_void_p(self.x.data_ptr()), B, L,
+                                            C.byref(self._kw) if self._kw is not None else None,
+                                            C.c_void_p(self.out.data_ptr()), C.c_void_p(self.vad.data_ptr()),
+                                            C.c_void_p(self._ws.data_ptr()), self._ws.numel(), C.byref(self._g))
+            _lib.check(h.ptr, rc)
+            self.num_nodes = h.lib.septfa_graph_num_nodes(self._g)
+
+    def replay(self):
+        """Replay on the current stream with whatever ``self.x`` holds."""
+        with torch.cuda.device(self._dev):
+            _lib.check(self._h.ptr, self._h.lib.septfa_graph_launch(self._g, C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)))
+        return self._m._host_result(self.out, self.vad, self._kw)
+
+    def __call__(self, x):
+        assert tuple(x.shape) == (self.B, self.L)
+        self.x.copy_(x, non_blocking=True)
+        return self.replay()
+
+    def __del__(self):
+        try:
+            if self._g:
+                self._h.lib.septfa_graph_destroy(self._g)
+                self._g = None
+        except Exception:
+            pass
 
 
 class HostBatch:

@@ -23,6 +23,22 @@ def reorder_source_mse(preds, batch_indices):
     return torch.gather(preds, 1, gather_idx)
 
 
+def sisdr_moments(preds, target):
+    """One pass of ``septfa_sisdr`` over rows ``preds[r, :]`` / ``target[r, :]`` (CUDA, float32, contiguous 2-D): returns
+    ``(si_sdr_db [rows] float32 with zero_mean=True, moments [rows, 5] float64)`` where the moments are the raw sums
+    ``sum p, sum t, sum p t, sum t t, sum p p`` the kernel accumulates in double."""
+    rows, n = preds.shape
+    out = torch.empty(rows, dtype=torch.float32, device=preds.device)
+    scratch = torch.empty(rows * 5, dtype=torch.float64, device=preds.device)
+    with torch.cuda.device(preds.device):
+        rc = _lib.load().septfa_sisdr(C.c_void_p(preds.data_ptr()), C.c_void_p(target.data_ptr()), rows, n, 1,
+                                      C.c_void_p(out.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                      C.c_void_p(torch.cuda.current_stream(preds.device).cuda_stream))
+    if rc != 0:
+        raise _lib.SeptfaError(f"septfa_sisdr failed ({rc})")
+    return out, scratch.view(rows, 5)
+
+
 def calc_sisdr(preds, target, zero_mean=True):
     """model/combined_loss.py:16-56 (SI-SDR in dB over the last axis)."""
     if preds.shape != target.shape:

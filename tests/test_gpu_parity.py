@@ -663,21 +663,167 @@ def test_unusual_weights_against_oracle(cuda_models):
     assert sisdr_db(out.cpu().numpy(), ref_out) >= 60.0
 
 
-def test_known_targets_driver_runs(cuda_models):
-    """OnlineSaving (known targets): intended behaviour of model/online_class_known_targets.py:85-154."""
+@pytest.mark.parametrize("similarity", [False, True])
+def test_known_targets_driver_matches_reference(cuda_models, similarity):
+    """OnlineSaving (known targets), model/online_class_known_targets.py:85-154, against golden vectors produced by the
+    reference's own class (driven through a 6-tuple shim, the file being stale: tests/golden/make_golden.py): left
+    padding by 2 s, the remainder tail padding, per-window PIT against the true sources (or the L1 similarity stitch),
+    the final PIT of the stitched signal, and both SI-SDR figures."""
+    from septfa_b200.evaluate import pairwise_neg_sisdr
     from septfa_b200.online import OnlineSavingKnownTargets
-    from septfa_b200.pit import PITLossWrapper, calc_sisdr
-
-    def neg_sisdr(est, tgt):  # pairwise-point loss for PIT: mean over batch like the reference's loss functions
-        return -calc_sisdr(est, tgt).mean()
-    m = cuda_models(synth.CONFIG_WITH_VAD, 41, 0)
-    x = torch.from_numpy(synth.make_mixtures(1, 70000, 800)).cuda()
-    tgt = torch.stack([x * 0.6, x * 0.4], dim=1)
-    crit = PITLossWrapper(neg_sisdr, pit_from="pw_pt")
-    drv = OnlineSavingKnownTargets(m, "/tmp/septfa_online_test3", crit, criterion_similarity=PITLossWrapper(torch.nn.L1Loss(), pit_from="pw_pt"))
-    drv.num_save_samples = 0
-    sig = drv.calc_online(x, tgt, "n", 0, {})
+    from septfa_b200.pit import PITLossWrapper
+    g, meta = load_golden("online_known_sim_4s" if similarity else "online_known_pit_4s")
+    m = cuda_models(meta["args"], meta["weight_seed"], 0)
+    L = meta["length"]
+    x = torch.from_numpy(synth.make_mixtures(1, L, meta["base_seed"]))
+    rng = np.random.default_rng(meta["base_seed"])
+    w = torch.from_numpy(rng.uniform(0.3, 0.7, size=(1, 1, L)).astype(np.float32))
+    tgt = torch.cat([x[:, None] * w, x[:, None] * (1 - w)], dim=1)
+    crit_sep = PITLossWrapper(pairwise_neg_sisdr, pit_from="pw_mtx")                       # test.py:49-56
+    crit_sim = PITLossWrapper(torch.nn.L1Loss(), pit_from="pw_pt") if similarity else None
+    drv = OnlineSavingKnownTargets(crit_sep, m, "/tmp/septfa_online_test3", "cuda", crit_sim)   # the reference's argument order
+    sig = drv.calc_online(x.cuda(), tgt.cuda(), "n", 0).cpu().numpy()
+    ref = g["online_signal"]
     # left-padded by 2 s (:92-93), then padded by the *remainder* (102000 - 48000) % 16000 = 6000 (:94-97, a quirk of
     # the reference: it pads by the remainder, not up to the next hop) -> 108000 -> floor(60000 / 16000) + 1 = 4 hops
-    assert sig.shape == (1, 2, 4 * 16000)
-    assert len(drv.online_sisdr) == 1 and len(drv.reference_sisdr) == 1 and np.isfinite(drv.online_sisdr[0])
+    assert sig.shape == ref.shape == (1, 2, 4 * 16000)
+    assert np.abs(sig - ref).max() <= 5e-4, np.abs(sig - ref).max()
+    assert len(drv.online_sisdr) == 1 and len(drv.reference_sisdr) == 1
+    assert abs(drv.online_sisdr[0] - float(g["online_sisdr"][0])) < 2e-2
+    assert abs(drv.reference_sisdr[0] - float(g["reference_sisdr"][0])) < 2e-2
+    # criteria the device stitch does not implement are refused, not silently replaced
+    with pytest.raises(NotImplementedError):
+        OnlineSavingKnownTargets(crit_sep, m, "/tmp/x", "cuda", PITLossWrapper(torch.nn.MSELoss(), pit_from="pw_pt"))
+
+
+def test_evaluation_helpers_match_reference(cuda_models):
+    """septfa_b200.evaluate against the reference's own functions (imported through oracle/ref_loader.py): the pairwise
+    negative SI-SDR matrix + PIT of test.py's separation criterion, the mask-based simple VAD, the VAD accuracy."""
+    import importlib
+    from oracle import ref_loader
+    from septfa_b200 import evaluate as E
+    ns = ref_loader.load()
+    SDR = importlib.import_module("model.sdr")
+    rng = np.random.default_rng(3)
+    tgt = torch.from_numpy(rng.standard_normal((5, 2, 32000)).astype(np.float32) * 0.1)
+    est = tgt.clone()
+    est[[1, 3]] = est[[1, 3]][:, [1, 0]]
+    est = est * 0.8 + 0.03 * torch.from_numpy(rng.standard_normal(est.shape).astype(np.float32))
+    ref_pw = SDR.pairwise_neg_sisdr(est, tgt)
+    got_pw = E.pairwise_neg_sisdr(est.cuda(), tgt.cuda()).cpu()
+    assert (got_pw - ref_pw).abs().max().item() < 1e-2
+    ref_loss, ref_idx = ns.pit_wrapper.PITLossWrapper(SDR.pairwise_neg_sisdr, pit_from="pw_mtx")(est, tgt, return_incides=True)
+    loss, reordered, idx = E.pit_sisdr(est.cuda(), tgt.cuda())
+    assert torch.equal(idx.cpu(), ref_idx) and abs(loss.item() - ref_loss.item()) < 1e-2
+    mix = tgt.sum(dim=1)
+    rep = E.separation_report(mix.cuda(), est.cuda(), tgt.cuda())
+    ref_sdr = ns.combined_loss.calc_sisdr(ns.combined_loss.reorder_source_mse(est, ref_idx), tgt)
+    assert (rep["si_sdr"].cpu() - ref_sdr).abs().max().item() < 1e-2
+    assert (rep["si_sdr_start"].cpu() - ns.combined_loss.calc_sisdr(mix[:, None].repeat(1, 2, 1), tgt)).abs().max().item() < 1e-2
+    UT = importlib.import_module("Our_utils.utils_test")
+    masks = torch.rand(3, 2, 257, 40)
+    assert torch.equal(E.simple_vad_from_masks(masks.cuda()).cpu(), UT.calc_vad(masks))
+    p = torch.rand(4, 2, 50)
+    t = (torch.rand(4, 2, 50) > 0.5).float()
+    acc = E.vad_accuracy(p.cuda(), t.cuda())
+    d = (p > 0.5).float()
+    assert abs(acc[0].item() - (d == t).float().mean().item()) < 1e-6
+    assert abs(acc[1].item() - (d[:, 0] == t[:, 0]).float().mean().item()) < 1e-6
+
+
+def test_inference_cli_end_to_end(cuda_models, tmp_path):
+    """`python -m septfa_b200.inference` (only_inference.py:27-137): a synthetic stereo int16 wav and a synthetic .pth in
+    the checkpoint layout of only_inference.py:49-55, flags -c -r -pm -sp -o -ps -ikw; the written wav files are compared
+    with what the UNMODIFIED reference script wrote for the same inputs (tests/golden/cli_with_vad_ps32.npz)."""
+    import json
+    from scipy.io.wavfile import read, write
+    from septfa_b200 import inference
+    g, meta = load_golden("cli_with_vad_ps32")
+    wav, ckpt, cfg = tmp_path / "mix.wav", tmp_path / "model_with_vad.pth", tmp_path / "config.json"
+    write(str(wav), 16000, synth.make_cli_wav(meta["weight_seed"], fs=16000))
+    torch.save(synth.make_checkpoint(meta["args"], meta["weight_seed"]), str(ckpt))
+    cfg.write_text(json.dumps({"name": "t", "arch": {"type": "SeparationModel", "args": meta["args"]}}))
+    out_dir = tmp_path / "out"
+    ikw = json.dumps({"filter_signals_by_smo_vad": True})
+    out, vad = inference.main(["-c", str(cfg), "-r", str(ckpt), "-pm", str(wav), "-sp", str(out_dir), "-o", "", "-ps", "32",
+                               "-ikw", ikw, "-d", "0"])
+    assert out.shape == (1, 2, 48000)
+    for name in ("Mixed_0", "Speaker_0", "Speaker_1"):
+        sr, a = read(str(out_dir / f"{name}.wav"))
+        assert sr == 16000 and a.dtype == np.float32
+        tol = 1e-6 if name == "Mixed_0" else 5e-4
+        assert np.abs(a - g[name]).max() <= tol, (name, np.abs(a - g[name]).max())
+    # online mode (-o non-empty, the reference's bool-of-string flag) writes the stitched signals and the per-window dumps
+    inference.main(["-c", str(cfg), "-r", str(ckpt), "-pm", str(wav), "-sp", str(out_dir), "-o", "1", "-ps", "16", "-ikw", ikw])
+    for f in ("online_results/online_signal0.wav", "online_results/online_signal1.wav", "online_results/ref_mix.wav",
+              "online_results/indx_0/mixed.wav", "online_results/indx_0/output_0.wav", "online_results/indx_0/output_1.wav"):
+        assert (out_dir / f).exists(), f
+    sr, a16 = read(str(out_dir / "Speaker_0.wav"))
+    assert a16.dtype == np.int16                      # -ps 16: 16-bit PCM (the reference hands float16 to scipy, which raises)
+    assert np.abs(a16 / 32767.0 - g["Speaker_0"]).max() < 1e-3
+    sr, w0 = read(str(out_dir / "online_results/indx_0/output_0.wav"))
+    assert w0.shape == (48000,) and np.isfinite(w0).all()
+    # an 8 kHz input is resampled (the reference's own resampling branch ends in a TypeError at only_inference.py:82)
+    wav8 = tmp_path / "mix8.wav"
+    write(str(wav8), 8000, synth.make_cli_wav(3, fs=8000)[:, 0].copy())
+    x8 = inference.read_mixture(str(wav8))
+    assert x8.shape == (1, 48000) and abs(x8.max().item() - 0.9) < 1e-6 and abs(x8.min().item() + 0.9) < 1e-6
+    # save_vad (Our_utils/utlis_inference.py:39-46)
+    inference.save_vad(vad, str(out_dir / "vad"))
+    assert any((out_dir / "vad").iterdir())
+    # checkpoint loader: the 'state_dict' of a reference-layout checkpoint, incl. numpy scalars in monitor_best
+    ck = synth.make_checkpoint(meta["args"], 1)
+    ck["monitor_best"] = np.float64(3.5)
+    torch.save(ck, str(tmp_path / "np.pth"))
+    assert len(inference.load_checkpoint_state_dict(str(tmp_path / "np.pth"))) == 719
+
+
+def test_graphed_forward_equals_eager(cuda_models):
+    """SeparationModel.graphed (septfa_graph_capture / _launch): the forward of one small request replayed as a CUDA
+    graph gives what the eager launch sequence gives, for successive inputs, and stays correct after eager calls in between."""
+    m = cuda_models(synth.CONFIG_WITH_VAD, 31, 0)
+    kw = dict(synth.DEFAULT_INFERENCE_KW, filter_signals_by_smo_vad=True)
+    xs = torch.from_numpy(synth.make_mixtures(3, 64000, 4100)).cuda()
+    g = m.graphed(1, 64000, kw)
+    assert g.num_nodes > 70
+    for i in range(3):
+        out, vad = g(xs[i:i + 1])
+        out, vad = out.clone(), vad.clone()
+        eo, ev, _ = m(xs[i:i + 1].contiguous(), kw)
+        assert (out - eo).abs().max().item() < 5e-4 and (vad - ev).abs().max().item() < 1e-3
+    o1 = g(xs[0:1])[0].clone()
+    o2 = g(xs[0:1])[0].clone()
+    assert torch.equal(o1, o2)
+    g8 = m.graphed(8, 16000, {})
+    x8 = torch.from_numpy(synth.make_mixtures(8, 16000, 4200)).cuda()
+    out8, vad8 = g8(x8)
+    e8, v8, _ = m(x8, {})
+    assert (out8 - e8).abs().max().item() < 5e-4 and (vad8 - v8).abs().max().item() < 1e-3
+
+
+def test_separate_files_batched_pcm_pipeline(cuda_models, tmp_path):
+    """septfa_b200.inference.separate_files: wav files -> int16 PCM batches -> device-side astype/normalise -> forward ->
+    fp16/fp32 -> wav files; equal to the single-file path of only_inference.py per file."""
+    from scipy.io.wavfile import read, write
+    from septfa_b200 import inference
+    m = cuda_models(synth.CONFIG_WITH_VAD, 31, 0)
+    kw = {"filter_signals_by_smo_vad": True}
+    paths = []
+    for i, n in enumerate((20000, 20000, 20000, 31000)):
+        pcm = np.round(synth.make_mixture(i, n, 6000) * 25000.0).astype(np.int16)
+        pth = tmp_path / f"f{i}.wav"
+        write(str(pth), 16000, pcm)
+        paths.append(str(pth))
+    vads = inference.separate_files(m, paths, str(tmp_path / "sep"), kw, precision_save=32, batch=2)
+    assert set(vads) == set(paths)
+    full_kw = dict(synth.DEFAULT_INFERENCE_KW, **kw)
+    for pth in paths:
+        x = inference.read_mixture(pth).cuda()
+        ref_out, ref_vad, _ = m(x, full_kw)
+        for s_ in range(2):
+            sr, a = read(str(tmp_path / "sep" / f"{__import__('pathlib').Path(pth).stem}_Speaker_{s_}.wav"))
+            assert sr == 16000 and a.dtype == np.float32
+            assert np.abs(a - ref_out[0, s_].cpu().numpy()).max() < 5e-4
+        assert (vads[pth] - ref_vad[0].cpu()).abs().max().item() < 1e-3
+
+

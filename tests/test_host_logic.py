@@ -143,3 +143,58 @@ def test_two_rank_gloo_sharding_and_metric_gather(tmp_path):
                        capture_output=True, text=True, timeout=280)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "OK 11 1.5" in r.stdout
+
+
+def test_pit_helpers_equal_reference_functions():
+    """The re-written pairwise-loss / exhaustive-permutation helpers against the reference's own (imported through
+    oracle/ref_loader.py), 2 and 3 sources, including exact ties (-> identity, torch.min's first index)."""
+    from oracle import ref_loader
+    from septfa_b200.pit import PITLossWrapper
+    ns = ref_loader.load()
+    RP = ns.pit_wrapper.PITLossWrapper
+    g = torch.Generator().manual_seed(5)
+    for n_src in (2, 3):
+        pw = torch.rand(64, n_src, n_src, generator=g)
+        pw[::7] = 0.25                                     # all permutations tie
+        pw[1::9, 0, 0] = pw[1::9, 1, 0]                    # partial ties
+        pw[1::9, 1, 1] = pw[1::9, 0, 1]
+        loss, idx = PITLossWrapper.find_best_perm_factorial(pw)
+        ref_loss, ref_idx = RP.find_best_perm_factorial(pw)
+        assert torch.equal(idx, ref_idx) and torch.allclose(loss, ref_loss, atol=1e-7)
+    est, tgt = torch.randn(3, 2, 500, generator=g), torch.randn(3, 2, 500, generator=g)
+    l1 = torch.nn.L1Loss()
+    assert torch.equal(PITLossWrapper.get_pw_losses(l1, est, tgt), RP.get_pw_losses(l1, est, tgt))
+    mine, theirs = PITLossWrapper(l1, pit_from="pw_pt"), RP(l1, pit_from="pw_pt")
+    a, b = mine(est, tgt, return_incides=True), theirs(est, tgt, return_incides=True)
+    assert torch.equal(a[1], b[1]) and abs(a[0].item() - b[0].item()) < 1e-7
+
+
+def test_reference_bytecode_build_matches_source(tmp_path):
+    """oracle/ref_loader.py: the byte-compiled reference under oracle/_ref (what the GPU box imports) is the same program
+    as /root/reference (what this container imports): same forward result for the same weights and input."""
+    from oracle import ref_loader
+    if not os.path.isdir(ref_loader.REF_SRC):
+        pytest.skip("reference sources not present")
+    assert ref_loader.build_ref()
+    code = (
+        "import sys, io, contextlib, warnings; warnings.filterwarnings('ignore'); sys.path.insert(0, %r)\n"
+        "import numpy as np, torch\n"
+        "from oracle import ref_loader\n"
+        "from septfa_b200 import synth\n"
+        "ns = ref_loader.load()\n"
+        "with contextlib.redirect_stdout(io.StringIO()):\n"
+        "    m = ns.model.SeparationModel(**synth.CONFIG_WITH_VAD)\n"
+        "m.load_state_dict(synth.make_state_dict(synth.CONFIG_WITH_VAD, 3)); m.eval()\n"
+        "with torch.no_grad():\n"
+        "    out, vad, _ = m(torch.from_numpy(synth.make_mixtures(1, 9000, 77)), {})\n"
+        "np.save(sys.argv[1], np.concatenate([out.numpy().ravel(), vad.numpy().ravel()]))\n"
+        "print(ns.kind)\n" % ROOT)
+    res = {}
+    for kind, env_ref in (("source", ref_loader.REF_SRC), ("bytecode", "/nonexistent")):
+        out = tmp_path / f"{kind}.npy"
+        r = subprocess.run([sys.executable, "-c", code, str(out)], capture_output=True, text=True,
+                           env=dict(os.environ, SEPTFA_REFERENCE=env_ref, PYTHONDONTWRITEBYTECODE="1"))
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert r.stdout.strip().endswith(kind)
+        res[kind] = np.load(out)
+    assert np.array_equal(res["source"], res["bytecode"])
