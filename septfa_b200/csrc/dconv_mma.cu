@@ -37,6 +37,7 @@
 // Synchronisation is mbarriers only. Requires T >= 128 (a tile touches at most two utterances) and the plane layout of
 // p (conv1's persistent kernel writes it); otherwise launch_tc_dconv's kernel is used.
 #include <algorithm>
+#include <cuda.h>
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -69,6 +70,8 @@ constexpr int kThreadsD = 16 * 32;
 static_assert(kOffW % 1024 == 0 && kSmemBytes <= 232448, "shared-memory plan");
 
 struct DmParams {
+  alignas(64) CUtensorMap w_tmap;   // res_out weight image as a 2-D tensor [2048 rows][64 halves], box = one K-chunk
+  int use_tmap;
   int M, T, ntiles, Mp, dil;
   float slope2;
   const __half* p_planes;      // [32 K-groups][Mp slots][8 channels]; frame r lives in slot r + kHalo
@@ -103,8 +106,16 @@ __device__ long long g_dm_tl[10][64];
 #define DTL(role, idx) do { } while (0)
 #endif
 
+// TMA tensor load of a 2-D box (SASS: UTMALDG), completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
 template <bool AMAX>
-__global__ void __launch_bounds__(kThreadsD, 1) k_dconv_mma(DmParams p) {
+__global__ void __launch_bounds__(kThreadsD, 1) k_dconv_mma(const __grid_constant__ DmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* w_full = bars + 6;        // [2]
@@ -178,9 +189,11 @@ __global__ void __launch_bounds__(kThreadsD, 1) k_dconv_mma(DmParams p) {
           if (u > 0) mbar_wait(w_empty + s, (u - 1) & 1, 150 + j);   // both CTAs' MMAs are done with the stage
           DTL(1, g);
           mbar_expect_tx(w_full + s, kWBytes);
-          if (cs == 1)
+          if (cs == 1 && p.use_tmap)   // tensor-map TMA load of the chunk's 256 x 64 box (measured: same rate as the linear copy)
+            tma_load_2d(smem + kOffW + s * kWBytes, &p.w_tmap, 0, j * 256, w_full + s);
+          else if (cs == 1)
             bulk_copy_g2s(smem + kOffW + s * kWBytes, reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)j * kWBytes, kWBytes, w_full + s);
-          else if (crank == 0)
+          else if ((uint32_t)(j & 1) == crank)   // the two CTAs' TMA engines take turns: each issues half of the stream
             bulk_copy_g2s_mc(smem + kOffW + s * kWBytes, reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)j * kWBytes, kWBytes, w_full + s,
                              (uint16_t)3);
         }
@@ -461,6 +474,8 @@ void launch_dconv_mma(const DconvMmaParams& c, cudaStream_t st) {
   p.p_planes = c.p_planes; p.st_p = c.st_p; p.tap_img = c.tap_img; p.swc = c.swc; p.w16 = c.w16; p.bog = c.bog;
   p.w_img = c.w_img; p.racc = c.racc; p.rowsum = c.rowsum; p.colsum = c.colsum; p.st_q = c.st_q;
   p.desc_swap = ctx().dconv_desc_swap;
+  p.use_tmap = (c.w_tmap != nullptr && ctx().dconv_w_tmap) ? 1 : 0;
+  if (p.use_tmap) p.w_tmap = *reinterpret_cast<const CUtensorMap*>(c.w_tmap);
   p.cluster = ctx().dconv_cluster == 2 ? 2 : 1;
   const int npairs = (p.ntiles + p.cluster - 1) / p.cluster;
   cudaLaunchConfig_t cfg{};

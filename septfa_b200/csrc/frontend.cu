@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
   __shared__ float win[kNfft];
   __shared__ float P[kFrontRows][kPPitch];
   __shared__ float red[64];
+  __shared__ double nyq[4][2][2];   // [group][warp of the group][frame a / b]: Nyquist bins recomputed in double
+  __shared__ int nyq_flag[4];
   pdl_launch_dependents();
   const int tid = threadIdx.x, grp = tid >> 6, j = tid & 63;
   const int b = blockIdx.y, t0 = blockIdx.x * kFrontFrames;
@@ -79,6 +81,36 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
       buf[grp][fft_idx(n)] = make_float2(a, c);
     }
     fft512_r8<false>(buf[grp], tw, j, grp);
+    // The Nyquist bin is REAL, X[256] = sum_n (-1)^n x[n] w[n], and for some frames it lands arbitrarily close to zero; the
+    // dB (a logarithm) then amplifies the fp32 FFT's round-off without bound - 0.2 dB on one such frame moved VAD
+    // probabilities by 4e-4 on long inputs (more frames, more near-zero draws; profiles/r2_precision.md). When the bin is
+    // small against its neighbours (~2 % of the frame pairs) the group's 64 threads recompute it in double: n = j + 64 r
+    // has the parity of j, so a thread's eight terms share one sign.
+    if (j == 0) {
+      const float2 zk = buf[grp][fft_idx(kNfft / 2)], z1 = buf[grp][fft_idx(kNfft / 2 - 1)], z2 = buf[grp][fft_idx(kNfft / 2 + 1)];
+      const float scale = 0.02f * (fabsf(z1.x) + fabsf(z1.y) + fabsf(z2.x) + fabsf(z2.y));
+      nyq_flag[grp] = ((va && fabsf(zk.x) < scale) ? 1 : 0) | ((vb && fabsf(zk.y) < scale) ? 2 : 0);
+    }
+    group_barrier(grp);
+    if (nyq_flag[grp] != 0) {   // uniform over the group
+      double sa = 0.0, sc = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int n = j + 64 * r;
+        int64_t ia = (int64_t)ta * kHop + n - kNfft / 2, ib = ia + kHop;
+        if (ia < 0) ia = -ia;
+        if (ia >= L) ia = 2 * (L - 1) - ia;
+        if (ib < 0) ib = -ib;
+        if (ib >= L) ib = 2 * (L - 1) - ib;
+        if (va) sa += (double)__ldg(xb + ia) * (double)win[n];
+        if (vb) sc += (double)__ldg(xb + ib) * (double)win[n];
+      }
+      if (j & 1) { sa = -sa; sc = -sc; }
+      sa = warp_sum(sa);
+      sc = warp_sum(sc);
+      if ((tid & 31) == 0) { nyq[grp][(tid >> 5) & 1][0] = sa; nyq[grp][(tid >> 5) & 1][1] = sc; }
+      group_barrier(grp);
+    }
     const bool wa = va && la >= 1 && la <= kFrontFrames;  // frames this CTA owns (not halo)
     const bool wb = vb && (la + 1) <= kFrontFrames;
     for (int f = j; f < kBins; f += 64) {
@@ -87,6 +119,10 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
         const float2 zk = buf[grp][fft_idx(f)], zn = buf[grp][fft_idx((kNfft - f) & (kNfft - 1))];
         A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         Bc = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+        if (f == kNfft / 2) {
+          if (nyq_flag[grp] & 1) A.x = (float)(nyq[grp][0][0] + nyq[grp][1][0]);
+          if (nyq_flag[grp] & 2) Bc.x = (float)(nyq[grp][0][1] + nyq[grp][1][1]);
+        }
       }
       // lg2.approx (2^-22 relative on a value of at most ~100 dB) instead of the ~30-instruction log10f
       if (va) P[la][f + 1] = 10.f * __log10f(fmaxf(A.x * A.x + A.y * A.y, 1e-10f));

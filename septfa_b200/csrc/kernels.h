@@ -78,6 +78,7 @@ struct DconvMmaParams {
   float slope2; int dil;
   int M, T, B;
   const __half* w_img;      // res_out image, as DconvParams
+  const void* w_tmap;       // host pointer to a CUtensorMap over w_img ([2048 rows][64 halves], box 256 x 64), or nullptr
   __half* racc; float* rowsum; double* colsum; Stat2* st_q;
 };
 
@@ -213,6 +214,7 @@ struct LaunchCtx {
   int fused_pdl = 1;           // the cluster-resident residual kernel launches programmatically after dconv
   int dconv_mma = 1;           // tensor-core depthwise + res_out kernel (dconv_mma.cu) when applicable
   int dconv_desc_swap = 0;     // bring-up: exchange LBO / SBO of its no-swizzle descriptors
+  int dconv_w_tmap = 1;        // stream the res_out weight image with tensor-map TMA loads (0: linear bulk copies)
   int dconv_cluster = 1;       // 2: clusters of two CTAs with a multicast weight stream (measured: no gain)
 };
 LaunchCtx& ctx();

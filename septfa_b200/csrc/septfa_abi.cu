@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
 #include "../../include/septfa.h"
 #include "kernels.h"
 
@@ -29,6 +31,7 @@ struct DevBlock {
   const float4* w2b; const float4* w2f; const float* c2f; float a2; int dil;
   const float4* wtab; const float* bog;   // tcgen05 dconv producer: pair-ordered tap table, beta1 / gamma1
   const uint8_t* tap_img; const float4* swc; const float* w16; bool mma_ok;   // tensor-core depthwise kernel (dconv_mma.cu)
+  alignas(64) CUtensorMap w3_tmap; bool tmap_ok;   // res_out weight image as a TMA tensor
   const __half* w3_img; const float* w3_t; const float* s3_tc; const float* s3_ref; const float* c03;
   TfParams tf;
   const float* lf_g; const float* lf_b; const float* ls_g; const float* ls_b;  // recursive
@@ -234,6 +237,31 @@ std::vector<double> split_lo(const std::vector<double>& w) {
   return lo;
 }
 
+// CUtensorMap over a pre-swizzled weight image of `rows` x 64 halves (128-byte rows): box = 256 rows = one 32 KB K-chunk,
+// copied verbatim (no TMA swizzle: the image already has the operand layout). The encoder comes from the driver through
+// the runtime's entry-point query, so nothing links against libcuda.
+bool make_weight_tmap(CUtensorMap* out, const void* gptr, int rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || sym == nullptr) {
+      cudaGetLastError();
+      return false;
+    }
+    fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  const cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {64, 256};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 const std::vector<float>& T_(septfa_handle* h, const std::string& k) { return h->host.at(k); }
 
 struct Workspace {
@@ -350,6 +378,7 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
   if (const char* e = getenv("SEPTFA_DCONV_LATE_TRIGGER")) h->lctx.dconv_late_trigger = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SEPTFA_FUSED_PDL")) h->lctx.fused_pdl = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SEPTFA_DCONV_MMA")) h->lctx.dconv_mma = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SEPTFA_DCONV_CLUSTER")) h->lctx.dconv_cluster = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("SEPTFA_DCONV_DESC_SWAP")) h->lctx.dconv_desc_swap = atoi(e) ? 1 : 0;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, "cudaSetDevice failed"); }
   cudaError_t e = tc_gemm_setup();
@@ -431,6 +460,10 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "dconv_mma") == 0) {
     h->lctx.dconv_mma = value ? 1 : 0;
+    return 0;
+  }
+  if (std::strcmp(name, "dconv_w_tmap") == 0) {
+    h->lctx.dconv_w_tmap = value ? 1 : 0;
     return 0;
   }
   if (std::strcmp(name, "dconv_cluster") == 0) {
@@ -631,6 +664,7 @@ int septfa_commit_weights(septfa_handle* h) {
           upload(h, wt, &d.w3_t) || upload(h, s3_tc, &d.s3_tc) ||
           upload(h, s3_ref, &d.s3_ref) || upload(h, c03, &d.c03))
         return SEPTFA_E_CUDA;
+      d.tmap_ok = make_weight_tmap(&d.w3_tmap, d.w3_img, 8 * 256);
     }
     d.tf.enabled = c.tf_attention;
     if (c.tf_attention) {
@@ -793,7 +827,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     }
 #endif
     if (planes) {
-      DconvMmaParams dm{reinterpret_cast<const __half*>(ws.p), Mp, st_p, d.tap_img, d.swc, d.w16, d.bog, d.a2, d.dil, M, T, B, d.w3_img,
+      DconvMmaParams dm{reinterpret_cast<const __half*>(ws.p), Mp, st_p, d.tap_img, d.swc, d.w16, d.bog, d.a2, d.dil, M, T, B, d.w3_img, d.tmap_ok ? &d.w3_tmap : nullptr,
                         reinterpret_cast<__half*>(ws.racc), ws.rowsum, colsum, st_q};
       launch_dconv_mma(dm, st);
     } else if (tc_dconv) {

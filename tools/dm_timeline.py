@@ -12,7 +12,8 @@ with contextlib.redirect_stdout(io.StringIO()):
 m.load_state_dict(synth.make_state_dict(args, 9), strict=True)
 m.eval().cuda()
 m.materialize.update(estimated_stfts=False, mask_per_speaker=False, spectrum=False, masks_b=False)
-x = torch.from_numpy(np.tile(synth.make_mixtures(8, 64000, 1), (32, 1))).cuda()
+B, L = int(os.environ.get("TL_B", 256)), int(os.environ.get("TL_L", 64000))
+x = torch.from_numpy(np.tile(synth.make_mixtures(min(B, 8), L, 1), ((B + 7) // 8, 1))[:B]).cuda()
 for _ in range(3): m(x, {})
 torch.cuda.synchronize()
 buf = (C.c_longlong * 640)()
