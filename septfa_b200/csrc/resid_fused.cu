@@ -18,7 +18,8 @@ namespace septfa {
 
 namespace {
 
-constexpr int kRowBytes = kC * 4 + kC * 2;   // fp32 stream row + fp16 accumulator row in shared memory
+// shared-memory bytes per frame: the stream row (fp32, or fp16 in the half-stream mode) + the fp16 accumulator row
+__host__ __device__ constexpr int row_bytes(bool in_half) { return kC * (in_half ? 2 : 4) + kC * 2; }
 
 __device__ __forceinline__ float tf_chain2(const float* m, int n, int j, const float* w1, float b1, const float* w2,
                                            float b2, float slope) {
@@ -40,7 +41,8 @@ __device__ __forceinline__ float tf_chain2(const float* m, int n, int j, const f
 }
 
 struct FusedParams {
-  float* w;                 // [M,256] residual stream, updated in place
+  const void* w_in;         // [M,256] residual stream before the block: fp32, or fp16 (IN_H)
+  void* w_out;              // [M,256] residual stream after the block: fp32, or fp16 (OUT_H); may alias w_in (same type)
   const __half* racc;       // [M,256] raw res_out accumulators (fp16)
   StreamNorm norm;          // affine that turns w into y
   const Stat2* st_q;        // [B] statistics of q (GroupNorm reg2, folded into res_out)
@@ -77,8 +79,14 @@ constexpr int kPersistWarps = kPersistThreads / 32;
 constexpr int kRowGroups = kPersistThreads / 64;   // a thread owns 4 channels of every kRowGroups-th frame of the tile
 constexpr int kMaxTc = 144;
 
+// IN_H / OUT_H: the stream is read / written as fp16 (the half-stream mode of the forward: blocks 1 .. n-1 read fp16,
+// blocks 0 .. n-2 write fp16; the statistics of the new stream are those of the ROUNDED values, which is what the
+// consumers normalise).
+template <bool IN_H, bool OUT_H>
 __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParams p) {
   using namespace tc;
+  constexpr int kInBytes = IN_H ? 2 : 4;
+  constexpr int kRowBytes = row_bytes(IN_H);
   extern __shared__ __align__(16) uint8_t smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
@@ -110,8 +118,8 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
   auto fetch = [&](int b) {   // one thread: two bulk copies onto the tile's mbarrier
     const int64_t row0 = (int64_t)b * p.T + t0;
     mbar_expect_tx(&full, (uint32_t)nt * kRowBytes);
-    bulk_copy_g2s(smem, p.w + row0 * kC, (uint32_t)nt * kC * 4, &full);
-    bulk_copy_g2s(smem + (size_t)TC * kC * 4, p.racc + row0 * kC, (uint32_t)nt * kC * 2, &full);
+    bulk_copy_g2s(smem, reinterpret_cast<const uint8_t*>(p.w_in) + row0 * kC * kInBytes, (uint32_t)nt * kC * kInBytes, &full);
+    bulk_copy_g2s(smem + (size_t)TC * kC * kInBytes, p.racc + row0 * kC, (uint32_t)nt * kC * 2, &full);
   };
   if (tid == 0 && cluster_id < p.B) fetch(cluster_id);
 
@@ -201,8 +209,17 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
   bool peers_up = false;
   for (int b = cluster_id, it = 0; b < p.B; b += n_clusters, ++it) {
     const int buf = it & 1;
-    const float* w_s = reinterpret_cast<const float*>(smem);                                   // [TC][256] fp32 stream rows
-    const __half* r_s = reinterpret_cast<const __half*>(smem + (size_t)TC * kC * 4);           // [TC][256] fp16 accumulators
+    const uint8_t* w_s = smem;                                                                 // [TC][256] stream rows (fp32 / fp16)
+    const __half* r_s = reinterpret_cast<const __half*>(smem + (size_t)TC * kC * kInBytes);    // [TC][256] fp16 accumulators
+    auto load_w4 = [&](int i) -> float4 {     // this thread's 4 channels of frame i
+      if constexpr (IN_H) {
+        const uint2 hw = *reinterpret_cast<const uint2*>(w_s + ((size_t)i * kC + c0) * 2);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&hw.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        return *reinterpret_cast<const float4*>(w_s + ((size_t)i * kC + c0) * 4);
+      }
+    };
     const int b_next = b + n_clusters;
     const bool has_next = b_next < p.B;
     FTL(8 + it * 8 + 0);
@@ -242,7 +259,7 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
         if (i >= nt) break;
         const float g = gt_cur[i];
         const float2 gt2 = make_float2(g, g);
-        const float4 wv = *reinterpret_cast<const float4*>(w_s + i * kC + c0);
+        const float4 wv = load_w4(i);
         const uint2 hv = *reinterpret_cast<const uint2*>(r_s + i * kC + c0);
         const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
         const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
@@ -301,7 +318,7 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
       }
     }
     float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-    float* wout = p.w + ((int64_t)b * p.T + t0) * kC + c0;
+    uint8_t* wout = reinterpret_cast<uint8_t*>(p.w_out) + (((int64_t)b * p.T + t0) * kC + c0) * (OUT_H ? 2 : 4);
     for (int i0 = rg; i0 < nt; i0 += 4 * kRowGroups)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -309,16 +326,24 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
       if (i >= nt) break;
       const float g = gt_cur[i];
       const float2 gt2 = make_float2(g, g);
-      const float4 wv = *reinterpret_cast<const float4*>(w_s + i * kC + c0);
+      const float4 wv = load_w4(i);
       const uint2 hv = *reinterpret_cast<const uint2*>(r_s + i * kC + c0);
       const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
       const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
-      const float2 o0 = __ffma2_rn(gt2, __ffma2_rn(r0, R1[0], R2[0]), __ffma2_rn(make_float2(wv.x, wv.y), P[0], Q[0]));
-      const float2 o1 = __ffma2_rn(gt2, __ffma2_rn(r1, R1[1], R2[1]), __ffma2_rn(make_float2(wv.z, wv.w), P[1], Q[1]));
+      float2 o0 = __ffma2_rn(gt2, __ffma2_rn(r0, R1[0], R2[0]), __ffma2_rn(make_float2(wv.x, wv.y), P[0], Q[0]));
+      float2 o1 = __ffma2_rn(gt2, __ffma2_rn(r1, R1[1], R2[1]), __ffma2_rn(make_float2(wv.z, wv.w), P[1], Q[1]));
+      if constexpr (OUT_H) {
+        const __half2 h0 = __floats2half2_rn(o0.x, o0.y), h1 = __floats2half2_rn(o1.x, o1.y);
+        o0 = __half22float2(h0);
+        o1 = __half22float2(h1);
+        *reinterpret_cast<uint2*>(wout + (int64_t)i * kC * 2) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      } else {
+        *reinterpret_cast<float4*>(wout + (int64_t)i * kC * 4) = make_float4(o0.x, o0.y, o1.x, o1.y);
+      }
       s2 = __fadd2_rn(s2, __fadd2_rn(o0, o1));
       q2 = __ffma2_rn(o0, o0, q2);
       q2 = __ffma2_rn(o1, o1, q2);
-      *reinterpret_cast<float4*>(wout + (int64_t)i * kC) = make_float4(o0.x, o0.y, o1.x, o1.y);
     }
     FTL(8 + it * 8 + 5);
     if (has_next) gate_stage1(buf ^ 1);
@@ -367,22 +392,30 @@ int resid_fused_cluster_size(int T) {   // 0: the utterance does not fit one clu
   return std::min(8, (T + 31) / 32);
 }
 
+typedef void (*ResidKernel)(FusedParams);
+static ResidKernel resid_kernel(int in_half, int out_half) {
+  return in_half ? (out_half ? k_resid_persist<true, true> : k_resid_persist<true, false>)
+                 : (out_half ? k_resid_persist<false, true> : k_resid_persist<false, false>);
+}
+
 cudaError_t resid_fused_setup() {
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  cudaFuncAttributes fa{};
-  cudaError_t e = cudaFuncGetAttributes(&fa, k_resid_persist);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_resid_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+  for (int v = 0; v < 4; ++v) {
+    cudaFuncAttributes fa{};
+    cudaError_t e = cudaFuncGetAttributes(&fa, resid_kernel(v >> 1, v & 1));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resid_kernel(v >> 1, v & 1), cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
-// Clusters of `cs` CTAs of the persistent kernel the device keeps resident at once (cached per cluster size / footprint).
-static int persist_clusters(int cs, size_t smem) {
-  static int cache[9][2] = {};
-  static size_t cache_smem[9][2] = {};
-  const int slot = smem > 100 * 1024 ? 1 : 0;
-  if (cache[cs][slot] != 0 && cache_smem[cs][slot] == smem) return cache[cs][slot];
+// Clusters of `cs` CTAs of the persistent kernel the device keeps resident at once (cached per variant / cluster size / footprint).
+static int persist_clusters(int variant, int cs, size_t smem) {
+  static int cache[4][9] = {};
+  static size_t cache_smem[4][9] = {};
+  if (cache[variant][cs] != 0 && cache_smem[variant][cs] == smem) return cache[variant][cs];
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cs * 1024);
   cfg.blockDim = dim3(kPersistThreads);
@@ -393,9 +426,9 @@ static int persist_clusters(int cs, size_t smem) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, k_resid_persist, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-  cache[cs][slot] = n;
-  cache_smem[cs][slot] = smem;
+  if (cudaOccupancyMaxActiveClusters(&n, resid_kernel(variant >> 1, variant & 1), &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[variant][cs] = n;
+  cache_smem[variant][cs] = smem;
   return n;
 }
 
@@ -422,14 +455,17 @@ bool launch_resid_fused(const ResidParams& rp, const GateParams& gp, cudaStream_
   const int cs = resid_fused_cluster_size(rp.T);
   if (!rp.racc_half || cs == 0) return false;
   FusedParams p{};
-  p.w = rp.w; p.racc = reinterpret_cast<const __half*>(rp.racc); p.norm = rp.norm;
+  p.w_in = rp.w_half_in ? rp.w_half_in : static_cast<const void*>(rp.w);
+  p.w_out = rp.w_half_out ? rp.w_half_out : static_cast<void*>(rp.w);
+  p.racc = reinterpret_cast<const __half*>(rp.racc); p.norm = rp.norm;
   p.st_q = gp.st_q; p.s3 = gp.s3; p.c03 = gp.c03; p.rowsum = gp.rowsum; p.colsum = gp.colsum; p.tf = gp.tf;
   p.T = rp.T; p.B = rp.B; p.Tc = (rp.T + cs - 1) / cs;
   p.mode = rp.mode; p.g_a = rp.g_a; p.b_a = rp.b_a; p.st_w = rp.st_w;
-  const size_t smem = (size_t)p.Tc * kRowBytes;
-  const int n_clusters = persist_clusters(cs, smem);
+  const int in_half = rp.w_half_in ? 1 : 0, out_half = rp.w_half_out ? 1 : 0, variant = in_half * 2 + out_half;
+  const size_t smem = (size_t)p.Tc * row_bytes(in_half);
+  const int n_clusters = persist_clusters(variant, cs, smem);
   if (n_clusters <= 0) return false;
-  launch_cluster(k_resid_persist, p, std::min(n_clusters, rp.B), cs, kPersistThreads, smem, st);
+  launch_cluster(resid_kernel(in_half, out_half), p, std::min(n_clusters, rp.B), cs, kPersistThreads, smem, st);
   return true;
 }
 

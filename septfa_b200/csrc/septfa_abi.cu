@@ -27,9 +27,11 @@ struct KeySpec {
 };
 
 struct DevBlock {
+  const float4* sb1;   // gemm_conv1_tma.cu: {S[2i], S[2i+1], b1f[2i], b1f[2i+1]}
   const __half* w1_img; const __half* w1_img_lo; const __half* w3_img_lo; const float* w1_t; const float* b1; const float* b1f; float a1; const float* g1; const float* be1;
   const float4* w2b; const float4* w2f; const float* c2f; float a2; int dil;
   const float4* wtab; const float* bog;   // tcgen05 dconv producer: pair-ordered tap table, beta1 / gamma1
+  const uint8_t* tap_img2;   // dconv_mma2.cu: per-rank halves of the tap matrices
   const uint8_t* tap_img; const float4* swc; const float* w16; bool mma_ok;   // tensor-core depthwise kernel (dconv_mma.cu)
   alignas(64) CUtensorMap w3_tmap; bool tmap_ok;   // res_out weight image as a TMA tensor
   const __half* w3_img; const float* w3_t; const float* s3_tc; const float* s3_ref; const float* c03;
@@ -262,10 +264,34 @@ bool make_weight_tmap(CUtensorMap* out, const void* gptr, int rows) {
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// CUtensorMap over the fp16 residual stream [rows][256]: box = 64 halves x 128 rows with the 128-byte swizzle, i.e. one
+// K-chunk of a 128-frame tile lands in shared memory as a K-major SWIZZLE_128B tcgen05 operand (rows past `rows`: zeros).
+bool make_stream_tmap(CUtensorMap* out, const void* gptr, int64_t rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || sym == nullptr) {
+      cudaGetLastError();
+      return false;
+    }
+    fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)kC, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)kC * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 const std::vector<float>& T_(septfa_handle* h, const std::string& k) { return h->host.at(k); }
 
 struct Workspace {
-  float2* S; float* w; float* dcg; float* p; float* racc; float* rowsum; float* gt; float* mt; float* logits;
+  float2* S; float* w; __half* wh; float* dcg; float* p; float* racc; float* rowsum; float* gt; float* mt; float* logits;
   float* ra; float* rb; float* gf; float* c4; float* prob; float* smooth;
   uint8_t* zero_begin; size_t zero_bytes;
   Stat2* st0; Stat2* st_blk; Stat2* st_o; Stat2* st_vad; double* colsum;
@@ -283,6 +309,7 @@ Workspace carve(const septfa_handle* h, void* base, int B, int64_t L) {
   };
   w.S = (float2*)take(M * kBins * sizeof(float2));
   w.w = (float*)take(M * kC * sizeof(float));
+  w.wh = (__half*)take(M * kC * sizeof(__half));   // the residual stream as fp16 (half-stream mode)
   w.dcg = (float*)take(M * sizeof(float));
   w.p = (float*)take(M * kC * sizeof(float) + (size_t)(256 + 2 * kPlaneHalo) * 512);   // also holds the fp16 plane layout (Mp slots)
   w.racc = (float*)take(M * kC * sizeof(float));
@@ -384,6 +411,8 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
   cudaError_t e = tc_gemm_setup();
   if (e == cudaSuccess) e = resid_fused_setup();
   if (e == cudaSuccess) e = conv1_persist_setup();
+  if (e == cudaSuccess) e = conv1_tma_setup();
+  if (e == cudaSuccess) e = dconv_mma2_setup();
   if (e == cudaSuccess) e = dconv_mma_setup();
   if (e != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, std::string("tc_gemm_setup: ") + cudaGetErrorString(e)); }
   *out = h;
@@ -450,6 +479,14 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
     h->lctx.conv1_persist = value ? 1 : 0;
     return 0;
   }
+  if (std::strcmp(name, "stream_half") == 0) {
+    h->lctx.stream_half = value ? 1 : 0;
+    return 0;
+  }
+  if (std::strcmp(name, "conv1_wres") == 0) {
+    h->lctx.conv1_wres = value ? 1 : 0;
+    return 0;
+  }
   if (std::strcmp(name, "fused_resid") == 0) {
     h->fused_resid = value ? 1 : 0;
     return 0;
@@ -460,6 +497,10 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "dconv_mma") == 0) {
     h->lctx.dconv_mma = value ? 1 : 0;
+    return 0;
+  }
+  if (std::strcmp(name, "dconv_pair") == 0) {
+    h->lctx.dconv_pair = value ? 1 : 0;
     return 0;
   }
   if (std::strcmp(name, "dconv_w_tmap") == 0) {
@@ -546,6 +587,18 @@ int septfa_commit_weights(septfa_handle* h) {
           b1f[n] = (float)((double)b1f[n] + acc);
         }
       }
+      {
+        std::vector<float> sb(4 * 128);
+        for (int n = 0; n < kC; ++n) {
+          double srow = 0.0;
+          for (int k = 0; k < kC; ++k) srow += (double)__half2float(__float2half((float)wf[(size_t)n * kC + k]));   // the fp16 operand the tensor core sees
+          sb[(n / 2) * 4 + (n & 1)] = (float)srow;
+          sb[(n / 2) * 4 + 2 + (n & 1)] = b1f[n];
+        }
+        const float* sp = nullptr;
+        if (upload(h, sb, &sp)) return SEPTFA_E_CUDA;
+        d.sb1 = reinterpret_cast<const float4*>(sp);
+      }
       if (upload(h, pack_image(wf, kC, kC, 1, 256), &d.w1_img) || upload(h, pack_image(split_lo(wf), kC, kC, 1, 256), &d.w1_img_lo) ||
           upload(h, wt, &d.w1_t) ||
           upload(h, T_(h, p + ".conv1d.bias"), &d.b1) || upload(h, b1f, &d.b1f))
@@ -611,7 +664,7 @@ int septfa_commit_weights(septfa_handle* h) {
       // The kernel's affine uses the SAME rounded taps (sw = their sum, c2f = b2 + beta / gamma * sw), so the result is
       // an exact depthwise conv with the effective weights fp16(w gamma) / gamma.
       {
-        std::vector<uint8_t> img(kDconvTapBytes, 0);
+        std::vector<uint8_t> img(kDconvTapBytes, 0), img2(kDconvTapBytes, 0);
         std::vector<float> swc(4 * 256), w16(3 * kH);
         bool ok = true;
         for (int cch = 0; cch < kC; ++cch) ok = ok && std::isfinite(g1v[cch]) && std::fabs(g1v[cch]) >= 1e-3f;
@@ -627,13 +680,17 @@ int septfa_commit_weights(septfa_handle* h) {
             const int gi = o / 32, n = o % 32, kk = (o / 2) % 16;
             const size_t byte = (size_t)((gi * 3 + k) * 1024) + (size_t)(kk / 8) * 512 + (size_t)n * 16 + (size_t)(kk % 8) * 2;
             std::memcpy(img.data() + byte, &hq, 2);
+            // pair layout: [rank = n / 16][group][tap][K half][16 outputs][8 inputs]
+            const size_t byte2 = (size_t)(n / 16) * (kDconvTapBytes / 2) + (size_t)((gi * 3 + k) * 512) + (size_t)(kk / 8) * 256 +
+                                 (size_t)(n % 16) * 16 + (size_t)(kk % 8) * 2;
+            std::memcpy(img2.data() + byte2, &hq, 2);
           }
           const double bogv = ok ? (double)be1v[o / 2] / (double)g1v[o / 2] : 0.0;
           swc[(o / 2) * 4 + (o & 1)] = (float)sw;
           swc[(o / 2) * 4 + 2 + (o & 1)] = (float)((double)b2[o] + bogv * sw);
         }
         const float* sp = nullptr;
-        if (upload(h, img, &d.tap_img) || upload(h, swc, &sp) || upload(h, w16, &d.w16)) return SEPTFA_E_CUDA;
+        if (upload(h, img2, &d.tap_img2) || upload(h, img, &d.tap_img) || upload(h, swc, &sp) || upload(h, w16, &d.w16)) return SEPTFA_E_CUDA;
         d.swc = reinterpret_cast<const float4*>(sp);
         d.mma_ok = ok;
       }
@@ -799,6 +856,16 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     CUDA_TRY(h, cudaMemset2DAsync(pb, (size_t)Mp * 16, 0, (size_t)kPlaneHalo * 16, 32, st));
     CUDA_TRY(h, cudaMemset2DAsync(pb + (size_t)(M + kPlaneHalo) * 16, (size_t)Mp * 16, 0, (size_t)(Mp - M - kPlaneHalo) * 16, 32, st));
   }
+  // Half-stream mode: between the blocks the residual stream is stored as fp16 (written by the cluster-resident residual
+  // kernel of block i, read by TMA as the A operand of conv1 of block i + 1 and by the residual kernel of block i + 1); the
+  // first block reads the front end's fp32 features, the last block writes fp32 for the output layer. Recursive-LN wiring
+  // in the fast precision mode only: the stream is re-normalised by every block, so its fp16 rounding is one more source of
+  // the size of the operand roundings ("Precision"), and the residual-LN wiring runs the accurate mode anyway.
+  const bool stream_half = planes && h->lctx.stream_half && h->ln_mode == LN_RECURSIVE && h->fused_resid && resid_fused_cluster_size(T) > 0 && h->nblk > 1;
+  alignas(64) CUtensorMap wh_tmap;
+  if (stream_half && !make_stream_tmap(&wh_tmap, ws.wh, M)) return fail(h, SEPTFA_E_CUDA, "cuTensorMapEncodeTiled failed for the fp16 stream");
+  // CTA-pair dconv kernel (dconv_mma2.cu): cta_group::2 MMAs, res_out weights resident in shared memory
+  const bool pair = planes && h->lctx.dconv_pair;
   const double inv_n = 1.0 / ((double)kC * T);
   StreamNorm norm{ws.st0, h->ln_g, h->ln_b, 1e-8f, inv_n};  // TCN.LN, model.py:333
   for (int i = 0; i < h->nblk; ++i) {
@@ -814,7 +881,14 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     g_tl_conv1 = (i == 6 && getenv("SEPTFA_TIMELINE") && septfa_dbg_ptr) ? septfa_dbg_ptr + 1024 : nullptr;
 #endif
     prof_mark(h, SEPTFA_PROF_CONV1, st);
-    if (tc_conv1) launch_tc_conv1(c1, st); else launch_ref_conv1(c1, st);
+    if (stream_half && i > 0) {
+      Conv1TmaParams ct{&wh_tmap, norm, M, T, B, d.w1_img, d.sb1, d.a1, reinterpret_cast<__half*>(ws.p), Mp, st_p};
+      launch_conv1_tma(ct, st);
+    } else if (tc_conv1) {
+      launch_tc_conv1(c1, st);
+    } else {
+      launch_ref_conv1(c1, st);
+    }
 
     prof_mark(h, SEPTFA_PROF_DCONV, st);
     DconvParams dc{ws.p, st_p, d.g1, d.be1, d.w2b, d.w2f, d.c2f, d.a2, d.dil, M, T, B, d.w3_img, d.w3_t, ws.racc, ws.rowsum, colsum, st_q,
@@ -827,9 +901,9 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     }
 #endif
     if (planes) {
-      DconvMmaParams dm{reinterpret_cast<const __half*>(ws.p), Mp, st_p, d.tap_img, d.swc, d.w16, d.bog, d.a2, d.dil, M, T, B, d.w3_img, d.tmap_ok ? &d.w3_tmap : nullptr,
+      DconvMmaParams dm{reinterpret_cast<const __half*>(ws.p), Mp, st_p, d.tap_img, d.tap_img2, d.swc, d.w16, d.bog, d.a2, d.dil, M, T, B, d.w3_img, d.tmap_ok ? &d.w3_tmap : nullptr,
                         reinterpret_cast<__half*>(ws.racc), ws.rowsum, colsum, st_q};
-      launch_dconv_mma(dm, st);
+      if (pair) launch_dconv_mma2(dm, st); else launch_dconv_mma(dm, st);
     } else if (tc_dconv) {
       launch_tc_dconv(dc, st);
     } else {
@@ -841,6 +915,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     ResidParams rp{};
     rp.w = ws.w; rp.norm = norm; rp.racc = ws.racc; rp.racc_half = half_io; rp.ra = ws.ra; rp.rb = ws.rb; rp.gf = ws.gf; rp.gt = ws.gt;
     rp.M = M; rp.T = T; rp.B = B; rp.mode = h->ln_mode; rp.st_v = st_v; rp.st_w = st_w;
+    if (stream_half) { rp.w_half_in = i > 0 ? ws.wh : nullptr; rp.w_half_out = i + 1 < h->nblk ? ws.wh : nullptr; }
     if (h->ln_mode == LN_RECURSIVE) { rp.g_a = d.lf_g; rp.b_a = d.lf_b; }        // model.py:347-348
     else if (h->ln_mode == LN_RESIDUAL) { rp.g_a = d.lm_g; rp.b_a = d.lm_b; }    // model.py:349-350
     // gates + both residual GroupNorm steps in one cluster-resident kernel when an utterance fits a cluster
