@@ -17,8 +17,8 @@
 //                 ahead as the ring allows; peer: relay ("my p slab / my weights have landed" -> the leader's barriers)
 //   warps 4-11    transform  : tcgen05.ld D1 (the next chunk's load in flight) -> affine, PReLU, statistics, fp16 ->
 //                 tcgen05.st back into the same tensor-memory buffer; one elected lane per warp arrives on the LEADER's barrier
-//   warps 12-15   epilogue   : tcgen05.ld D2 -> fp16 rows staged per lane, 128 columns at a time (the resident weights leave
-//                 room for half a row) -> per-utterance column sums, row sums, one TMA bulk store per row and half
+//   warps 12-15   epilogue   : tcgen05.ld D2 -> fp16, staged 128 columns at a time (the resident weights leave room for half a row) in
+//                 128-byte-swizzled boxes -> one TMA tensor store per box (UTMASTG), per-utterance column sums, row sums
 // Tensor memory (per CTA, allocated with cta_group::2): D2 = columns 0-255; ring of 4 x 64 columns at 256-511 (D1, then q).
 // Synchronisation: mbarriers only; barriers the leader's MMA thread waits on receive remote (cluster-scope) arrivals from
 // the peer, MMA completion is multicast to both CTAs. Requires T >= 128 and the plane layout of p.
@@ -49,9 +49,8 @@ constexpr int kOffP = kOffTap + kTapHalfBytes;
 constexpr int kOffSwc = kOffP + kPStages * kPChunkBytes;
 constexpr int kOffEdge = kOffSwc + 4096;            // edge-correction tables: fp16-rounded taps 0 and 2 [2][512] and beta1 / gamma1 [256], fp32
 constexpr int kOffCorr = kOffEdge + 5120;           // edge corrections of the chunk in each p stage: [kPStages][8 rows][64 outputs] fp32
-constexpr int kEpiPitch = 256 + 16;                 // bytes per staged half row (128 fp16 columns + pad: conflict-free STS.128)
-constexpr int kEpiWarpBytes = 32 * kEpiPitch;
-constexpr int kOffEpi = kOffCorr + kPStages * 2048;
+constexpr int kEpiWarpBytes = 2 * 32 * 128;         // two staging boxes per epilogue warp: 32 rows x 64 fp16 columns, 128-byte-swizzled rows
+constexpr int kOffEpi = (kOffCorr + kPStages * 2048 + 1023) / 1024 * 1024;
 constexpr int kOffBar = kOffEpi + 4 * kEpiWarpBytes;
 constexpr int kSmemBytes = kOffBar + 512;
 static_assert(kPStages <= 4, "barrier slots");
@@ -59,6 +58,7 @@ constexpr int kThreadsD = 16 * 32;
 static_assert(kOffW % 1024 == 0 && kOffP % 16 == 0 && kSmemBytes <= 232448, "shared-memory plan");
 
 struct DmParams {
+  alignas(64) CUtensorMap racc_tmap;   // racc as a 2-D tensor [M rows][256 halves], box 64 columns x 32 rows, SWIZZLE_128B
   int M, T, ntiles, Mp, dil;
   float slope2;
   const __half* p_planes;      // [32 K-groups][Mp slots][8 channels]; frame r lives in slot r + kHalo
@@ -132,6 +132,11 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// TMA tensor store of a 2-D box (SASS: UTMASTG), tracked by the thread's bulk async-group.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, int c0, int c1, const void* ssrc) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(ssrc))
+               : "memory");
+}
 // tcgen05.st without the wait (follow with tmem_st_wait())
 __device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -163,7 +168,7 @@ __device__ long long g_dm2_tl[10][64];
 #endif
 
 template <bool AMAX>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dconv_mma2(const DmParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dconv_mma2(const __grid_constant__ DmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* w_full = bars;            // [8] bulk-copy bytes: this CTA's half of weight chunk j (once)
@@ -172,11 +177,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
   uint64_t* tap_peer = bars + 17;     //     leader: relay
   uint64_t* p_full = bars + 18;       // [kPStages <= 4] bulk-copy bytes
   uint64_t* p_peer = bars + 22;       // [kPStages] leader: the peer's slab has landed (relay)
-  uint64_t* p_empty = bars + 26;      // [kPStages] mini-MMA commit (multicast) + one lane of each local transform warp + the edge warp
+  uint64_t* p_empty = bars + 26;      // [kPStages] mini-MMA commit (multicast) + one lane of the 4 local transform warps of the chunk + the edge warp
   uint64_t* corr_full = bars + 30;    // [kPStages] the edge warp has written the corrections of the chunk in this p stage
   uint64_t* d1_full = bars + 34;      // [4] mini-MMA commit (multicast)
   uint64_t* d1_empty = bars + 38;     // [4] leader: res_out MMA commit (the buffer held D1, then q)
-  uint64_t* a2_full = bars + 42;      // [4] leader: 16 transform warps of the pair (q is in tensor memory)
+  uint64_t* a2_full = bars + 42;      // [4] leader: the 8 transform warps of the pair that take this chunk (q is in tensor memory)
   uint64_t* d2_full = bars + 46;      //     MMA commit (multicast)
   uint64_t* d2_empty = bars + 47;     //     leader: 8 epilogue warps of the pair
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
@@ -193,8 +198,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     for (int j = 0; j < 8; ++j) { mbar_init(w_full + j, 1); mbar_init(w_peer + j, 1); }
     mbar_init(tap_full, 1); mbar_init(tap_peer, 1);
-    for (int s = 0; s < kPStages; ++s) { mbar_init(p_full + s, 1); mbar_init(p_peer + s, 1); mbar_init(p_empty + s, 10); mbar_init(corr_full + s, 1); }
-    for (int s = 0; s < kD1Bufs; ++s) { mbar_init(d1_full + s, 1); mbar_init(d1_empty + s, 1); mbar_init(a2_full + s, 16); }
+    for (int s = 0; s < kPStages; ++s) { mbar_init(p_full + s, 1); mbar_init(p_peer + s, 1); mbar_init(p_empty + s, 6); mbar_init(corr_full + s, 1); }
+    for (int s = 0; s < kD1Bufs; ++s) { mbar_init(d1_full + s, 1); mbar_init(d1_empty + s, 1); mbar_init(a2_full + s, 8); }
     mbar_init(d2_full, 1); mbar_init(d2_empty, 8);
     fence_mbar_init();
   }
@@ -388,7 +393,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
     __syncwarp();
   } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------ transform: D1 -> q -> A2
-    const int q4 = warp & 3, hf = (warp - 4) >> 2;       // TMEM lane quarter (hardware: warp % 4), column half of the chunk
+    const int q4 = warp & 3, par = (warp - 4) >> 2;      // TMEM lane quarter (hardware: warp % 4), parity of the chunks this warp takes
     const int rl = q4 * 32 + lane;                        // a lane = a row of the tile
     const float2 sl2 = make_float2(p.slope2, p.slope2);
     float2* k0_s = reinterpret_cast<float2*>(smem + kOffSwc);   // [2 utterances of the tile][256 output pairs]
@@ -421,26 +426,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float2* k0_row = k0_s + (second ? 256 : 0);
       float2 accS = make_float2(0.f, 0.f), accQ = make_float2(0.f, 0.f);
-      auto t_addr = [&](int gg) { return tmem_base + 256u + (uint32_t)((gg % kD1Bufs) * 64 + hf * 32) + ((uint32_t)(q4 * 32) << 16); };
-      // one chunk: v (the fp32 depthwise accumulators of this lane's row, 32 outputs) -> q (fp16 pairs) -> tensor memory
-      auto chunk = [&](uint32_t (&u)[32], int j, int gg) {
-        const int sp = gg % kPStages;
-        if (warp == 4 && lane == 0 && gg < 32) DTL(7, gg);
-        if (cslot >= 0) {
-          // zero padding of the normalised signal: take back what the out-of-utterance tap contributed (edge warp's table)
-          mbar_wait(corr_full + sp, (gg / kPStages) & 1, 310 + j);
-          const float4* cr = reinterpret_cast<const float4*>(corr_s + (sp * 8 + cslot) * 64 + hf * 32);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 c4 = cr[e];
-            u[4 * e] = __float_as_uint(__uint_as_float(u[4 * e]) - c4.x);
-            u[4 * e + 1] = __float_as_uint(__uint_as_float(u[4 * e + 1]) - c4.y);
-            u[4 * e + 2] = __float_as_uint(__uint_as_float(u[4 * e + 2]) - c4.z);
-            u[4 * e + 3] = __float_as_uint(__uint_as_float(u[4 * e + 3]) - c4.w);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_empty + sp);
+      auto t_addr = [&](int gg, int hf) { return tmem_base + 256u + (uint32_t)((gg % kD1Bufs) * 64 + hf * 32) + ((uint32_t)(q4 * 32) << 16); };
+      // half a chunk: v (the fp32 depthwise accumulators of this lane's row, 32 outputs) -> q (fp16 pairs) -> tensor memory
+      auto half_chunk = [&](uint32_t (&u)[32], int j, int gg, int hf) {
         const float2* kk0 = k0_row + j * 32 + hf * 16;
         uint32_t h[16];
 #pragma unroll
@@ -458,44 +446,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
             h[i * 4 + k] = pack_half2(qv.x, qv.y);
           }
         }
+        tmem_st16_nowait(t_addr(gg, hf), h);   // q (fp16 pairs) over the first 16 of the 32 columns that were read
+      };
+      // The two warps of a lane quarter take ALTERNATE chunks (all 64 columns each) instead of half of every chunk: the
+      // transform is bound by the FP32 pipe of its SM sub-partition, and two warps in lock step (same barrier, same
+      // instruction mix) fight for it during the arithmetic and leave it idle during their tensor-memory round trips.
+      uint32_t va[32], vb[32];
+#pragma unroll 1
+      for (int j = par; j < 8; j += 2) {
+        const int gg = g + j, sp = gg % kPStages;
+        mbar_wait(d1_full + (gg % kD1Bufs), (gg / kD1Bufs) & 1, 300 + j);
+        tc_fence_after();
+        tmem_ld32_nowait(t_addr(gg, 0), va);
+        tmem_ld32_nowait(t_addr(gg, 1), vb);
+        tmem_ld_wait();
+        if (warp == 4 && lane == 0) DTL(4, gg);
+        if (cslot >= 0) {
+          // zero padding of the normalised signal: take back what the out-of-utterance tap contributed (edge warp's table)
+          mbar_wait(corr_full + sp, (gg / kPStages) & 1, 310 + j);
+          const float4* cr = reinterpret_cast<const float4*>(corr_s + (sp * 8 + cslot) * 64);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 c4 = cr[e], d4 = cr[8 + e];
+            va[4 * e] = __float_as_uint(__uint_as_float(va[4 * e]) - c4.x);
+            va[4 * e + 1] = __float_as_uint(__uint_as_float(va[4 * e + 1]) - c4.y);
+            va[4 * e + 2] = __float_as_uint(__uint_as_float(va[4 * e + 2]) - c4.z);
+            va[4 * e + 3] = __float_as_uint(__uint_as_float(va[4 * e + 3]) - c4.w);
+            vb[4 * e] = __float_as_uint(__uint_as_float(vb[4 * e]) - d4.x);
+            vb[4 * e + 1] = __float_as_uint(__uint_as_float(vb[4 * e + 1]) - d4.y);
+            vb[4 * e + 2] = __float_as_uint(__uint_as_float(vb[4 * e + 2]) - d4.z);
+            vb[4 * e + 3] = __float_as_uint(__uint_as_float(vb[4 * e + 3]) - d4.w);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_empty + sp);
+        half_chunk(va, j, gg, 0);
+        half_chunk(vb, j, gg, 1);
         if (warp == 4 && lane == 0 && gg < 32) DTL(7, 32 + gg);
-        tmem_st16_nowait(t_addr(gg), h);   // q (fp16 pairs) over the first 16 of the 32 columns this warp has read
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cl(a2_full + (gg % kD1Bufs), 0);   // one arrival per warp, on the leader's barrier
         if (warp == 4 && lane == 0) DTL(5, gg);
-      };
-      // the next chunk's tensor-memory load is in flight while the current chunk is transformed - if its depthwise
-      // accumulators are already there (never wait for chunk g + 1 before chunk g is handed on: at a tile boundary the
-      // mini-GEMMs of g + 1 may need the D1 buffer that the res_out MMA of an earlier chunk still holds)
-      auto d1_ready = [&](int gg) {   // warp-uniform poll
-        int ok = 0;
-        if (lane == 0) ok = mbar_test_wait(d1_full + (gg % kD1Bufs), (gg / kD1Bufs) & 1) ? 1 : 0;
-        return __shfl_sync(0xffffffffu, ok, 0) != 0;
-      };
-      auto d1_load = [&](int gg, uint32_t (&u)[32], bool block) {
-        if (block) mbar_wait(d1_full + (gg % kD1Bufs), (gg / kD1Bufs) & 1, 300);
-        tc_fence_after();
-        tmem_ld32_nowait(t_addr(gg), u);
-      };
-      uint32_t va[32], vb[32];
-      d1_load(g, va, true);
-#pragma unroll 1
-      for (int j2 = 0; j2 < 4; ++j2, g += 2) {
-        tmem_ld_wait();                                      // va = chunk g
-        if (warp == 4 && lane == 0) DTL(4, g);
-        const bool pre_b = d1_ready(g + 1);
-        if (pre_b) d1_load(g + 1, vb, false);
-        chunk(va, 2 * j2, g);
-        if (!pre_b) d1_load(g + 1, vb, true);
-        tmem_ld_wait();                                      // vb = chunk g + 1
-        if (warp == 4 && lane == 0) DTL(4, g + 1);
-        const bool pre_a = j2 < 3 && d1_ready(g + 2);
-        if (pre_a) d1_load(g + 2, va, false);
-        chunk(vb, 2 * j2 + 1, g + 1);
-        if (j2 < 3 && !pre_a) d1_load(g + 2, va, true);
       }
+      g += 8;
       // statistics of q of this warp's 32 rows x 256 columns, per utterance: fixed-order shuffle trees, double atomics
       const float sv = valid ? accS.x + accS.y : 0.f, qv = valid ? accQ.x + accQ.y : 0.f;
       const float a0 = warp_sum(second ? 0.f : sv), c0 = warp_sum(second ? 0.f : qv);
@@ -512,12 +506,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
   } else if (warp >= 12) {
     // ------------------------------------------------------------ epilogue: D2 -> racc (fp16), row / column sums
     // The resident weights leave room to stage HALF a row per lane: the accumulator's two 128-column halves go through the
-    // same buffer (fp16 row piece per lane -> per-utterance column sums from the staged tile -> one TMA bulk store per row
-    // and half), and D2 is handed back when the second half is in registers.
+    // same buffer, two boxes of 32 rows x 64 columns per warp in the TMA 128-byte-swizzle layout (a lane = a row writes its
+    // 16-byte pieces conflict-free), and leave with ONE tensor-map store per box: 16 TMA requests per CTA and tile. (One
+    // 256-byte bulk store per row and half = 256 requests per tile kept the SM's TMA unit busy for ~5 k cycles per half.)
     const int q4 = warp & 3;
     const int rl = q4 * 32 + lane;
-    uint8_t* stg_w = smem + kOffEpi + (warp - 12) * kEpiWarpBytes;
-    uint8_t* stg = stg_w + lane * kEpiPitch;
+    uint8_t* box_w = smem + kOffEpi + (warp - 12) * kEpiWarpBytes;   // [2 boxes][32 rows][128 B], 1024-aligned
+    const uint32_t rsw = (uint32_t)(lane & 7);
     int lt = 0;
     for (int tile = first; tile < tile_end; tile += stride, ++lt) {
       const int r0 = tile * kTileM, nrows = max(0, min(kTileM, p.M - r0));
@@ -532,7 +527,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
       float2 racc2 = make_float2(0.f, 0.f);
       const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16);
       auto pack_store = [&](const uint32_t (&u)[32], int cc) {   // cc: 32-column piece within the staged half row
-        uint4* dst = reinterpret_cast<uint4*>(stg + cc * 64);
+        uint8_t* dst = box_w + (cc >> 1) * 4096 + lane * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float v8[8];
@@ -540,47 +535,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
           for (int e = 0; e < 8; ++e) v8[e] = __uint_as_float(u[8 * i + e]);
           racc2 = __fadd2_rn(racc2, __fadd2_rn(__fadd2_rn(make_float2(v8[0], v8[1]), make_float2(v8[2], v8[3])),
                                                __fadd2_rn(make_float2(v8[4], v8[5]), make_float2(v8[6], v8[7]))));
-          dst[i] = make_uint4(pack_half2(v8[0], v8[1]), pack_half2(v8[2], v8[3]), pack_half2(v8[4], v8[5]), pack_half2(v8[6], v8[7]));
+          *reinterpret_cast<uint4*>(dst + ((((uint32_t)((cc & 1) * 4 + i)) ^ rsw) << 4)) =
+              make_uint4(pack_half2(v8[0], v8[1]), pack_half2(v8[2], v8[3]), pack_half2(v8[4], v8[5]), pack_half2(v8[6], v8[7]));
         }
       };
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {     // the accumulator's two 128-column halves, through the same staging buffer
-        bulk_wait_read_all();              // this lane's previous half row has left the staging buffer
+      // the staged half (two boxes) leaves with one tensor store per box
+      auto store_half = [&](int hh) {
+        fence_proxy_async();             // our generic-proxy stores -> visible to the tensor store
         __syncwarp();
-        uint32_t va[32], vb[32];
-        const uint32_t t_h = t_row + (uint32_t)(hh * 128);
-        tmem_ld32_nowait(t_h, va);
-        tmem_ld_wait();
-        tmem_ld32_nowait(t_h + 32u, vb);
-        pack_store(va, 0);
-        tmem_ld_wait();
-        tmem_ld32_nowait(t_h + 64u, va);
-        pack_store(vb, 1);
-        tmem_ld_wait();
-        tmem_ld32_nowait(t_h + 96u, vb);
-        pack_store(va, 2);
-        tmem_ld_wait();
-        if (hh == 1) {                     // the whole accumulator is in registers / shared memory: hand D2 back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cl(d2_empty, 0);
-          if (warp == 12 && lane == 0) DTL(6, lt * 4 + 1);
+        if (lane == 0 && nv_w > 0) {       // rows past M are clipped by the tensor map
+          tma_store_2d(&p.racc_tmap, hh * 128, r0 + q4 * 32, box_w);
+          tma_store_2d(&p.racc_tmap, hh * 128 + 64, r0 + q4 * 32, box_w + 4096);
+          bulk_commit_group();
         }
-        pack_store(vb, 3);
-        __syncwarp();
-        // per-utterance column sums of this warp's rows (from the stored fp16 values): lane -> 4 columns
+      };
+      // per-utterance column sums of this warp's rows (from the staged fp16 values): lane -> 4 columns of one box
+      auto colsum_half = [&](int hh) {
         float2 c0[2], c1[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) c0[e] = c1[e] = make_float2(0.f, 0.f);
-        for (int r = 0; r < nv_w; ++r) {
-          const uint2 raw = *reinterpret_cast<const uint2*>(stg_w + r * kEpiPitch + lane * 8);
-          const uint32_t rw[2] = {raw.x, raw.y};
-          if (r < n0_w) {
+        const uint8_t* colb = box_w + (lane >> 4) * 4096 + (lane & 1) * 8;
+        const uint32_t c16 = (uint32_t)((lane & 15) >> 1);
+        if (nv_w == 32 && (n0_w == 32 || n0_w == 0)) {
+          // all 32 rows belong to one utterance (every warp but the one on an utterance boundary / the tensor's end): rows
+          // are first added four at a time as fp16 pairs, then accumulated in fp32 - a third of the instructions of the
+          // general path below, in independent chains. (The fp16 partial sums round like racc itself does, and the column
+          // MEANS over >= 128 frames average those roundings away.)
+          float2 f0 = make_float2(0.f, 0.f), f1 = f0, g0 = f0, g1 = f0;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) c0[e] = __fadd2_rn(c0[e], __half22float2(*reinterpret_cast<const __half2*>(&rw[e])));
-          } else {
+          for (int r4 = 0; r4 < 32; r4 += 4) {
+            uint2 raw[4];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) c1[e] = __fadd2_rn(c1[e], __half22float2(*reinterpret_cast<const __half2*>(&rw[e])));
+            for (int k = 0; k < 4; ++k) raw[k] = *reinterpret_cast<const uint2*>(colb + (r4 + k) * 128 + ((c16 ^ (uint32_t)((r4 + k) & 7)) << 4));
+            const __half2 lo = __hadd2(__hadd2(*reinterpret_cast<const __half2*>(&raw[0].x), *reinterpret_cast<const __half2*>(&raw[1].x)),
+                                       __hadd2(*reinterpret_cast<const __half2*>(&raw[2].x), *reinterpret_cast<const __half2*>(&raw[3].x)));
+            const __half2 hi = __hadd2(__hadd2(*reinterpret_cast<const __half2*>(&raw[0].y), *reinterpret_cast<const __half2*>(&raw[1].y)),
+                                       __hadd2(*reinterpret_cast<const __half2*>(&raw[2].y), *reinterpret_cast<const __half2*>(&raw[3].y)));
+            if (r4 & 4) { g0 = __fadd2_rn(g0, __half22float2(lo)); g1 = __fadd2_rn(g1, __half22float2(hi)); }
+            else { f0 = __fadd2_rn(f0, __half22float2(lo)); f1 = __fadd2_rn(f1, __half22float2(hi)); }
+          }
+          f0 = __fadd2_rn(f0, g0);
+          f1 = __fadd2_rn(f1, g1);
+          if (n0_w == 32) { c0[0] = f0; c0[1] = f1; } else { c1[0] = f0; c1[1] = f1; }
+        } else {
+#pragma unroll 1
+          for (int r4 = 0; r4 < nv_w; r4 += 4) {
+            uint2 raw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = min(r4 + k, 31);
+              raw[k] = *reinterpret_cast<const uint2*>(colb + r * 128 + ((c16 ^ (uint32_t)(r & 7)) << 4));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = r4 + k;
+              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw[k].x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&raw[k].y));
+              if (r < n0_w) { c0[0] = __fadd2_rn(c0[0], lo); c0[1] = __fadd2_rn(c0[1], hi); }
+              else if (r < nv_w) { c1[0] = __fadd2_rn(c1[0], lo); c1[1] = __fadd2_rn(c1[1], hi); }
+            }
           }
         }
         double* cdst = p.colsum + (size_t)b_first * kC + hh * 128 + lane * 4;
@@ -593,17 +605,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
 #pragma unroll
           for (int e = 0; e < 2; ++e) { atomicAdd(cdst + 2 * e, (double)c1[e].x); atomicAdd(cdst + 2 * e + 1, (double)c1[e].y); }
         }
-        fence_proxy_async();             // our generic-proxy stores -> visible to the bulk copy
-        __syncwarp();                    // every lane's column-sum reads of the staging buffer are done
-        if (valid) {
-          bulk_copy_s2g(p.racc + (size_t)row * kC + hh * 128, stg, 256);
-          bulk_commit_group();
+        __syncwarp();                    // every lane's column-sum reads of the staging boxes are done
+      };
+      // columns 0-127: tensor memory -> fp16 -> staging boxes (two loads in flight) -> tensor stores
+      if (lane == 0) bulk_wait_read_all();   // the previous tile's boxes have left the staging buffer
+      __syncwarp();
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32_nowait(t_row, va);
+        tmem_ld_wait();
+        tmem_ld32_nowait(t_row + 32u, vb);
+        pack_store(va, 0);
+        tmem_ld_wait();
+        tmem_ld32_nowait(t_row + 64u, va);
+        pack_store(vb, 1);
+        tmem_ld_wait();
+        tmem_ld32_nowait(t_row + 96u, vb);
+        pack_store(va, 2);
+        tmem_ld_wait();
+        pack_store(vb, 3);
+      }
+      store_half(0);
+      // columns 128-255: tensor memory -> fp16 pairs held in REGISTERS, so that D2 goes back to the MMA warp before the
+      // column sums of either half and before the first half has left the staging boxes (waiting for both held the
+      // accumulator for 3.5-6 k cycles per tile, the pace of the slowest of the pair's eight epilogue warps)
+      uint32_t h2[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t u[32];
+        tmem_ld32_nowait(t_row + (uint32_t)(128 + c * 32), u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v8[e] = __uint_as_float(u[8 * i + e]);
+          racc2 = __fadd2_rn(racc2, __fadd2_rn(__fadd2_rn(make_float2(v8[0], v8[1]), make_float2(v8[2], v8[3])),
+                                               __fadd2_rn(make_float2(v8[4], v8[5]), make_float2(v8[6], v8[7]))));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[c * 16 + i * 4 + e] = pack_half2(v8[2 * e], v8[2 * e + 1]);
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cl(d2_empty, 0);
+      if (warp == 12 && lane == 0) DTL(6, lt * 4 + 1);
+      colsum_half(0);
+      if (lane == 0) bulk_wait_read_all();   // the first half's boxes have left the staging buffer
+      __syncwarp();
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint8_t* dst = box_w + (cc >> 1) * 4096 + lane * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(dst + ((((uint32_t)((cc & 1) * 4 + i)) ^ rsw) << 4)) =
+              make_uint4(h2[cc * 16 + i * 4], h2[cc * 16 + i * 4 + 1], h2[cc * 16 + i * 4 + 2], h2[cc * 16 + i * 4 + 3]);
+      }
+      store_half(1);
+      colsum_half(1);
       if (valid) p.rowsum[row] = racc2.x + racc2.y;
       if (warp == 12 && lane == 0) DTL(6, lt * 4 + 2);
     }
-    bulk_wait_read_all();
+    if (lane == 0) bulk_wait_read_all();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -636,6 +700,7 @@ void launch_dconv_mma2(const DconvMmaParams& c, cudaStream_t st) {
   p.M = c.M; p.T = c.T; p.ntiles = (c.M + kTileM - 1) / kTileM; p.Mp = c.Mp; p.dil = c.dil; p.slope2 = c.slope2;
   p.p_planes = c.p_planes; p.st_p = c.st_p; p.tap_img2 = c.tap_img2; p.swc = c.swc; p.w16 = c.w16; p.bog = c.bog;
   p.w_img = c.w_img; p.racc = c.racc; p.rowsum = c.rowsum; p.colsum = c.colsum; p.st_q = c.st_q;
+  p.racc_tmap = *reinterpret_cast<const CUtensorMap*>(c.racc_tmap);
   const int npairs = (p.ntiles + 1) / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * std::min(g_dm2_sm_count / 2, npairs));

@@ -81,6 +81,7 @@ struct DconvMmaParams {
   const __half* w_img;      // res_out image, as DconvParams
   const void* w_tmap;       // host pointer to a CUtensorMap over w_img ([2048 rows][64 halves], box 256 x 64), or nullptr
   __half* racc; float* rowsum; double* colsum; Stat2* st_q;
+  const void* racc_tmap = nullptr;   // dconv_mma2.cu: host pointer to a CUtensorMap over racc ([M rows][256 halves], box 64 x 32, SWIZZLE_128B)
 };
 
 // TCN.output (model/model.py:322-325,357): logits = Wo GN(PReLU(y)) + bo, N = 514 padded to 576.

@@ -266,7 +266,7 @@ bool make_weight_tmap(CUtensorMap* out, const void* gptr, int rows) {
 
 // CUtensorMap over the fp16 residual stream [rows][256]: box = 64 halves x 128 rows with the 128-byte swizzle, i.e. one
 // K-chunk of a 128-frame tile lands in shared memory as a K-major SWIZZLE_128B tcgen05 operand (rows past `rows`: zeros).
-bool make_stream_tmap(CUtensorMap* out, const void* gptr, int64_t rows) {
+bool make_stream_tmap(CUtensorMap* out, const void* gptr, int64_t rows, int box_rows = 128) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -282,7 +282,7 @@ bool make_stream_tmap(CUtensorMap* out, const void* gptr, int64_t rows) {
   }
   const cuuint64_t dims[2] = {(cuuint64_t)kC, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)kC * 2};
-  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -866,6 +866,8 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   if (stream_half && !make_stream_tmap(&wh_tmap, ws.wh, M)) return fail(h, SEPTFA_E_CUDA, "cuTensorMapEncodeTiled failed for the fp16 stream");
   // CTA-pair dconv kernel (dconv_mma2.cu): cta_group::2 MMAs, res_out weights resident in shared memory
   const bool pair = planes && h->lctx.dconv_pair;
+  alignas(64) CUtensorMap racc_tmap;   // the pair kernel's epilogue stores racc with TMA tensor stores (boxes of 32 rows x 64 columns)
+  if (pair && !make_stream_tmap(&racc_tmap, ws.racc, M, 32)) return fail(h, SEPTFA_E_CUDA, "cuTensorMapEncodeTiled failed for racc");
   const double inv_n = 1.0 / ((double)kC * T);
   StreamNorm norm{ws.st0, h->ln_g, h->ln_b, 1e-8f, inv_n};  // TCN.LN, model.py:333
   for (int i = 0; i < h->nblk; ++i) {
@@ -903,6 +905,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     if (planes) {
       DconvMmaParams dm{reinterpret_cast<const __half*>(ws.p), Mp, st_p, d.tap_img, d.tap_img2, d.swc, d.w16, d.bog, d.a2, d.dil, M, T, B, d.w3_img, d.tmap_ok ? &d.w3_tmap : nullptr,
                         reinterpret_cast<__half*>(ws.racc), ws.rowsum, colsum, st_q};
+      dm.racc_tmap = pair ? &racc_tmap : nullptr;
       if (pair) launch_dconv_mma2(dm, st); else launch_dconv_mma(dm, st);
     } else if (tc_dconv) {
       launch_tc_dconv(dc, st);
