@@ -351,7 +351,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
 #ifdef SEPTFA_EXP_ONE_TAP
         for (int k = 1; k < 2; ++k) {
 #else
+#ifdef SEPTFA_EXP_ONE_TAP
+        for (int k = 1; k < 2; ++k) {
+#else
         for (int k = 0; k < 3; ++k) {       // tap-major: consecutive MMAs accumulate into different columns
+#endif
 #endif
 #pragma unroll
           for (int grp = 0; grp < 2; ++grp) {
@@ -361,7 +365,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
 #ifdef SEPTFA_EXP_ONE_TAP
                       make_ns_desc(b_addr, 256u, 128u), IDESC_MINI, 0);
 #else
+#ifdef SEPTFA_EXP_ONE_TAP
+                      make_ns_desc(b_addr, 256u, 128u), IDESC_MINI, 0);
+#else
                       make_ns_desc(b_addr, 256u, 128u), IDESC_MINI, k != 0);
+#endif
 #endif
           }
         }

@@ -589,6 +589,61 @@ def test_tensor_core_depthwise_kernel_equals_cuda_core_producer(cuda_models, B, 
     assert np.abs(v1.cpu().numpy() - ref_vad).max() < 1e-3
 
 
+@pytest.mark.parametrize("B,L", [(3, 64000), (2, 40000), (1, 200000), (5, 33000), (1, 33024), (7, 48000)])
+def test_pair_dconv_kernel_equals_single_cta_kernel(cuda_models, B, L):
+    """dconv_mma2.cu (CTA pairs, cta_group::2 MMAs, res_out weights resident in shared memory, edge warp, TMA tensor stores)
+    against dconv_mma.cu (one CTA per tile, weight stream) on the same buffers: same arithmetic up to the association of the
+    edge corrections and the fp16 partial sums of the column means; even and odd tile counts, utterance boundaries inside
+    tiles, a tile pair with an empty tile; run-to-run bit-reproducible; both within the band of the oracle."""
+    from oracle import septfa_oracle as O
+    args = synth.CONFIG_WITH_VAD
+    m = cuda_models(args, 34, 0)
+    xh = synth.make_mixtures(B, L, 781)
+    x = torch.from_numpy(xh).cuda()
+    try:
+        m.set_option("dconv_pair", 0)
+        o0, v0, _ = m(x, {})
+        m.set_option("dconv_pair", 1)
+        o1, v1, _ = m(x, {})
+        o2, v2, _ = m(x, {})
+    finally:
+        m.set_option("dconv_pair", 1)
+    tail = (L % 256) if (L % 256) > 200 else 0     # samples only the last frame covers: overlap-add envelope ~1e-8 (SURVEY A.10)
+    assert (o1 - o0)[..., :L - tail].abs().max().item() < 5e-4
+    assert (v1 - v0).abs().max().item() < 1e-3
+    assert torch.equal(o1, o2) and torch.equal(v1, v2)
+    W = O.OracleWeights(synth.make_state_dict_numpy(args, 34), args, np.float64)
+    _, ref_vad, _, _ = O.forward(xh, W, {})
+    assert np.abs(v1.cpu().numpy() - ref_vad).max() < 1e-3
+
+
+def test_half_stream_mode_is_opt_in_and_close(cuda_models):
+    """Option "stream_half" (off by default): blocks 1 .. n-1 carry the residual stream as fp16 - written by the residual
+    kernel, read by TMA as the A operand of gemm_conv1_tma.cu. 11 % faster, but the stream's rounding random-walks through
+    all 24 blocks (worst VAD error on the shape sweep 9.5e-4 against 2.1e-4), so it stays outside the default parity
+    envelope: checked here against the default mode with its own, looser bounds."""
+    from oracle import septfa_oracle as O
+    args = synth.CONFIG_WITH_VAD
+    m = cuda_models(args, 31, 0)
+    xh = synth.make_mixtures(3, 64000, 4242)
+    x = torch.from_numpy(xh).cuda()
+    o0, v0, _ = m(x, {})
+    try:
+        m.set_option("stream_half", 1)
+        o1, v1, _ = m(x, {})
+        o2, v2, _ = m(x, {})
+    finally:
+        m.set_option("stream_half", 0)
+    o3, v3, _ = m(x, {})
+    assert torch.equal(o0, o3) and torch.equal(v0, v3)          # the default path is unchanged by the round trip
+    assert torch.equal(o1, o2) and torch.equal(v1, v2)
+    assert not torch.equal(o0, o1)                              # the option does select another path
+    W = O.OracleWeights(synth.make_state_dict_numpy(args, 31), args, np.float64)
+    ref_out, ref_vad, _, _ = O.forward(xh, W, {})
+    assert np.abs(v1.cpu().numpy() - ref_vad).max() < 2e-3
+    assert sisdr_db(o1.cpu().numpy(), ref_out) >= 60.0
+
+
 def test_host_16bit_formats(cuda_models):
     """septfa_forward_host_submit_fmt: int16 PCM input (only_inference.py:68-81 on the device: astype float32 + min-max
     normalisation, bit-identical to numpy) and fp16 output (save_audio's `-ps 16` cast, utlis_inference.py:30-32)."""
