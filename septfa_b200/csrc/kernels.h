@@ -184,6 +184,19 @@ struct Conv1TmaParams {
 };
 cudaError_t conv1_tma_setup();
 void launch_conv1_tma(const Conv1TmaParams& p, cudaStream_t st);
+// gemm_conv1_pair.cu: conv1 on CTA pairs with TF32 operands (the fp32 stream is the A operand itself, fed by TMA; weights resident)
+struct Conv1PairParams {
+  const void* a_tmap;       // host pointer to a CUtensorMap over the fp32 stream [M rows][256], box 32 x 128, SWIZZLE_128B
+  StreamNorm norm;          // statistics of the stream (gamma == nullptr: y = w); the affine is folded into w_img / sb
+  int M, T, B;
+  const float* w_img;       // TF32 image of W1 * diag(gamma_in): 8 K-chunks x [256 rows x 128 B]
+  const float4* sb;         // [128] {S[2i], S[2i+1], b'[2i], b'[2i+1]}: row sums of the TF32 image, folded bias
+  float slope;
+  __half* p_planes; int Mp;
+  Stat2* st_p;
+};
+cudaError_t conv1_pair_setup();
+void launch_conv1_pair(const Conv1PairParams& p, cudaStream_t st);
 // gemm_conv1_persist.cu
 cudaError_t conv1_persist_setup();
 bool launch_conv1_persist(const Conv1Params& p, cudaStream_t st);   // false: not applicable, use launch_tc_conv1's kernel
@@ -231,6 +244,7 @@ struct LaunchCtx {
   int use_pdl = 1;             // launch with the programmatic-stream-serialization attribute
   int conv1_persist = 1;       // persistent warp-specialised conv1 kernel (0: always the one-tile-per-CTA kernel)
   int conv1_wres = 1;          // ... with the whole W1 image resident in shared memory (plane layout of p only)
+  int conv1_pair = 1;          // blocks 1 .. n-1, recursive-LN wiring, fast mode: TF32 CTA-pair conv1 fed by TMA from the fp32 stream
   int stream_half = 0;         // opt-in: blocks 1 .. n-1 carry the residual stream as fp16 (recursive-LN wiring, fast precision
                                // mode). 11 % faster, but the stream's rounding random-walks through all blocks: worst VAD
                                // error on the shape sweep 9.5e-4 against 2.1e-4 - outside the default parity envelope

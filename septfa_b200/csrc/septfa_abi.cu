@@ -27,6 +27,7 @@ struct KeySpec {
 };
 
 struct DevBlock {
+  const float* w1_img32; const float4* sb1_32;   // gemm_conv1_pair.cu: TF32 image of W1 diag(gamma), {row sums, folded bias}
   const float4* sb1;   // gemm_conv1_tma.cu: {S[2i], S[2i+1], b1f[2i], b1f[2i+1]}
   const __half* w1_img; const __half* w1_img_lo; const __half* w3_img_lo; const float* w1_t; const float* b1; const float* b1f; float a1; const float* g1; const float* be1;
   const float4* w2b; const float4* w2f; const float* c2f; float a2; int dil;
@@ -266,7 +267,7 @@ bool make_weight_tmap(CUtensorMap* out, const void* gptr, int rows) {
 
 // CUtensorMap over the fp16 residual stream [rows][256]: box = 64 halves x 128 rows with the 128-byte swizzle, i.e. one
 // K-chunk of a 128-frame tile lands in shared memory as a K-major SWIZZLE_128B tcgen05 operand (rows past `rows`: zeros).
-bool make_stream_tmap(CUtensorMap* out, const void* gptr, int64_t rows, int box_rows = 128) {
+bool make_stream_tmap(CUtensorMap* out, const void* gptr, int64_t rows, int box_rows = 128, bool f32 = false) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -281,10 +282,10 @@ bool make_stream_tmap(CUtensorMap* out, const void* gptr, int64_t rows, int box_
     fn = reinterpret_cast<EncodeFn>(sym);
   }
   const cuuint64_t dims[2] = {(cuuint64_t)kC, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)kC * 2};
-  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)kC * (f32 ? 4 : 2)};
+  const cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)box_rows};   // 128-byte rows either way
   const cuuint32_t estr[2] = {1, 1};
-  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -412,6 +413,7 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
   if (e == cudaSuccess) e = resid_fused_setup();
   if (e == cudaSuccess) e = conv1_persist_setup();
   if (e == cudaSuccess) e = conv1_tma_setup();
+  if (e == cudaSuccess) e = conv1_pair_setup();
   if (e == cudaSuccess) e = dconv_mma2_setup();
   if (e == cudaSuccess) e = dconv_mma_setup();
   if (e != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, std::string("tc_gemm_setup: ") + cudaGetErrorString(e)); }
@@ -477,6 +479,10 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "conv1_persist") == 0) {
     h->lctx.conv1_persist = value ? 1 : 0;
+    return 0;
+  }
+  if (std::strcmp(name, "conv1_pair") == 0) {
+    h->lctx.conv1_pair = value ? 1 : 0;
     return 0;
   }
   if (std::strcmp(name, "stream_half") == 0) {
@@ -598,6 +604,27 @@ int septfa_commit_weights(septfa_handle* h) {
         const float* sp = nullptr;
         if (upload(h, sb, &sp)) return SEPTFA_E_CUDA;
         d.sb1 = reinterpret_cast<const float4*>(sp);
+      }
+      {
+        // TF32 operand image (gemm_conv1_pair.cu): weights rounded to nearest at 11 significant bits, 8 K-chunks of 32 floats,
+        // each chunk = 256 rows x 128 B, K-major with the 128-byte swizzle (16-byte unit index XOR row % 8)
+        auto tf32_rn = [](float v) { uint32_t b; std::memcpy(&b, &v, 4); b = (b + 0x1000u) & 0xFFFFE000u; std::memcpy(&v, &b, 4); return v; };
+        std::vector<float> img((size_t)kC * kC, 0.f), sb(4 * 128);
+        for (int n = 0; n < kC; ++n) {
+          double srow = 0.0;
+          for (int k = 0; k < kC; ++k) {
+            const float v = tf32_rn((float)wf[(size_t)n * kC + k]);
+            srow += (double)v;
+            const int j = k >> 5, kk = k & 31;
+            const size_t byte = (size_t)j * 256 * 128 + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((kk >> 2) ^ (n & 7)) << 4) + (size_t)(kk & 3) * 4;
+            img[byte / 4] = v;
+          }
+          sb[(n / 2) * 4 + (n & 1)] = (float)srow;
+          sb[(n / 2) * 4 + 2 + (n & 1)] = b1f[n];
+        }
+        const float* sp = nullptr;
+        if (upload(h, img, &d.w1_img32) || upload(h, sb, &sp)) return SEPTFA_E_CUDA;
+        d.sb1_32 = reinterpret_cast<const float4*>(sp);
       }
       if (upload(h, pack_image(wf, kC, kC, 1, 256), &d.w1_img) || upload(h, pack_image(split_lo(wf), kC, kC, 1, 256), &d.w1_img_lo) ||
           upload(h, wt, &d.w1_t) ||
@@ -866,6 +893,10 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   if (stream_half && !make_stream_tmap(&wh_tmap, ws.wh, M)) return fail(h, SEPTFA_E_CUDA, "cuTensorMapEncodeTiled failed for the fp16 stream");
   // CTA-pair dconv kernel (dconv_mma2.cu): cta_group::2 MMAs, res_out weights resident in shared memory
   const bool pair = planes && h->lctx.dconv_pair;
+  // TF32 CTA-pair conv1 (gemm_conv1_pair.cu) for blocks 1 .. n-1: the fp32 stream is its A operand, fetched by TMA
+  const bool c1pair = planes && !stream_half && h->lctx.conv1_pair && h->ln_mode == LN_RECURSIVE && h->nblk > 1;
+  alignas(64) CUtensorMap w32_tmap;
+  if (c1pair && !make_stream_tmap(&w32_tmap, ws.w, M, 128, true)) return fail(h, SEPTFA_E_CUDA, "cuTensorMapEncodeTiled failed for the fp32 stream");
   alignas(64) CUtensorMap racc_tmap;   // the pair kernel's epilogue stores racc with TMA tensor stores (boxes of 32 rows x 64 columns)
   if (pair && !make_stream_tmap(&racc_tmap, ws.racc, M, 32)) return fail(h, SEPTFA_E_CUDA, "cuTensorMapEncodeTiled failed for racc");
   const double inv_n = 1.0 / ((double)kC * T);
@@ -886,6 +917,9 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     if (stream_half && i > 0) {
       Conv1TmaParams ct{&wh_tmap, norm, M, T, B, d.w1_img, d.sb1, d.a1, reinterpret_cast<__half*>(ws.p), Mp, st_p};
       launch_conv1_tma(ct, st);
+    } else if (c1pair && i > 0) {
+      Conv1PairParams cp{&w32_tmap, norm, M, T, B, d.w1_img32, d.sb1_32, d.a1, reinterpret_cast<__half*>(ws.p), Mp, st_p};
+      launch_conv1_pair(cp, st);
     } else if (tc_conv1) {
       launch_tc_conv1(c1, st);
     } else {

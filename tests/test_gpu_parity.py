@@ -617,6 +617,36 @@ def test_pair_dconv_kernel_equals_single_cta_kernel(cuda_models, B, L):
     assert np.abs(v1.cpu().numpy() - ref_vad).max() < 1e-3
 
 
+@pytest.mark.parametrize("B,L", [(3, 64000), (1, 200000), (5, 33000)])
+def test_tf32_pair_conv1_equals_persistent_conv1(cuda_models, B, L):
+    """gemm_conv1_pair.cu (blocks 1 .. n-1: the fp32 stream is the TF32 A operand itself, fetched by TMA; CTA pairs with the
+    TF32 weight image resident; normalisation applied to the accumulator) against gemm_conv1_persist.cu (producer warps
+    normalise and round to fp16): same precision class (11 significant bits in both operands), different roundings; both
+    within the band of the oracle, bit-reproducible."""
+    from oracle import septfa_oracle as O
+    args = synth.CONFIG_WITH_VAD
+    m = cuda_models(args, 34, 0)
+    xh = synth.make_mixtures(B, L, 783)
+    x = torch.from_numpy(xh).cuda()
+    try:
+        m.set_option("conv1_pair", 0)
+        o0, v0, _ = m(x, {})
+        m.set_option("conv1_pair", 1)
+        o1, v1, _ = m(x, {})
+        o2, v2, _ = m(x, {})
+    finally:
+        m.set_option("conv1_pair", 1)
+    tail = (L % 256) if (L % 256) > 200 else 0
+    assert (o1 - o0)[..., :L - tail].abs().max().item() < 5e-4
+    assert (v1 - v0).abs().max().item() < 1e-3
+    assert not torch.equal(o1, o0)
+    assert torch.equal(o1, o2) and torch.equal(v1, v2)
+    W = O.OracleWeights(synth.make_state_dict_numpy(args, 34), args, np.float64)
+    _, ref_vad, _, _ = O.forward(xh, W, {})
+    assert np.abs(v1.cpu().numpy() - ref_vad).max() < 1e-3
+    assert np.abs(v0.cpu().numpy() - ref_vad).max() < 1e-3
+
+
 def test_half_stream_mode_is_opt_in_and_close(cuda_models):
     """Option "stream_half" (off by default): blocks 1 .. n-1 carry the residual stream as fp16 - written by the residual
     kernel, read by TMA as the A operand of gemm_conv1_tma.cu. 11 % faster, but the stream's rounding random-walks through
