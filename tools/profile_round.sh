@@ -12,7 +12,8 @@ $PY > $OUT/plain_${TAG}.log 2>&1 || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file $OUT/launches_${TAG}.csv $PY > $OUT/ncu_launches_${TAG}.log 2>&1
 # 2. per forward: memsets, 1 frontend, (export), 24 x (conv1, dconv, resid), out_stats, outconv, vad_final, istft, export = 79 launches.
 #    block kernels: frontend + first block of the 4th forward
-ncu --set full --clock-control none --import-source on -k regex:"k_frontend|k_conv1_persist|k_dconv_mma|k_resid_persist" -s 219 -c 4 \
+#    (per forward 1 k_frontend + 23 k_conv1_pair + 24 k_dconv_mma2 + 24 k_resid_persist = 72 matches; block 0's conv1 is k_conv1_persist)
+ncu --set full --clock-control none --import-source on -k regex:"k_frontend|k_conv1_pair|k_dconv_mma2|k_resid_persist" -s 216 -c 4 \
     -o $OUT/prof_block_${TAG} -f $PY > $OUT/ncu_block_${TAG}.log 2>&1
 #    output conv = the only k_tc_gemm launch of a forward at this configuration
 ncu --set full --clock-control none --import-source on -k regex:"k_tc_gemm" -s 3 -c 1 \

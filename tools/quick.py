@@ -32,7 +32,8 @@ for B, L in shapes:
           f"finite {bool(torch.isfinite(o1).all())} reproducible {torch.equal(o1, o2) and torch.equal(v1, v2)}", flush=True)
 x = torch.from_numpy(np.tile(synth.make_mixtures(8, 64000, 1), (32, 1))).cuda()
 kw = dict(synth.DEFAULT_INFERENCE_KW, filter_signals_by_smo_vad=True)
-m.materialize.update(estimated_stfts=False, mask_per_speaker=False, spectrum=False, masks_b=False)
+if not os.environ.get("QUICK_EXPORTS"):
+    m.materialize.update(estimated_stfts=False, mask_per_speaker=False, spectrum=False, masks_b=False)
 ab = os.environ.get("QUICK_AB")
 for mode in ((0, 1) if ab else (None,)):
     if ab: m.set_option(ab, mode)
