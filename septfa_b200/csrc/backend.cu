@@ -93,7 +93,7 @@ void launch_vad(const VadParams& p, cudaStream_t st) {
 //   out[256 j + n] = (w[256+n] fr_j[256+n] + w[n] fr_{j+1}[n]) / (w[256+n]^2 + w[n]^2)        (:460)
 constexpr int kIstftBlocks = 15;   // output blocks per CTA = 16 frames in 4 rounds of 4 FFTs (one frame of overlap with the neighbour CTA: 6 % redundant)
 
-__global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S, const float* __restrict__ logits,
+__global__ void __launch_bounds__(256, 3) k_mask_istft(const float2* __restrict__ S, const float* __restrict__ logits,
                                                     const float* __restrict__ gate, const float* __restrict__ window,
                                                     const float2* __restrict__ twiddle, int64_t L, int T,
                                                     float* __restrict__ out) {
@@ -112,33 +112,52 @@ __global__ void __launch_bounds__(256) k_mask_istft(const float2* __restrict__ S
   float* out0 = out + ((int64_t)b * 2) * L;
   float* out1 = out0 + L;
   const int t_last = min(j0 + kIstftBlocks, T - 1);   // frames j0 .. t_last
+  // A frame's operands (its row of S, its two rows of mask logits, its gates) are fetched one round AHEAD into registers:
+  // the loads of round r + 1 are in flight during the FFT and the overlap-add of round r. Without that every round began
+  // with a full HBM latency that only the other CTAs of the SM could cover (issue-active 36 %).
+  struct FrameOps { float2 sv[4]; float l0[4], l1[4]; float g0, g1; };
+  auto fetch = [&](int round, FrameOps& fo) {
+    const int t = j0 + round * 4 + grp;
+    if (t <= t_last) {
+      const int64_t row = (int64_t)b * T + t;
+      fo.g0 = fo.g1 = 1.f;
+      if (gate != nullptr) {
+        fo.g0 = __ldg(gate + ((int64_t)b * 2) * T + t);
+        fo.g1 = __ldg(gate + ((int64_t)b * 2 + 1) * T + t);
+      }
+      const float* lr = logits + row * kLogitStride;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int f = j + 64 * r, ff = f >= 1 ? f : 256;   // the thread of bin 0 (DC: zero) takes the Nyquist bin
+        fo.sv[r] = __ldg(S + row * kBins + ff);
+        fo.l0[r] = __ldg(lr + ff);
+        fo.l1[r] = __ldg(lr + kBins + ff);
+      }
+    }
+  };
+  FrameOps fa, fb;
+  fetch(0, fa);
+#pragma unroll
   for (int round = 0; round < (kIstftBlocks + 1) / 4; ++round) {
     const int tbase = j0 + round * 4;
     if (tbase > t_last) break;                        // uniform
     const int t = tbase + grp;                        // this group's frame
     const bool vt = t <= t_last;
+    FrameOps& cur = (round & 1) ? fb : fa;
     __syncthreads();                                  // previous round's reads of buf are done
+    if (round + 1 < (kIstftBlocks + 1) / 4) fetch(round + 1, (round & 1) ? fa : fb);
     if (vt) {
-      const int64_t row = (int64_t)b * T + t;
-      float g0 = 1.f, g1 = 1.f;
-      if (gate != nullptr) {
-        g0 = __ldg(gate + ((int64_t)b * 2) * T + t);
-        g1 = __ldg(gate + ((int64_t)b * 2 + 1) * T + t);
-      }
-      const float* lr = logits + row * kLogitStride;
       float2* bg = buf[grp];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int f = j + 64 * r;  // 0..255
+        const float2 sv = cur.sv[r];
+        const float m0 = sigmoidf_fast(cur.l0[r]) * cur.g0, m1 = sigmoidf_fast(cur.l1[r]) * cur.g1;
         if (f >= 1) {
-          const float2 sv = __ldg(S + row * kBins + f);
-          const float m0 = sigmoidf_fast(__ldg(lr + f)) * g0, m1 = sigmoidf_fast(__ldg(lr + kBins + f)) * g1;
           const float a0 = sv.x * m0, b0 = sv.y * m0, a1 = sv.x * m1, b1 = sv.y * m1;
           bg[fft_idx(f)] = make_float2(a0 - b1, b0 + a1);               // E0[f] + i E1[f]
           bg[fft_idx(kNfft - f)] = make_float2(a0 + b1, a1 - b0);       // conj(E0[f]) + i conj(E1[f])
         } else {
-          const float2 sv = __ldg(S + row * kBins + 256);
-          const float m0 = sigmoidf_fast(__ldg(lr + 256)) * g0, m1 = sigmoidf_fast(__ldg(lr + kBins + 256)) * g1;
           bg[fft_idx(0)] = make_float2(0.f, 0.f);                       // DC bin is zero
           bg[fft_idx(256)] = make_float2(sv.x * m0, sv.x * m1);         // irfft ignores the imaginary part of Nyquist
         }
