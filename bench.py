@@ -404,27 +404,28 @@ def main():
     t_e2e_sync = gather_max_time(time.perf_counter() - t0)
     assert out_h[0].shape == (B, 2, L)
 
-    # ---- the same through the batch-stream API (forward_host_submit / result, two slots): every step still copies
+    # ---- the same through the batch-stream API (forward_host_submit / result, three slots in rotation): every step still copies
     # its input from pinned host memory and its results back to pinned host memory; successive steps overlap their
     # PCIe copies with each other's kernels, which is how a file loop (only_inference.py:80-100) would call it.
     # The timed region runs from the first submit to the last result (pipeline fill and drain included).
     def stream_leg(xs, out_dtype):
-        outs = [torch.empty((B, 2, L), dtype=out_dtype, pin_memory=True) for _ in range(2)]
-        vads = [torch.empty((B, 2, T), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        NS = 3   # pipeline slots in rotation: with two, the copy-in of step i + 1 queues behind the copy-out of step i - 1
+        outs = [torch.empty((B, 2, L), dtype=out_dtype, pin_memory=True) for _ in range(NS)]
+        vads = [torch.empty((B, 2, T), dtype=torch.float32, pin_memory=True) for _ in range(NS)]
 
         def stream_steps(n):
-            pend = [None, None]
+            pend = [None] * NS
             for i in range(n):
-                sl = i & 1
+                sl = i % NS
                 if pend[sl] is not None:
                     pend[sl].result()
-                pend[sl] = model.forward_host_submit(xs[sl], kw, device=local_rank, slot=sl, out=outs[sl], vad=vads[sl],
+                pend[sl] = model.forward_host_submit(xs[i & 1], kw, device=local_rank, slot=sl, out=outs[sl], vad=vads[sl],
                                                      out_dtype=out_dtype)
             for f in pend:
                 if f is not None:
                     f.result()
 
-        stream_steps(3)
+        stream_steps(4)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -496,7 +497,7 @@ def main():
         n_mine = shard_range(total, rank, world)[1] - shard_range(total, rank, world)[0]
         nb = n_mine // B
         xs = [x_host, x_host.clone().pin_memory()]
-        for _ in model.forward_host_stream((xs[i & 1] for i in range(4)), kw, device=local_rank, reuse_outputs=True):
+        for _ in model.forward_host_stream((xs[i & 1] for i in range(6)), kw, device=local_rank, reuse_outputs=True):
             pass
         if world > 1:
             dist.barrier()
@@ -614,7 +615,7 @@ def main():
                              "what": "pinned H2D and D2H copies of one step's bytes, both directions at once, all ranks at the "
                                      "same time, no kernels: the copy-only floor of a step on this box"},
                     "api": "SeparationModel.forward_host_submit / HostBatch.result (septfa_forward_host_submit_fmt / _wait), "
-                           "two batches in flight; pinned host input and output per step; fill and drain inside the timing"},
+                           "three batches in flight (pipeline slots in rotation); pinned host input and output per step; fill and drain inside the timing"},
             "e2e_sync": {"value": audio_s / t_e2e_sync, "unit": "audio-s/s", "ms_per_step": 1e3 * t_e2e_sync / a.steps,
                          "api": "SeparationModel.forward_host (septfa_forward_host): one synchronous call per step, "
                                 "two-chunk copy/compute pipeline inside the call"},

@@ -1133,7 +1133,7 @@ int septfa_forward_host_submit_fmt(septfa_handle* h, int slot, const void* x_hos
   if (int rc = check_forward_args(h, B, L)) return rc;
   if (x_fmt != SEPTFA_FMT_F32 && x_fmt != SEPTFA_FMT_PCM16) return fail(h, SEPTFA_E_INVALID, "x_fmt must be SEPTFA_FMT_F32 or SEPTFA_FMT_PCM16");
   if (out_fmt != SEPTFA_FMT_F32 && out_fmt != SEPTFA_FMT_F16) return fail(h, SEPTFA_E_INVALID, "out_fmt must be SEPTFA_FMT_F32 or SEPTFA_FMT_F16");
-  if (slot < 0 || slot >= SEPTFA_HOST_SLOTS) return fail(h, SEPTFA_E_INVALID, "slot must be 0 or 1");
+  if (slot < 0 || slot >= SEPTFA_HOST_SLOTS) return fail(h, SEPTFA_E_INVALID, "slot must be 0 .. SEPTFA_HOST_SLOTS - 1");
   if (!x_host || !out_wav_host) return fail(h, SEPTFA_E_INVALID, "null host buffer");
   auto& sl = h->slots[slot];
   if (sl.busy) return fail(h, SEPTFA_E_STATE, "slot has a batch in flight: call septfa_forward_host_wait first");
@@ -1205,7 +1205,7 @@ int septfa_forward_host_submit_fmt(septfa_handle* h, int slot, const void* x_hos
 
 int septfa_forward_host_wait(septfa_handle* h, int slot) {
   if (!h) return SEPTFA_E_INVALID;
-  if (slot < 0 || slot >= SEPTFA_HOST_SLOTS) return fail(h, SEPTFA_E_INVALID, "slot must be 0 or 1");
+  if (slot < 0 || slot >= SEPTFA_HOST_SLOTS) return fail(h, SEPTFA_E_INVALID, "slot must be 0 .. SEPTFA_HOST_SLOTS - 1");
   auto& sl = h->slots[slot];
   if (!sl.busy) return fail(h, SEPTFA_E_STATE, "slot has no batch in flight");
   CUDA_TRY(h, cudaSetDevice(h->device));

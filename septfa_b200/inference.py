@@ -132,7 +132,7 @@ def separate_files(model, paths, save_dir, inference_kw=None, precision_save=32,
     """The file loop either side of the forward, batched: 16-bit mono 16 kHz wav files of
     EQUAL length are grouped into batches; each batch travels to the device as int16 PCM, is converted and min-max
     normalised there (only_inference.py:69,81, bit-identical to numpy), separated, and comes back as float32 or - for
-    ``precision_save=16`` - float16, two batches in flight (forward_host_stream). Other files (stereo, other rates or
+    ``precision_save=16`` - float16, three batches in flight (forward_host_stream). Other files (stereo, other rates or
     sample formats) take the single-file path of :func:`read_mixture`. Writes ``<stem>_Speaker_{0,1}.wav`` into
     ``save_dir`` (float32 wav, or 16-bit PCM for precision 16) and returns ``{path: vad [2, T]}``."""
     from scipy.io.wavfile import read, write

@@ -260,8 +260,9 @@ class SeparationModel(nn.Module):
     def forward_host_submit(self, x_host: torch.Tensor, inference_kw={}, device=0, slot=0, out=None, vad=None,
                             out_dtype=torch.float32):
         """Asynchronous half of :meth:`forward_host` (septfa_forward_host_submit_fmt): enqueue copy-in, forward and
-        copy-out of one batch on pipeline slot 0 or 1 and return a :class:`HostBatch` whose ``result()`` waits for
-        it. Two slots let successive batches overlap their PCIe copies with each other's kernels. ``x_host`` is
+        copy-out of one batch on a pipeline slot (0 .. 3) and return a :class:`HostBatch` whose ``result()`` waits for
+        it. Slots in rotation (three keep the pipeline full) let successive batches overlap their PCIe copies with each
+        other's kernels. ``x_host`` is
         pinned if it is not already; ``out`` / ``vad`` may be caller-provided pinned result tensors (reused across
         batches), otherwise fresh pinned tensors are allocated.
 
@@ -301,20 +302,22 @@ class SeparationModel(nn.Module):
 
     def forward_host_stream(self, batches, inference_kw={}, device=0, out_dtype=torch.float32, reuse_outputs=False):
         """Generator over an iterable of host batches ``[B, L]`` (the loop of only_inference.py:80-100 over a data
-        loader): yields ``(out_separation, output_vad)`` per batch, in order, keeping two batches in flight. Batches
+        loader): yields ``(out_separation, output_vad)`` per batch, in order, keeping three batches in flight. Batches
         may be float32 (normalised) or int16 PCM; ``out_dtype`` as in :meth:`forward_host_submit`.
-        ``reuse_outputs=True`` recycles three sets of pinned result buffers instead of page-locking fresh memory for
+        ``reuse_outputs=True`` recycles five sets of pinned result buffers instead of page-locking fresh memory for
         every batch (cudaHostAlloc of 130 MB costs more than the batch's forward): a yielded result then stays valid
         until TWO further results have been yielded - enough for a loop that writes each result out before asking for
         the next."""
         pending = []
-        pool = {}
+        # pinned result sets are kept on the module between calls (page-locking 130 MB costs ~15 ms: more than four forwards)
+        pool = self.__dict__.setdefault("_host_result_pool", {})
+        depth = 3   # batches in flight (pipeline slots in rotation): see include/septfa.h
 
         def buffers(i, xb):
             if not reuse_outputs:
                 return None, None
             B, L = xb.shape
-            key = (B, L, i % 3)
+            key = (B, L, str(out_dtype), i % (depth + 2))
             if key not in pool:
                 pool[key] = (torch.empty((B, self.num_spk, L), dtype=out_dtype, pin_memory=True),
                              torch.empty((B, self.num_spk, _lib.num_frames(L)), dtype=torch.float32, pin_memory=True)
@@ -322,10 +325,10 @@ class SeparationModel(nn.Module):
             return pool[key]
 
         for i, xb in enumerate(batches):
-            if len(pending) == 2:
+            if len(pending) == depth:
                 yield pending.pop(0).result()
             o, v = buffers(i, xb)
-            pending.append(self.forward_host_submit(xb, inference_kw, device, slot=i & 1, out=o, vad=v, out_dtype=out_dtype))
+            pending.append(self.forward_host_submit(xb, inference_kw, device, slot=i % depth, out=o, vad=v, out_dtype=out_dtype))
         while pending:
             yield pending.pop(0).result()
 
