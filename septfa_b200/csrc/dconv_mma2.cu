@@ -137,6 +137,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, int c0, in
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(ssrc))
                : "memory");
 }
+// One lane of a fully converged warp (elect.sync). The MMA issuers run their loops with the WHOLE warp (all lanes poll the
+// barriers) and predicate the tcgen05 instructions on this: inside an `if (lane == 0)` region the compiler wraps every
+// uniform-datapath instruction (UTCHMMA, UTCBAR) in its own elect / branch loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // tcgen05.st without the wait (follow with tmem_st_wait())
 __device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -331,7 +339,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
           }
         }
       }
-    } else if (lane == 0) {
+    } else {
       // ---------------------------------------------------------- depthwise mini-GEMM issuer (leader CTA). A thread of its own:
       // issuing a tcgen05.mma costs its thread ~100 cycles whatever the shape, so one thread issuing the 6 mini-MMAs and the 4
       // res_out MMAs of a chunk (~1.7 k cycles) set the pace of the whole pair.
@@ -345,8 +353,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
         mbar_wait(p_peer + sp, up & 1, 205 + j);
         if (ub > 0) mbar_wait(d1_empty + b, (ub - 1) & 1, 210 + j);
         tc_fence_after();
-        DTL(2, gi);
+        if (lane == 0) DTL(2, gi);
         const uint32_t slab = smem_u32(smem + kOffP + sp * kPChunkBytes);
+        if (elect_one()) {
 #pragma unroll
 #ifdef SEPTFA_EXP_ONE_TAP
         for (int k = 1; k < 2; ++k) {
@@ -375,12 +384,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
         }
         umma2_commit(d1_full + b, (uint16_t)3);
         umma2_commit(p_empty + sp, (uint16_t)3);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
   } else if (warp == 2) {
     // ------------------------------------------------------------ res_out MMA issuer (leader CTA)
-    if (leader && lane == 0) {
+    if (leader) {
       const int total = my_tiles * 8;
       for (int gm = 0; gm < total; ++gm) {
         const int j = gm & 7, lt = gm >> 3, ba = gm % kD1Bufs, ua = gm / kD1Bufs;
@@ -388,14 +399,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
         if (lt == 0) { mbar_wait(w_full + j, 0, 230 + j); mbar_wait(w_peer + j, 0, 235 + j); }
         mbar_wait(a2_full + ba, ua & 1, 240 + j);
         tc_fence_after();
-        DTL(3, gm);
+        if (lane == 0) DTL(3, gm);
         const uint32_t a_tmem = tmem_base + 256u + (uint32_t)(ba * 64);   // q: K 0..31 at +0..15, K 32..63 at +32..47
         const uint64_t b_desc = make_sw128_desc(smem_u32(smem + kOffW + j * kWHalfBytes));
+        if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma2_f16_ts(tmem_base, a_tmem + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8), b_desc + (uint64_t)(kk * 2), IDESC_MAIN, (j | kk) != 0);
         umma2_commit(d1_empty + ba, (uint16_t)1);
         if (j == 7) umma2_commit(d2_full, (uint16_t)3);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -449,8 +463,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
             float2 qv;
             if constexpr (AMAX) qv = make_float2(fmaxf(x.x, ax.x), fmaxf(x.y, ax.y));
             else qv = make_float2(fminf(x.x, ax.x), fminf(x.y, ax.y));
+#ifndef SEPTFA_EXP_NO_STATS
             accS = __fadd2_rn(accS, qv);
             accQ = __ffma2_rn(qv, qv, accQ);
+#endif
             h[i * 4 + k] = pack_half2(qv.x, qv.y);
           }
         }
