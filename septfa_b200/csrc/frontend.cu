@@ -38,7 +38,8 @@ struct GateK { float k[9]; float bias, slope; int enabled; };
 __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, int64_t L, int T,
                                                   const float* __restrict__ window, const float2* __restrict__ twiddle,
                                                   GateK gk, float2* __restrict__ S, float* __restrict__ z0,
-                                                  float* __restrict__ dc_gated, Stat2* __restrict__ st0) {
+                                                  float* __restrict__ dc_gated, Stat2* __restrict__ st0,
+                                                  float* __restrict__ spectrum /*[B,257,T] or null*/) {
   __shared__ float2 buf[4][kFftPad];
   __shared__ float2 tw[kNfft];
   __shared__ float win[kNfft];
@@ -152,7 +153,12 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
     };
     const float z = gate(tid + 1);
     z0[row * kC + tid] = z;
-    if (tid == 0) dc_gated[row] = gate(0);
+    if (spectrum != nullptr) spectrum[((int64_t)b * kBins + tid + 1) * T + t] = z;   // the optional torch-layout export (model.py:421)
+    if (tid == 0) {
+      const float zd = gate(0);
+      dc_gated[row] = zd;
+      if (spectrum != nullptr) spectrum[((int64_t)b * kBins) * T + t] = zd;
+    }
     s += z;
     ss += z * z;
   }
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
 
 void launch_frontend(const float* x, int B, int64_t L, int T, const float* window, const float2* twiddle, int enabled,
                      const float* k3x3, float bias, float slope, float2* S, float* z0, float* dc_gated, Stat2* st0,
-                     cudaStream_t st) {
+                     float* spectrum, cudaStream_t st) {
   GateK gk;
   for (int i = 0; i < 9; ++i) gk.k[i] = k3x3[i];  // Conv2d weight [1,1,3,3]: k[i*3+j], i = frequency tap, j = time tap
   gk.bias = bias;
@@ -169,7 +175,7 @@ void launch_frontend(const float* x, int B, int64_t L, int T, const float* windo
   gk.enabled = enabled;
   dim3 grid((T + kFrontFrames - 1) / kFrontFrames, B);
   // first kernel of the chain: it follows a memset, so it is launched without the PDL attribute
-  launch_k(k_frontend, grid, dim3(256), 0, st, false, x, L, T, window, twiddle, gk, S, z0, dc_gated, st0);
+  launch_k(k_frontend, grid, dim3(256), 0, st, false, x, L, T, window, twiddle, gk, S, z0, dc_gated, st0, spectrum);
 }
 
 }  // namespace septfa

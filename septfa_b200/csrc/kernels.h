@@ -146,7 +146,7 @@ struct ResidParams {
 void make_twiddles(float2* host256);
 void launch_frontend(const float* x, int B, int64_t L, int T, const float* window, const float2* twiddle, int enabled,
                      const float* k3x3, float bias, float slope, float2* S, float* z0, float* dc_gated, Stat2* st0,
-                     cudaStream_t st);
+                     float* spectrum /*optional [B,257,T] export, nullable*/, cudaStream_t st);
 // tcn.cu
 void launch_ref_conv1(const Conv1Params& p, cudaStream_t st);
 void launch_ref_dconv(const DconvParams& p, cudaStream_t st);

@@ -872,8 +872,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   prof_mark(h, SEPTFA_PROF_FRONTEND, st);
   CUDA_TRY(h, cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, st));
   launch_frontend(x, B, L, T, h->win_fwd, h->twiddle, c.activity_input_bool, h->act_k, h->act_b, h->act_a, ws.S, ws.w,
-                  ws.dcg, ws.st0, st);
-  if (spectrum) launch_export(ws.S, ws.logits, nullptr, ws.w, ws.dcg, B, T, nullptr, nullptr, spectrum, nullptr, st);
+                  ws.dcg, ws.st0, spectrum, st);   // (the optional spectrum export leaves from the front end's own rows)
 
   // Tensor-core depthwise kernel (dconv_mma.cu): p travels as K-group planes; its halo slots must read as zeros.
   const bool planes = half_io && T >= 128 && h->lctx.conv1_persist && h->lctx.dconv_mma && h->all_mma_ok;
