@@ -223,34 +223,37 @@ __global__ void __launch_bounds__(256) k_export(const float2* __restrict__ S, co
   pdl_wait();
   const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32, b = blockIdx.z >> 1, s = blockIdx.z & 1;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  // the spectrum-only call (before the TCN overwrites the stream in place) needs neither the logits nor S, and only
-  // its s == 0 blocks have work: it used to load 264 MB for nothing
+  // the spectrum-only call needs neither the logits nor S, and only its s == 0 blocks have work
   const bool need_masks = mask != nullptr || logits_out != nullptr || est != nullptr;
   if (!need_masks && s != 0) return;
-  for (int i = ty; i < 32; i += 8) {
-    const int t = t0 + i, f = f0 + tx;
-    if (t < T && f < kBins) {
-      const int64_t row = (int64_t)b * T + t;
-      if (need_masks) tl[i][tx] = __ldg(logits + row * kLogitStride + s * kBins + f);
-      if (est != nullptr) ts[i][tx] = __ldg(S + row * kBins + f);
-      if (spectrum != nullptr && s == 0) tz[i][tx] = (f == 0) ? __ldg(dc_gated + row) : __ldg(z0 + row * kC + f - 1);
+  // 64-bit address arithmetic once per CTA, 32-bit offsets inside the loops (the kernel is issue-bound: 67 % issue-active)
+  const int64_t row0 = (int64_t)b * T + t0;
+  const float* lg_in = logits + row0 * kLogitStride + s * kBins + f0;
+  const float2* s_in = S + row0 * kBins + f0;
+  const float* z_in = z0 + row0 * kC + f0 - 1;
+  const int nt = min(32, T - t0), nf = min(32, kBins - f0);
+  if (tx < nf) {
+    for (int i = ty; i < nt; i += 8) {
+      if (need_masks) tl[i][tx] = __ldg(lg_in + i * kLogitStride + tx);
+      if (est != nullptr) ts[i][tx] = __ldg(s_in + i * kBins + tx);
+      if (spectrum != nullptr && s == 0) tz[i][tx] = (f0 + tx == 0) ? __ldg(dc_gated + row0 + i) : __ldg(z_in + i * kC + tx);
     }
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int f = f0 + i, t = t0 + tx;
-    if (t < T && f < kBins) {
+  const int64_t o0 = (((int64_t)b * 2 + s) * kBins + f0) * T + t0;
+  const float g = (est != nullptr && gate != nullptr && tx < nt) ? __ldg(gate + ((int64_t)b * 2 + s) * T + t0 + tx) : 1.f;
+  if (tx < nt) {
+    for (int i = ty; i < nf; i += 8) {
       const float lg = need_masks ? tl[tx][i] : 0.f;
       const float m = sigmoidf_fast(lg);
-      const int64_t o = (((int64_t)b * 2 + s) * kBins + f) * T + t;
+      const int64_t o = o0 + i * T + tx;
       if (mask != nullptr) mask[o] = m;
       if (logits_out != nullptr) logits_out[o] = lg;  // [B, 514, T] with n = s*257 + f
       if (est != nullptr) {
-        const float g = gate != nullptr ? __ldg(gate + ((int64_t)b * 2 + s) * T + t) : 1.f;
         const float2 sv = ts[tx][i];
         est[o] = make_float2(sv.x * m * g, sv.y * m * g);
       }
-      if (spectrum != nullptr && s == 0) spectrum[((int64_t)b * kBins + f) * T + t] = tz[tx][i];
+      if (spectrum != nullptr && s == 0) spectrum[((int64_t)b * kBins + f0 + i) * T + t0 + tx] = tz[tx][i];
     }
   }
 }
