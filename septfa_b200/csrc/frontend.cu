@@ -35,6 +35,7 @@ struct GateK { float k[9]; float bias, slope; int enabled; };
 // torch.stft(center=True, pad_mode='reflect', onesided), no normalisation, DC bin zeroed (model.py:24,410);
 // P = 10 log10(max(|S|^2, 1e-10)); spectrum *= PReLU(Conv2d 3x3 (zero pad 1) over the (257, T) plane),
 // rows 1..256 feed the TCN (model.py:411-421).
+template <bool SPECTRUM>
 __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, int64_t L, int T,
                                                   const float* __restrict__ window, const float2* __restrict__ twiddle,
                                                   GateK gk, float2* __restrict__ S, float* __restrict__ z0,
@@ -153,11 +154,11 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
     };
     const float z = gate(tid + 1);
     z0[row * kC + tid] = z;
-    if (spectrum != nullptr) spectrum[((int64_t)b * kBins + tid + 1) * T + t] = z;   // the optional torch-layout export (model.py:421)
+    if constexpr (SPECTRUM) spectrum[((int64_t)b * kBins + tid + 1) * T + t] = z;   // the optional torch-layout export (model.py:421)
     if (tid == 0) {
       const float zd = gate(0);
       dc_gated[row] = zd;
-      if (spectrum != nullptr) spectrum[((int64_t)b * kBins) * T + t] = zd;
+      if constexpr (SPECTRUM) spectrum[((int64_t)b * kBins) * T + t] = zd;
     }
     s += z;
     ss += z * z;
@@ -175,7 +176,8 @@ void launch_frontend(const float* x, int B, int64_t L, int T, const float* windo
   gk.enabled = enabled;
   dim3 grid((T + kFrontFrames - 1) / kFrontFrames, B);
   // first kernel of the chain: it follows a memset, so it is launched without the PDL attribute
-  launch_k(k_frontend, grid, dim3(256), 0, st, false, x, L, T, window, twiddle, gk, S, z0, dc_gated, st0, spectrum);
+  if (spectrum != nullptr) launch_k(k_frontend<true>, grid, dim3(256), 0, st, false, x, L, T, window, twiddle, gk, S, z0, dc_gated, st0, spectrum);
+  else launch_k(k_frontend<false>, grid, dim3(256), 0, st, false, x, L, T, window, twiddle, gk, S, z0, dc_gated, st0, spectrum);
 }
 
 }  // namespace septfa

@@ -103,9 +103,12 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
   __shared__ float s_sc[8];
   __shared__ float s_nx[2][4];
   __shared__ __align__(8) uint64_t full;
+  __shared__ __align__(8) uint64_t xbar[2];     // [parity]: the peers' partials of v have arrived (16 bytes each, st.async)
 
   if (tid == 0) {
     mbar_init(&full, 1);
+    mbar_init(&xbar[0], 1);
+    mbar_init(&xbar[1], 1);
     fence_mbar_init();
   }
   FTL(0);
@@ -276,14 +279,25 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
       block_total(s2.x + s2.y, q2.x + q2.y, ts, tq);
       FTL(8 + it * 8 + 3);
       if (!peers_up) { cluster.barrier_wait(); peers_up = true; }   // every peer is running: its shared memory may be written
-      if (warp == 0 && lane < CS) {
-        double* rx = cluster.map_shared_rank(&xch[buf][0], lane);
-        rx[2 * rank] = ts;
-        rx[2 * rank + 1] = tq;
+      // Push-style exchange without a cluster barrier: every CTA sends its 16-byte partial to every peer with st.async, which
+      // counts the bytes on the RECEIVER's mbarrier; a CTA then waits for its own 8 x 16 bytes. (cluster.sync() is
+      // arrive.release + wait: the release fence first drained the previous utterance's 32 KB of global stores - MEMBAR /
+      // ERRBAR were 7 % of the kernel's stall samples - and every CTA then waited for the slowest peer's drain.) A peer can
+      // be at most one utterance ahead (it needs OUR next partial to go further), so two buffers / barriers suffice.
+      if (warp == 0) {
+        if (lane == 0) mbar_expect_tx(&xbar[buf], (uint32_t)CS * 16u);
+        if (lane < CS) {
+          uint32_t rdst, rbar;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(&xch[buf][2 * rank])), "r"((uint32_t)lane));
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&xbar[buf])), "r"((uint32_t)lane));
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(rdst),
+                       "l"(__double_as_longlong(ts)), "l"(__double_as_longlong(tq)), "r"(rbar)
+                       : "memory");
+        }
       }
-      cluster.sync();                        // release our stores / acquire the peers'
       FTL(8 + it * 8 + 4);
       if (tid == 0) {
+        mbar_wait(&xbar[buf], (it >> 1) & 1, 710);
         Stat2 tot{0.0, 0.0};
         for (int r = 0; r < CS; ++r) { tot.s += xch[buf][2 * r]; tot.ss += xch[buf][2 * r + 1]; }
         const float2 m = stat_mean_rstd(&tot, 1.0 / ((double)kC * p.T), 1e-5f);
