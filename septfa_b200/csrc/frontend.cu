@@ -64,22 +64,21 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
     const int la = 2 * (round * 4 + grp);  // local row of frame a (rows 0 and 15 are halo rows)
     const int ta = t0 - 1 + la, tb = ta + 1;
     const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
+    // sample index within the utterance in 32 bits (check_forward_args bounds L), reflect padding of 256 samples
+    const int Li = (int)L, ia0 = ta * kHop + j - kNfft / 2;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int n = j + 64 * r;
       float a = 0.f, c = 0.f;
-      if (va) {
-        int64_t i = (int64_t)ta * kHop + n - kNfft / 2;
-        if (i < 0) i = -i;
-        if (i >= L) i = 2 * (L - 1) - i;
-        a = __ldg(xb + i) * win[n];
-      }
-      if (vb) {
-        int64_t i = (int64_t)tb * kHop + n - kNfft / 2;
-        if (i < 0) i = -i;
-        if (i >= L) i = 2 * (L - 1) - i;
-        c = __ldg(xb + i) * win[n];
-      }
+      int i = ia0 + 64 * r;
+      int ib = i + kHop;
+      if (i < 0) i = -i;
+      if (i >= Li) i = 2 * (Li - 1) - i;
+      if (ib < 0) ib = -ib;
+      if (ib >= Li) ib = 2 * (Li - 1) - ib;
+      const float w = win[n];
+      if (va) a = __ldg(xb + i) * w;
+      if (vb) c = __ldg(xb + ib) * w;
       buf[grp][fft_idx(n)] = make_float2(a, c);
     }
     fft512_r8<false>(buf[grp], tw, j, grp);
@@ -115,6 +114,8 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
     }
     const bool wa = va && la >= 1 && la <= kFrontFrames;  // frames this CTA owns (not halo)
     const bool wb = vb && (la + 1) <= kFrontFrames;
+    float2* Sa = S + ((int64_t)b * T + ta) * kBins;        // row of frame a; frame b is the next row
+    float2* Sb = Sa + kBins;
     for (int f = j; f < kBins; f += 64) {
       float2 A = make_float2(0.f, 0.f), Bc = A;
       if (f > 0) {
@@ -129,39 +130,61 @@ __global__ void __launch_bounds__(256) k_frontend(const float* __restrict__ x, i
       // lg2.approx (2^-22 relative on a value of at most ~100 dB) instead of the ~30-instruction log10f
       if (va) P[la][f + 1] = 10.f * __log10f(fmaxf(A.x * A.x + A.y * A.y, 1e-10f));
       if (vb) P[la + 1][f + 1] = 10.f * __log10f(fmaxf(Bc.x * Bc.x + Bc.y * Bc.y, 1e-10f));
-      if (wa) S[((int64_t)b * T + ta) * kBins + f] = A;
-      if (wb) S[((int64_t)b * T + tb) * kBins + f] = Bc;
+      if (wa) Sa[f] = A;
+      if (wb) Sb[f] = Bc;
     }
     __syncthreads();  // buf is rewritten by the next round
   }
 
-  // activity gate; kernel index [i][j]: i over frequency, j over time (the input plane is [257, T])
+  // activity gate; kernel index [i][j]: i over frequency, j over time (the input plane is [257, T]). A thread owns bin
+  // tid + 1 (thread 0 also the DC bin) and walks the CTA's frames with a sliding 3 x 3 window: three shared-memory loads
+  // per frame instead of nine.
   float s = 0.f, ss = 0.f;
-  for (int lf = 1; lf <= kFrontFrames; ++lf) {
-    const int t = t0 + lf - 1;
-    if (t >= T) break;
-    const int64_t row = (int64_t)b * T + t;
-    auto gate = [&](int f) {
-      const float c = P[lf][f + 1];
-      if (!gk.enabled) return c;
-      float acc = 0.f;
+  {
+    const int nfr = min(kFrontFrames, T - t0);
+    const int fcol = tid + 1;                      // column of P: [0] = bin -1 (zero), [f + 1] = bin f
+    float k[9];
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 9; ++i) k[i] = gk.k[i];
+    // window w[jj][i] = P[lf - 1 + jj][fcol + i], jj = time tap, i = frequency tap
+    float w0[3], w1[3], w2[3], d0[3], d1[3], d2[3];   // bins tid .. tid + 2 around bin tid + 1; d*: bins -1 .. 1 around the DC bin
 #pragma unroll
-        for (int jj = 0; jj < 3; ++jj) acc += gk.k[i * 3 + jj] * P[lf - 1 + jj][f + i];
-      acc += gk.bias;
-      return c * prelu(acc, gk.slope);
-    };
-    const float z = gate(tid + 1);
-    z0[row * kC + tid] = z;
-    if constexpr (SPECTRUM) spectrum[((int64_t)b * kBins + tid + 1) * T + t] = z;   // the optional torch-layout export (model.py:421)
-    if (tid == 0) {
-      const float zd = gate(0);
-      dc_gated[row] = zd;
-      if constexpr (SPECTRUM) spectrum[((int64_t)b * kBins) * T + t] = zd;
+    for (int i = 0; i < 3; ++i) { w0[i] = P[0][fcol + i]; w1[i] = P[1][fcol + i]; d0[i] = P[0][i]; d1[i] = P[1][i]; }
+    float* zrow = z0 + ((int64_t)b * T + t0) * kC + tid;
+    float* srow = SPECTRUM ? spectrum + ((int64_t)b * kBins + tid + 1) * T + t0 : nullptr;
+    for (int lf = 1; lf <= nfr; ++lf) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) w2[i] = P[lf + 1][fcol + i];
+      float z = w1[1];
+      if (gk.enabled) {
+        float acc = gk.bias;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) acc += k[i * 3] * w0[i] + k[i * 3 + 1] * w1[i] + k[i * 3 + 2] * w2[i];
+        z *= prelu(acc, gk.slope);
+      }
+      zrow[(int64_t)(lf - 1) * kC] = z;
+      if constexpr (SPECTRUM) srow[lf - 1] = z;   // the optional torch-layout export (model.py:421)
+      s += z;
+      ss += z * z;
+      if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) d2[i] = P[lf + 1][i];
+        float zd = d1[1];
+        if (gk.enabled) {
+          float acc = gk.bias;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) acc += k[i * 3] * d0[i] + k[i * 3 + 1] * d1[i] + k[i * 3 + 2] * d2[i];
+          zd *= prelu(acc, gk.slope);
+        }
+        const int64_t row = (int64_t)b * T + t0 + lf - 1;
+        dc_gated[row] = zd;
+        if constexpr (SPECTRUM) spectrum[((int64_t)b * kBins) * T + t0 + lf - 1] = zd;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { d0[i] = d1[i]; d1[i] = d2[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { w0[i] = w1[i]; w1[i] = w2[i]; }
     }
-    s += z;
-    ss += z * z;
   }
   block_stat_atomic(s, ss, st0 + b, red);
 }
