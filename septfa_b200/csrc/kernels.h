@@ -245,6 +245,7 @@ struct LaunchCtx {
   int conv1_persist = 1;       // persistent warp-specialised conv1 kernel (0: always the one-tile-per-CTA kernel)
   int conv1_wres = 1;          // ... with the whole W1 image resident in shared memory (plane layout of p only)
   int conv1_pair = 1;          // blocks 1 .. n-1, recursive-LN wiring, fast mode: TF32 CTA-pair conv1 fed by TMA from the fp32 stream
+                               // (1: from ~2.5 tiles per SM on, 2: always)
   int stream_half = 0;         // opt-in: blocks 1 .. n-1 carry the residual stream as fp16 (recursive-LN wiring, fast precision
                                // mode). 11 % faster, but the stream's rounding random-walks through all blocks: worst VAD
                                // error on the shape sweep 9.5e-4 against 2.1e-4 - outside the default parity envelope

@@ -64,6 +64,7 @@ struct septfa_handle {
   float act_k[9]{}; float act_b = 0.f; float act_a = 0.f;
   const float* win_fwd = nullptr; const float* win_inv = nullptr; const float2* twiddle = nullptr;
   int last_launches = 0;
+  int sm_count = 148;
   LaunchCtx lctx;   // launch options and counter of this handle (bound to the calling thread by every entry point)
   // forward_host resources
   cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
@@ -409,6 +410,7 @@ int septfa_create(septfa_handle** out, const septfa_config* cfg, int device) {
   if (const char* e = getenv("SEPTFA_DCONV_CLUSTER")) h->lctx.dconv_cluster = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("SEPTFA_DCONV_DESC_SWAP")) h->lctx.dconv_desc_swap = atoi(e) ? 1 : 0;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SEPTFA_E_CUDA, "cudaSetDevice failed"); }
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaError_t e = tc_gemm_setup();
   if (e == cudaSuccess) e = resid_fused_setup();
   if (e == cudaSuccess) e = conv1_persist_setup();
@@ -482,7 +484,7 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
     return 0;
   }
   if (std::strcmp(name, "conv1_pair") == 0) {
-    h->lctx.conv1_pair = value ? 1 : 0;
+    h->lctx.conv1_pair = value == 2 ? 2 : (value ? 1 : 0);
     return 0;
   }
   if (std::strcmp(name, "stream_half") == 0) {
@@ -893,7 +895,11 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
   // CTA-pair dconv kernel (dconv_mma2.cu): cta_group::2 MMAs, res_out weights resident in shared memory
   const bool pair = planes && h->lctx.dconv_pair;
   // TF32 CTA-pair conv1 (gemm_conv1_pair.cu) for blocks 1 .. n-1: the fp32 stream is its A operand, fetched by TMA
-  const bool c1pair = planes && !stream_half && h->lctx.conv1_pair && h->ln_mode == LN_RECURSIVE && h->nblk > 1;
+  // (from ~2.5 tiles per SM on: each of its CTAs first loads 128 KB of weights, which 1-2 tiles do not pay back - measured
+  // at 64 / 128 / 256 x 4 s: +0.06 / +0.03 / -0.055 ms per forward against the persistent producer kernel; option value 2
+  // forces it at any size)
+  const bool c1pair = planes && !stream_half && h->lctx.conv1_pair && h->ln_mode == LN_RECURSIVE && h->nblk > 1 &&
+                      (h->lctx.conv1_pair == 2 || (int64_t)((M + 127) / 128) * 2 >= (int64_t)h->sm_count * 5);
   alignas(64) CUtensorMap w32_tmap;
   if (c1pair && !make_stream_tmap(&w32_tmap, ws.w, M, 128, true)) return fail(h, SEPTFA_E_CUDA, "cuTensorMapEncodeTiled failed for the fp32 stream");
   alignas(64) CUtensorMap racc_tmap;   // the pair kernel's epilogue stores racc with TMA tensor stores (boxes of 32 rows x 64 columns)
