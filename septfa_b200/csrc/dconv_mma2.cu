@@ -360,11 +360,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
 #ifdef SEPTFA_EXP_ONE_TAP
         for (int k = 1; k < 2; ++k) {
 #else
-#ifdef SEPTFA_EXP_ONE_TAP
-        for (int k = 1; k < 2; ++k) {
-#else
         for (int k = 0; k < 3; ++k) {       // tap-major: consecutive MMAs accumulate into different columns
-#endif
 #endif
 #pragma unroll
           for (int grp = 0; grp < 2; ++grp) {
@@ -374,11 +370,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
 #ifdef SEPTFA_EXP_ONE_TAP
                       make_ns_desc(b_addr, 256u, 128u), IDESC_MINI, 0);
 #else
-#ifdef SEPTFA_EXP_ONE_TAP
-                      make_ns_desc(b_addr, 256u, 128u), IDESC_MINI, 0);
-#else
                       make_ns_desc(b_addr, 256u, 128u), IDESC_MINI, k != 0);
-#endif
 #endif
           }
         }
@@ -463,10 +455,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
             float2 qv;
             if constexpr (AMAX) qv = make_float2(fmaxf(x.x, ax.x), fmaxf(x.y, ax.y));
             else qv = make_float2(fminf(x.x, ax.x), fminf(x.y, ax.y));
-#ifndef SEPTFA_EXP_NO_STATS
             accS = __fadd2_rn(accS, qv);
             accQ = __ffma2_rn(qv, qv, accQ);
-#endif
             h[i * 4 + k] = pack_half2(qv.x, qv.y);
           }
         }
