@@ -357,25 +357,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
         const uint32_t slab = smem_u32(smem + kOffP + sp * kPChunkBytes);
         if (elect_one()) {
 #pragma unroll
-#ifdef SEPTFA_EXP_ONE_TAP
-        for (int k = 1; k < 2; ++k) {
-#else
-        for (int k = 0; k < 3; ++k) {       // tap-major: consecutive MMAs accumulate into different columns
-#endif
+          for (int k = 0; k < 3; ++k) {       // tap-major: consecutive MMAs accumulate into different columns
 #pragma unroll
-          for (int grp = 0; grp < 2; ++grp) {
-            const uint32_t a_addr = slab + (uint32_t)(grp * 2 * kPlaneBytes + (kHalo + (k - 1) * p.dil) * 16);
-            const uint32_t b_addr = smem_u32(smem + kOffTap + ((j * 2 + grp) * 3 + k) * 512);
-            umma2_f16(tmem_base + 256u + (uint32_t)(b * 64 + grp * 32), make_ns_desc(a_addr, (uint32_t)kPlaneBytes, 128u),
-#ifdef SEPTFA_EXP_ONE_TAP
-                      make_ns_desc(b_addr, 256u, 128u), IDESC_MINI, 0);
-#else
-                      make_ns_desc(b_addr, 256u, 128u), IDESC_MINI, k != 0);
-#endif
+            for (int grp = 0; grp < 2; ++grp) {
+              const uint32_t a_addr = slab + (uint32_t)(grp * 2 * kPlaneBytes + (kHalo + (k - 1) * p.dil) * 16);
+              const uint32_t b_addr = smem_u32(smem + kOffTap + ((j * 2 + grp) * 3 + k) * 512);
+              umma2_f16(tmem_base + 256u + (uint32_t)(b * 64 + grp * 32), make_ns_desc(a_addr, (uint32_t)kPlaneBytes, 128u),
+                        make_ns_desc(b_addr, 256u, 128u), IDESC_MINI, k != 0);
+            }
           }
-        }
-        umma2_commit(d1_full + b, (uint16_t)3);
-        umma2_commit(p_empty + sp, (uint16_t)3);
+          umma2_commit(d1_full + b, (uint16_t)3);
+          umma2_commit(p_empty + sp, (uint16_t)3);
         }
         __syncwarp();
       }
