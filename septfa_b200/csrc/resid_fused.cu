@@ -3,7 +3,8 @@
 // accumulators (fp16) are read from HBM once into shared memory, the statistics of v cross the cluster through
 // distributed shared memory in a fixed order, the statistics of the new stream leave as one double atomic pair per CTA,
 // and the new stream is written back once. Replaces k_tf_gate + k_resid<0> + k_resid<1> (which read the two tensors
-// twice) whenever an utterance fits a cluster of <= 8 CTAs (T <= 1152 frames, 18 s).
+// twice) whenever an utterance fits a cluster: <= 8 CTAs up to T = 1152 frames (18 s), 16 CTAs (non-portable cluster size) up to
+// T = 2304 (36.9 s).
 // Reference: model/model.py:197-208 (TF_Attention), :347-352 (post-block norms).
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
   __shared__ float mf_s[kC], mt_s[kMaxTc + 8];                              // channel / time means (scratch of the gate stages)
   __shared__ __align__(16) float gf_s[2][kC], rb_s[2][kC], gt_s[2][kMaxTc];   // [parity of the utterance]
   __shared__ float red_a[16], red_b[16], red_c[8];
-  __shared__ __align__(16) double xch[2][16];   // [parity][rank][2]: partial (sum, sum of squares) of v from the peers
+  __shared__ __align__(16) double xch[2][32];   // [parity][rank < 16][2]: partial (sum, sum of squares) of v from the peers
   __shared__ float s_sc[8];
   __shared__ float s_nx[2][4];
   __shared__ __align__(8) uint64_t full;
@@ -402,7 +403,8 @@ void resid_fused_dump_timeline() {   // bring-up: globaltimer stamps of the firs
 #endif
 
 int resid_fused_cluster_size(int T) {   // 0: the utterance does not fit one cluster (caller uses the streaming kernels)
-  if (T > 8 * kMaxTc) return 0;
+  if (T > 16 * kMaxTc) return 0;
+  if (T > 8 * kMaxTc) return 16;          // 18 .. 36 s: clusters of 16 CTAs (non-portable size, allowed per kernel in setup)
   return std::min(8, (T + 31) / 32);
 }
 
@@ -420,6 +422,7 @@ cudaError_t resid_fused_setup() {
     cudaFuncAttributes fa{};
     cudaError_t e = cudaFuncGetAttributes(&fa, resid_kernel(v >> 1, v & 1));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(resid_kernel(v >> 1, v & 1), cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resid_kernel(v >> 1, v & 1), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
@@ -427,8 +430,8 @@ cudaError_t resid_fused_setup() {
 
 // Clusters of `cs` CTAs of the persistent kernel the device keeps resident at once (cached per variant / cluster size / footprint).
 static int persist_clusters(int variant, int cs, size_t smem) {
-  static int cache[4][9] = {};
-  static size_t cache_smem[4][9] = {};
+  static int cache[4][17] = {};
+  static size_t cache_smem[4][17] = {};
   if (cache[variant][cs] != 0 && cache_smem[variant][cs] == smem) return cache[variant][cs];
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cs * 1024);

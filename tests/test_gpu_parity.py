@@ -228,7 +228,7 @@ def test_engines_agree(cuda_models):
 
 
 @pytest.mark.parametrize("cfg_name", ["with", "without"])
-@pytest.mark.parametrize("B,L", [(3, 64000), (2, 30000), (5, 9000), (2, 100000), (1, 200000)])
+@pytest.mark.parametrize("B,L", [(3, 64000), (2, 30000), (5, 9000), (2, 100000), (1, 200000), (2, 400000), (1, 580000)])
 def test_fused_residual_kernel_equals_streaming_kernels(cuda_models, cfg_name, B, L):
     """The cluster-resident gate + residual kernel (resid_fused.cu) against k_tf_gate + k_resid<0,1> on the
     same buffers: same arithmetic, different summation grouping of the GroupNorm statistics, so they agree
