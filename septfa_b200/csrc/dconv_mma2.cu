@@ -193,6 +193,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
   uint64_t* d2_full = bars + 46;      //     MMA commit (multicast)
   uint64_t* d2_empty = bars + 47;     //     leader: 8 epilogue warps of the pair
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
+  uint64_t* ms_full = bars + 49;      // [2] the edge warp has published mean / rstd of the tile's utterances (by tile parity)
+  float4* ms_s = reinterpret_cast<float4*>(bars + 52);   // [2] {mean0, rstd0, mean1, rstd1}
   constexpr uint32_t IDESC_MAIN = make_idesc_f16(2 * kTileM, 256);
   constexpr uint32_t IDESC_MINI = make_idesc_f16(2 * kTileM, 32);
 
@@ -209,6 +211,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
     for (int s = 0; s < kPStages; ++s) { mbar_init(p_full + s, 1); mbar_init(p_peer + s, 1); mbar_init(p_empty + s, 6); mbar_init(corr_full + s, 1); }
     for (int s = 0; s < kD1Bufs; ++s) { mbar_init(d1_full + s, 1); mbar_init(d1_empty + s, 1); mbar_init(a2_full + s, 8); }
     mbar_init(d2_full, 1); mbar_init(d2_empty, 8);
+    mbar_init(ms_full, 1); mbar_init(ms_full + 1, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc2(tmem_slot, 512);
@@ -273,14 +276,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
     float* corr_s = reinterpret_cast<float*>(smem + kOffCorr);
     const double inv_n = 1.0 / ((double)kC * p.T);
     const int slot = lane >> 2, part = lane & 3;
-    int g = 0;
-    for (int tile = first; tile < tile_end; tile += stride) {
+    int g = 0, lt = 0;
+    for (int tile = first; tile < tile_end; tile += stride, ++lt) {
       const int r0 = tile * kTileM, nrows = max(0, min(kTileM, p.M - r0));
       const int b_first = r0 / p.T, e1 = (b_first + 1) * p.T;
       float2 mr = make_float2(0.f, 1.f);
       if (nrows > 0 && lane < 2 && (lane == 0 || e1 < r0 + nrows)) mr = stat_mean_rstd(p.st_p + b_first + lane, inv_n, 1e-8f);
       const float m0 = __shfl_sync(0xffffffffu, mr.x, 0), s0 = __shfl_sync(0xffffffffu, mr.y, 0);
       const float m1 = __shfl_sync(0xffffffffu, mr.x, 1), s1 = __shfl_sync(0xffffffffu, mr.y, 1);
+      // ... published for the transform warps: this warp runs up to a p ring ahead of them, they are the pair's critical path at
+      // a tile boundary and the statistics cost two L2 round trips plus double arithmetic. (Slot lt & 1 was last read at the top
+      // of tile lt - 2; this warp gets here only after the transform has released chunk 4 of tile lt - 1.)
+      if (lane == 0) { ms_s[lt & 1] = make_float4(m0, s0, m1, s1); mbar_arrive(ms_full + (lt & 1)); }
       // the row of this lane's slot (if the tile has it) and its utterance
       int row = -1; bool second = false;
       if (slot < 4) {                       // t = T - i, i = 4 - slot: invalid iff i <= dil
@@ -405,15 +412,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
     float2* k0_s = reinterpret_cast<float2*>(smem + kOffSwc);   // [2 utterances of the tile][256 output pairs]
     const int tt = (warp - 4) * 32 + lane;                      // this thread's output pair when the table is built
     const float* corr_s = reinterpret_cast<const float*>(smem + kOffCorr);
-    const double inv_n = 1.0 / ((double)kC * p.T);
-    int g = 0;
-    for (int tile = first; tile < tile_end; tile += stride) {
+    const float4 t4 = __ldg(p.swc + tt);                         // tile-invariant: sums of the fp16 taps, folded constants
+    int g = 0, lt = 0;
+    for (int tile = first; tile < tile_end; tile += stride, ++lt) {
       const int r0 = tile * kTileM, nrows = max(0, min(kTileM, p.M - r0));
       const int b_first = r0 / p.T, e1 = (b_first + 1) * p.T;   // first row of the tile's second utterance
-      float2 mr = make_float2(0.f, 1.f);
-      if (nrows > 0 && lane < 2 && (lane == 0 || e1 < r0 + nrows)) mr = stat_mean_rstd(p.st_p + b_first + lane, inv_n, 1e-8f);
-      const float m0 = __shfl_sync(0xffffffffu, mr.x, 0), s0 = __shfl_sync(0xffffffffu, mr.y, 0);
-      const float m1 = __shfl_sync(0xffffffffu, mr.x, 1), s1 = __shfl_sync(0xffffffffu, mr.y, 1);
+      // mean / rstd of the tile's (at most two) utterances come from the edge warp, which runs ahead: at a tile boundary these
+      // warps are the pair's critical path (the first res_out MMA of a tile waits for their first chunk)
+      mbar_wait(ms_full + (lt & 1), (lt >> 1) & 1, 320);
+      const float4 ms4 = ms_s[lt & 1];
+      const float m0 = ms4.x, s0 = ms4.y, m1 = ms4.z, s1 = ms4.w;
       const int row = r0 + rl;
       const bool valid = rl < nrows, second = row >= e1;
       const float mean = second ? m1 : m0, rstd = second ? s1 : s0;
@@ -425,7 +433,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
       // per tile (two utterances x 512 outputs) instead of one FFMA2 per pair and row (the transform is bound by the FP32 pipe)
       asm volatile("bar.sync 1, 256;" ::: "memory");            // every transform warp is done with the previous tile's table
       {
-        const float4 t4 = __ldg(p.swc + tt);
         k0_s[tt] = __ffma2_rn(make_float2(-m0 * s0, -m0 * s0), make_float2(t4.x, t4.y), make_float2(t4.z, t4.w));
         k0_s[256 + tt] = __ffma2_rn(make_float2(-m1 * s1, -m1 * s1), make_float2(t4.x, t4.y), make_float2(t4.z, t4.w));
       }
@@ -498,12 +505,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
       g += 8;
       // statistics of q of this warp's 32 rows x 256 columns, per utterance: fixed-order shuffle trees, double atomics
       const float sv = valid ? accS.x + accS.y : 0.f, qv = valid ? accQ.x + accQ.y : 0.f;
-      const float a0 = warp_sum(second ? 0.f : sv), c0 = warp_sum(second ? 0.f : qv);
-      const float a1 = warp_sum(second ? sv : 0.f), c1 = warp_sum(second ? qv : 0.f);
+      // (an utterance boundary falls into one warp's 32 rows of few tiles: two shuffle trees instead of four elsewhere)
+      const unsigned secm = __ballot_sync(0xffffffffu, second);
+      float a0 = 0.f, c0 = 0.f, a1 = 0.f, c1 = 0.f;
+      if (secm == 0u) { a0 = warp_sum(sv); c0 = warp_sum(qv); }
+      else if (secm == 0xffffffffu) { a1 = warp_sum(sv); c1 = warp_sum(qv); }
+      else {
+        a0 = warp_sum(second ? 0.f : sv); c0 = warp_sum(second ? 0.f : qv);
+        a1 = warp_sum(second ? sv : 0.f); c1 = warp_sum(second ? qv : 0.f);
+      }
       if (lane == 0 && nrows > 0) {
-        atomicAdd(&p.st_q[b_first].s, (double)a0);
-        atomicAdd(&p.st_q[b_first].ss, (double)c0);
-        if (e1 < r0 + nrows) {
+        if (secm != 0xffffffffu) {
+          atomicAdd(&p.st_q[b_first].s, (double)a0);
+          atomicAdd(&p.st_q[b_first].ss, (double)c0);
+        }
+        if (secm != 0u && e1 < r0 + nrows) {
           atomicAdd(&p.st_q[b_first + 1].s, (double)a1);
           atomicAdd(&p.st_q[b_first + 1].ss, (double)c1);
         }
@@ -613,34 +629,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
         }
         __syncwarp();                    // every lane's column-sum reads of the staging boxes are done
       };
-      // columns 0-127: tensor memory -> fp16 -> staging boxes (two loads in flight) -> tensor stores
-      if (lane == 0) bulk_wait_read_all();   // the previous tile's boxes have left the staging buffer
-      __syncwarp();
-      {
-        uint32_t va[32], vb[32];
-        tmem_ld32_nowait(t_row, va);
-        tmem_ld_wait();
-        tmem_ld32_nowait(t_row + 32u, vb);
-        pack_store(va, 0);
-        tmem_ld_wait();
-        tmem_ld32_nowait(t_row + 64u, va);
-        pack_store(vb, 1);
-        tmem_ld_wait();
-        tmem_ld32_nowait(t_row + 96u, vb);
-        pack_store(va, 2);
-        tmem_ld_wait();
-        pack_store(vb, 3);
-      }
-      store_half(0);
-      // columns 128-255: tensor memory -> fp16 pairs held in REGISTERS, so that D2 goes back to the MMA warp before the
-      // column sums of either half and before the first half has left the staging boxes (waiting for both held the
-      // accumulator for 3.5-6 k cycles per tile, the pace of the slowest of the pair's eight epilogue warps)
+      // The whole accumulator leaves tensor memory in ONE software pipeline (a 32-column load in flight behind every
+      // conversion), because nothing else of this role is on the pair's critical path: the first res_out MMA of the next tile
+      // waits for D2. Columns 0-127 go to the staging boxes as fp16, columns 128-255 wait in REGISTERS as fp16 pairs, so that
+      // D2 goes back to the MMA warp before the tensor stores, the column sums of either half and the staging of the second
+      // (waiting for those held the accumulator for 3.5-6 k cycles per tile; the unpipelined second half for 2.1 k).
       uint32_t h2[64];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t u[32];
-        tmem_ld32_nowait(t_row + (uint32_t)(128 + c * 32), u);
-        tmem_ld_wait();
+      auto keep = [&](const uint32_t (&u)[32], int c) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float v8[8];
@@ -651,10 +646,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
 #pragma unroll
           for (int e = 0; e < 4; ++e) h2[c * 16 + i * 4 + e] = pack_half2(v8[2 * e], v8[2 * e + 1]);
         }
+      };
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32_nowait(t_row, va);
+        if (lane == 0) bulk_wait_read_all();   // the previous tile's boxes have left the staging buffer
+        __syncwarp();
+        tmem_ld_wait();
+        tmem_ld32_nowait(t_row + 32u, vb);
+        pack_store(va, 0);
+        tmem_ld_wait();
+        tmem_ld32_nowait(t_row + 64u, va);
+        pack_store(vb, 1);
+        tmem_ld_wait();
+        tmem_ld32_nowait(t_row + 96u, vb);
+        pack_store(va, 2);
+        tmem_ld_wait();
+        tmem_ld32_nowait(t_row + 128u, va);
+        pack_store(vb, 3);
+        tmem_ld_wait();
+        tmem_ld32_nowait(t_row + 160u, vb);
+        keep(va, 0);
+        tmem_ld_wait();
+        tmem_ld32_nowait(t_row + 192u, va);
+        keep(vb, 1);
+        tmem_ld_wait();
+        tmem_ld32_nowait(t_row + 224u, vb);
+        keep(va, 2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cl(d2_empty, 0);   // every column is in registers or staged
+        keep(vb, 3);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cl(d2_empty, 0);
+      store_half(0);   // the staged half (two boxes) leaves with one tensor store per box
       if (warp == 12 && lane == 0) DTL(6, lt * 4 + 1);
       colsum_half(0);
       if (lane == 0) bulk_wait_read_all();   // the first half's boxes have left the staging buffer
