@@ -9,7 +9,7 @@
 // image for every 128-frame tile, which bounds it at one SM's TMA ingress (~20 B/clk: 1.95 k cycles per 64-channel chunk
 // against 0.6 k cycles of MMA work); here the only per-tile traffic into an SM is its own 68 KB of p.
 // Roles per CTA (16 warps):
-//   warp 0        p loader   : 4 bulk copies (K-group planes) per 32-channel chunk, ring of 3
+//   warp 0        p loader   : 4 bulk copies (K-group planes) per 32-channel chunk, ring of 4
 //   warp 1        static loader (prologue), then EDGE warp: the exact zero-padding corrections of the <= 8 rows of a tile whose
 //                 tap falls outside their utterance, as a small table per p stage
 //   warp 2        res_out MMA issuer (leader CTA): per chunk 4 MMAs (M256 N256 K16, A from TMEM) into D2; multicast commits
@@ -39,7 +39,7 @@ constexpr int kHalo = kPlaneHalo;                   // 4 = the largest dilation
 constexpr int kSlabRows = kTileM + 2 * kHalo;       // 136 frames: tile + halo
 constexpr int kPlaneBytes = kSlabRows * 16;         // 2176: one K-group (8 channels) of the slab
 constexpr int kPChunkBytes = 4 * kPlaneBytes;       // 8704: 32 input channels
-constexpr int kPStages = 3;
+constexpr int kPStages = 4;
 constexpr int kWHalfBytes = 128 * 128;              // 16 KB: this CTA's 128 output rows of one K-chunk (64) of the res_out image
 constexpr int kTapHalfBytes = kDconvTapBytes / 2;   // 24 KB: [16 groups][3 taps][2 K halves][16 outputs x 8 inputs, fp16]
 constexpr int kD1Bufs = 4;
@@ -47,10 +47,12 @@ constexpr int kOffW = 0;                                      // 1024-aligned (1
 constexpr int kOffTap = kOffW + 8 * kWHalfBytes;
 constexpr int kOffP = kOffTap + kTapHalfBytes;
 constexpr int kOffSwc = kOffP + kPStages * kPChunkBytes;
-constexpr int kOffEdge = kOffSwc + 4096;            // edge-correction tables: fp16-rounded taps 0 and 2 [2][512] and beta1 / gamma1 [256], fp32
-constexpr int kOffCorr = kOffEdge + 5120;           // edge corrections of the chunk in each p stage: [kPStages][8 rows][64 outputs] fp32
+constexpr int kOffEdge = kOffSwc + 4096;            // edge-correction tables: folded taps 0 and 2 [2][512] fp16 (exactly what the MMA multiplies by), beta1 / gamma1 [256] fp32
+constexpr int kEdgeBytes = 2 * 512 * 2 + 256 * 4;
+// (the edge corrections of a chunk, [8 rows][64 outputs] fp32, are written over the first 2 KB of the chunk's own p stage once the
+// mini-GEMMs have read it: a table of their own per stage is what stood between three and four p stages)
 constexpr int kEpiWarpBytes = 2 * 32 * 128;         // two staging boxes per epilogue warp: 32 rows x 64 fp16 columns, 128-byte-swizzled rows
-constexpr int kOffEpi = (kOffCorr + kPStages * 2048 + 1023) / 1024 * 1024;
+constexpr int kOffEpi = (kOffEdge + kEdgeBytes + 1023) / 1024 * 1024;
 constexpr int kOffBar = kOffEpi + 4 * kEpiWarpBytes;
 constexpr int kSmemBytes = kOffBar + 512;
 static_assert(kPStages <= 4, "barrier slots");
@@ -216,10 +218,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
   }
   if (warp == 2) tmem_alloc2(tmem_slot, 512);
   {
-    float* edge = reinterpret_cast<float*>(smem + kOffEdge);
-    edge[threadIdx.x] = __ldg(p.w16 + threadIdx.x);                    // tap 0
-    edge[kH + threadIdx.x] = __ldg(p.w16 + 2 * kH + threadIdx.x);      // tap 2
-    if (threadIdx.x < kC) edge[2 * kH + threadIdx.x] = __ldg(p.bog + threadIdx.x);
+    __half* edge_w = reinterpret_cast<__half*>(smem + kOffEdge);
+    edge_w[threadIdx.x] = __float2half_rn(__ldg(p.w16 + threadIdx.x));                    // tap 0 (fp16 values stored as fp32: exact)
+    edge_w[kH + threadIdx.x] = __float2half_rn(__ldg(p.w16 + 2 * kH + threadIdx.x));      // tap 2
+    if (threadIdx.x < kC) reinterpret_cast<float*>(smem + kOffEdge + 4 * kH)[threadIdx.x] = __ldg(p.bog + threadIdx.x);
   }
   __syncthreads();
   if (warp == 1 && lane == 0) {
@@ -272,8 +274,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
     // transform warps - 170 divergent instructions per chunk and side - these few rows set the pace of the whole pair.)
     // lane -> (slot = lane / 4, K-group = lane % 4); slots 0-3: rows T - 4 .. T - 1 of an utterance (tap +dil invalid),
     // slots 4-7: rows 0 .. 3 (tap -dil invalid). With T >= 128 a tile holds at most one group of each kind.
-    const float* edge_s = reinterpret_cast<const float*>(smem + kOffEdge);
-    float* corr_s = reinterpret_cast<float*>(smem + kOffCorr);
+    const __half* edge_w = reinterpret_cast<const __half*>(smem + kOffEdge);
+    const float* edge_bog = reinterpret_cast<const float*>(smem + kOffEdge + 4 * kH);
     const double inv_n = 1.0 / ((double)kC * p.T);
     const int slot = lane >> 2, part = lane & 3;
     int g = 0, lt = 0;
@@ -305,26 +307,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
       }
       const float mean = second ? m1 : m0, inv_rstd = 1.0f / (second ? s1 : s0);
       const int srow = kHalo + (row - r0) + (slot < 4 ? p.dil : -p.dil);
-      const float* wk_side = edge_s + (slot < 4 ? kH : 0);   // tap 2 for the rows at an utterance's end, tap 0 at its start
+      const __half* wk_side = edge_w + (slot < 4 ? kH : 0);   // tap 2 for the rows at an utterance's end, tap 0 at its start
+      const bool any_row = __any_sync(0xffffffffu, row >= 0);
       for (int j = 0; j < 8; ++j, ++g) {
         const int sp = g % kPStages;
         mbar_wait(p_full + sp, (g / kPStages) & 1, 140 + j);
-        if (row >= 0) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(smem + kOffP + sp * kPChunkBytes + part * kPlaneBytes + srow * 16);
-          const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+        if (any_row) {
           float cv[16];
+          if (row >= 0) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(smem + kOffP + sp * kPChunkBytes + part * kPlaneBytes + srow * 16);
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-          for (int e2 = 0; e2 < 4; ++e2) {
-            const float2 pv = __half22float2(*reinterpret_cast<const __half2*>(&rw[e2]));
-            const int c = part * 8 + e2 * 2;     // input channel within the chunk's 32
-            const float2 bg = *reinterpret_cast<const float2*>(edge_s + 2 * kH + j * 32 + c);
-            const float u0 = (pv.x - mean) + bg.x * inv_rstd, u1 = (pv.y - mean) + bg.y * inv_rstd;
-            const float4 w4 = *reinterpret_cast<const float4*>(wk_side + j * 64 + 2 * c);
-            cv[4 * e2] = w4.x * u0; cv[4 * e2 + 1] = w4.y * u0; cv[4 * e2 + 2] = w4.z * u1; cv[4 * e2 + 3] = w4.w * u1;
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const float2 pv = __half22float2(*reinterpret_cast<const __half2*>(&rw[e2]));
+              const int c = part * 8 + e2 * 2;     // input channel within the chunk's 32
+              const float2 bg = *reinterpret_cast<const float2*>(edge_bog + j * 32 + c);
+              const float u0 = (pv.x - mean) + bg.x * inv_rstd, u1 = (pv.y - mean) + bg.y * inv_rstd;
+              const uint2 wr = *reinterpret_cast<const uint2*>(wk_side + j * 64 + 2 * c);
+              const float2 w01 = __half22float2(*reinterpret_cast<const __half2*>(&wr.x)), w23 = __half22float2(*reinterpret_cast<const __half2*>(&wr.y));
+              cv[4 * e2] = w01.x * u0; cv[4 * e2 + 1] = w01.y * u0; cv[4 * e2 + 2] = w23.x * u1; cv[4 * e2 + 3] = w23.y * u1;
+            }
           }
-          float4* dst = reinterpret_cast<float4*>(corr_s + (sp * 8 + slot) * 64 + part * 16);
+          // the table goes over the start of the stage itself, as soon as the mini-GEMMs of the chunk (both CTAs: multicast commit)
+          // have read it; the transform warps wait for their own tensor-memory loads meanwhile
+          mbar_wait(d1_full + (g % kD1Bufs), (g / kD1Bufs) & 1, 150 + j);
+          if (row >= 0) {
+            float4* dst = reinterpret_cast<float4*>(smem + kOffP + sp * kPChunkBytes + slot * 256 + part * 64);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) dst[e] = make_float4(cv[4 * e], cv[4 * e + 1], cv[4 * e + 2], cv[4 * e + 3]);
+            for (int e = 0; e < 4; ++e) dst[e] = make_float4(cv[4 * e], cv[4 * e + 1], cv[4 * e + 2], cv[4 * e + 3]);
+          }
+          fence_proxy_async();   // generic-proxy writes into a stage the next bulk copy will overwrite
         }
         __syncwarp();
         if (lane == 0) { mbar_arrive(corr_full + sp); mbar_arrive(p_empty + sp); }
@@ -411,7 +423,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
     const float2 sl2 = make_float2(p.slope2, p.slope2);
     float2* k0_s = reinterpret_cast<float2*>(smem + kOffSwc);   // [2 utterances of the tile][256 output pairs]
     const int tt = (warp - 4) * 32 + lane;                      // this thread's output pair when the table is built
-    const float* corr_s = reinterpret_cast<const float*>(smem + kOffCorr);
     const float4 t4 = __ldg(p.swc + tt);                         // tile-invariant: sums of the fp16 taps, folded constants
     int g = 0, lt = 0;
     for (int tile = first; tile < tile_end; tile += stride, ++lt) {
@@ -477,7 +488,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
         if (cslot >= 0) {
           // zero padding of the normalised signal: take back what the out-of-utterance tap contributed (edge warp's table)
           mbar_wait(corr_full + sp, (gg / kPStages) & 1, 310 + j);
-          const float4* cr = reinterpret_cast<const float4*>(corr_s + (sp * 8 + cslot) * 64);
+          const float4* cr = reinterpret_cast<const float4*>(smem + kOffP + sp * kPChunkBytes + cslot * 256);   // over the consumed stage
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float4 c4 = cr[e], d4 = cr[8 + e];

@@ -24,6 +24,9 @@ tl = np.array(buf).reshape(10, 64)
 t0 = tl[9, 0]
 names = ["p_issue", "w_issue", "mini_issue", "main_issue", "d1_ready(w4)", "a2_written(w4)", "epi(d2_full,released,done,-)", "", "w_ready", "start"]
 names[7] = "ld_done[0:32] / computed[32:64] (w4)"
+names[1] = "mini_issued"; names[8] = "main_issued"
 for r in (0, 1, 2, 8, 3, 4, 7, 5, 6):
     row = tl[r]
-    print(f"{names[r]:28s}", " ".join(str(int(v - t0)) if v else "-" for v in (row[:64] if r in (6, 7) else row[:36])))
+    print(f"{names[r]:28s}", " ".join(str(int(v - t0)) if v else "-" for v in (row[:64] if r in (6, 7) else row[:32])))
+print(f"{'p_full seen by mini issuer':28s}", " ".join(str(int(v - t0)) if v else "-" for v in tl[0][32:64]))
+print(f"{'p_peer seen by mini issuer':28s}", " ".join(str(int(v - t0)) if v else "-" for v in tl[1][32:64]))
