@@ -40,7 +40,9 @@ __device__ __forceinline__ float prelu(float x, float a) { return x >= 0.f ? x :
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
 // ex2.approx + rcp.approx: ~1e-6 absolute on a mask in (0, 1); for the masks only - the VAD probabilities that are
 // compared with a threshold use sigmoidf_acc.
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
+// (the approximate reciprocal, one MUFU, instead of the IEEE-rounded one: the masks move by <= 1 ulp, and in the iSTFT kernel the
+// rounded reciprocal's instruction sequence held a third of the stall samples)
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // mean / rstd of one utterance from its double accumulators (biased variance, GroupNorm(1,C)).
 __device__ __forceinline__ float2 stat_mean_rstd(const Stat2* st, double inv_n, float eps) {
