@@ -142,15 +142,19 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
   // and leaves them in shared memory (s_nx[parity]); 16 warps repeating that code was a third of the kernel's issue slots.
   double csv = 0.0;
   float rsv = 0.f;
-  auto scalars_for = [&](int b, int par) {   // one thread
-    const Stat2 sq{__ldg(&p.st_q[b].s), __ldg(&p.st_q[b].ss)};
-    const float2 mrq = stat_mean_rstd(&sq, 1.0 / ((double)kH * p.T), 1e-8f);
-    float2 my = make_float2(0.f, 1.f);
-    if (has_norm) {
-      const Stat2 sy{__ldg(&p.norm.st[b].s), __ldg(&p.norm.st[b].ss)};
-      my = stat_mean_rstd(&sy, p.norm.inv_n, p.norm.eps);
+  auto scalars_for = [&](int b, int par, int which) {   // two threads (of different warps): which = 0 the statistics of q, 1 those of the stream
+    if (which == 0) {
+      const Stat2 sq{__ldg(&p.st_q[b].s), __ldg(&p.st_q[b].ss)};
+      const float2 mrq = stat_mean_rstd(&sq, 1.0 / ((double)kH * p.T), 1e-8f);
+      s_nx[par][0] = mrq.y; s_nx[par][1] = mrq.x;
+    } else {
+      float2 my = make_float2(0.f, 1.f);
+      if (has_norm) {
+        const Stat2 sy{__ldg(&p.norm.st[b].s), __ldg(&p.norm.st[b].ss)};
+        my = stat_mean_rstd(&sy, p.norm.inv_n, p.norm.eps);
+      }
+      s_nx[par][2] = my.x; s_nx[par][3] = my.y;
     }
-    s_nx[par][0] = mrq.y; s_nx[par][1] = mrq.x; s_nx[par][2] = my.x; s_nx[par][3] = my.y;
   };
   auto fetch_small = [&](int b) {
     csv = __ldg(p.colsum + b * kC + tid);
@@ -188,7 +192,8 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
   };
   if (cluster_id < p.B) {
     fetch_small(cluster_id);
-    if (tid == kPersistThreads - 1) scalars_for(cluster_id, 0);
+    if (tid == kPersistThreads - 1) scalars_for(cluster_id, 0, 0);
+    if (tid == kPersistThreads - 33) scalars_for(cluster_id, 0, 1);
     __syncthreads();
     gate_stage0(0);
     __syncthreads();
@@ -229,7 +234,8 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
     FTL(8 + it * 8 + 0);
     if (has_next) {
       fetch_small(b_next);                    // consumed by the gate stages further down
-      if (tid == kPersistThreads - 1) scalars_for(b_next, buf ^ 1);
+      if (tid == kPersistThreads - 1) scalars_for(b_next, buf ^ 1, 0);
+      if (tid == kPersistThreads - 33) scalars_for(b_next, buf ^ 1, 1);
     }
     const float ra = s_nx[buf][0], mean_y = s_nx[buf][2], rstd_y = s_nx[buf][3];
     const float* gt_cur = gt_s[buf];
