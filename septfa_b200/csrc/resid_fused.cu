@@ -52,6 +52,8 @@ struct FusedParams {
   const double* colsum;     // [B,256]
   TfParams tf;
   int T, B, Tc;             // Tc = frames per CTA
+  double inv_T, inv_HT, inv_CT;   // 1 / T, 1 / (512 T), 1 / (256 T): computed on the host (a double division is a long software routine,
+                                  // and every thread of every CTA ran one before its first gate stage, thread 0 one per utterance)
   int mode;                 // LnMode
   const float* g_a; const float* b_a;   // ln_first / ln_modules
   Stat2* st_w;              // [B] statistics of the new stream (recursive mode), accumulated into a zeroed slot
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
 
   const bool has_norm = p.norm.gamma != nullptr;
   const bool recursive = p.mode == LN_RECURSIVE;
-  const double inv_T = 1.0 / (double)p.T;
+  const double inv_T = p.inv_T;
   // static per-channel operands, once per CTA
   const float c03v = __ldg(p.c03 + tid), s3v = __ldg(p.s3 + tid);
   float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
   auto scalars_for = [&](int b, int par, int which) {   // two threads (of different warps): which = 0 the statistics of q, 1 those of the stream
     if (which == 0) {
       const Stat2 sq{__ldg(&p.st_q[b].s), __ldg(&p.st_q[b].ss)};
-      const float2 mrq = stat_mean_rstd(&sq, 1.0 / ((double)kH * p.T), 1e-8f);
+      const float2 mrq = stat_mean_rstd(&sq, p.inv_HT, 1e-8f);
       s_nx[par][0] = mrq.y; s_nx[par][1] = mrq.x;
     } else {
       float2 my = make_float2(0.f, 1.f);
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
         mbar_wait(&xbar[buf], (it >> 1) & 1, 710);
         Stat2 tot{0.0, 0.0};
         for (int r = 0; r < CS; ++r) { tot.s += xch[buf][2 * r]; tot.ss += xch[buf][2 * r + 1]; }
-        const float2 m = stat_mean_rstd(&tot, 1.0 / ((double)kC * p.T), 1e-5f);
+        const float2 m = stat_mean_rstd(&tot, p.inv_CT, 1e-5f);
         s_sc[4] = m.x;
         s_sc[5] = m.y;
       }
@@ -483,6 +485,7 @@ bool launch_resid_fused(const ResidParams& rp, const GateParams& gp, cudaStream_
   p.racc = reinterpret_cast<const __half*>(rp.racc); p.norm = rp.norm;
   p.st_q = gp.st_q; p.s3 = gp.s3; p.c03 = gp.c03; p.rowsum = gp.rowsum; p.colsum = gp.colsum; p.tf = gp.tf;
   p.T = rp.T; p.B = rp.B; p.Tc = (rp.T + cs - 1) / cs;
+  p.inv_T = 1.0 / (double)rp.T; p.inv_HT = 1.0 / ((double)kH * rp.T); p.inv_CT = 1.0 / ((double)kC * rp.T);
   p.mode = rp.mode; p.g_a = rp.g_a; p.b_a = rp.b_a; p.st_w = rp.st_w;
   const int in_half = rp.w_half_in ? 1 : 0, out_half = rp.w_half_out ? 1 : 0, variant = in_half * 2 + out_half;
   const size_t smem = (size_t)p.Tc * row_bytes(in_half);
