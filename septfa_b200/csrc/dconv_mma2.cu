@@ -63,6 +63,7 @@ struct DmParams {
   alignas(64) CUtensorMap racc_tmap;   // racc as a 2-D tensor [M rows][256 halves], box 64 columns x 32 rows, SWIZZLE_128B
   int M, T, ntiles, Mp, dil;
   float slope2;
+  double inv_n;                // 1 / (256 T), from the host (a double division on the device is a long software routine)
   const __half* p_planes;      // [32 K-groups][Mp slots][8 channels]; frame r lives in slot r + kHalo
   const Stat2* st_p;
   const uint8_t* tap_img2;     // [2 ranks][16 groups][3 taps][2 K halves][16 outputs x 8 inputs fp16]: per-CTA halves of the tap matrices
@@ -276,7 +277,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
     // slots 4-7: rows 0 .. 3 (tap -dil invalid). With T >= 128 a tile holds at most one group of each kind.
     const __half* edge_w = reinterpret_cast<const __half*>(smem + kOffEdge);
     const float* edge_bog = reinterpret_cast<const float*>(smem + kOffEdge + 4 * kH);
-    const double inv_n = 1.0 / ((double)kC * p.T);
+    const double inv_n = p.inv_n;
     const int slot = lane >> 2, part = lane & 3;
     int g = 0, lt = 0;
     for (int tile = first; tile < tile_end; tile += stride, ++lt) {
@@ -739,7 +740,7 @@ cudaError_t dconv_mma2_setup() {
 
 void launch_dconv_mma2(const DconvMmaParams& c, cudaStream_t st) {
   DmParams p{};
-  p.M = c.M; p.T = c.T; p.ntiles = (c.M + kTileM - 1) / kTileM; p.Mp = c.Mp; p.dil = c.dil; p.slope2 = c.slope2;
+  p.M = c.M; p.T = c.T; p.ntiles = (c.M + kTileM - 1) / kTileM; p.Mp = c.Mp; p.dil = c.dil; p.slope2 = c.slope2; p.inv_n = 1.0 / ((double)kC * c.T);
   p.p_planes = c.p_planes; p.st_p = c.st_p; p.tap_img2 = c.tap_img2; p.swc = c.swc; p.w16 = c.w16; p.bog = c.bog;
   p.w_img = c.w_img; p.racc = c.racc; p.rowsum = c.rowsum; p.colsum = c.colsum; p.st_q = c.st_q;
   p.racc_tmap = *reinterpret_cast<const CUtensorMap*>(c.racc_tmap);
