@@ -61,7 +61,7 @@ static_assert(kOffW % 1024 == 0 && kOffP % 16 == 0 && kSmemBytes <= 232448, "sha
 
 struct DmParams {
   alignas(64) CUtensorMap racc_tmap;   // racc as a 2-D tensor [M rows][256 halves], box 64 columns x 32 rows, SWIZZLE_128B
-  int M, T, ntiles, Mp, dil;
+  int M, T, ntiles, Mp, dil, discard;
   float slope2;
   double inv_n;                // 1 / (256 T), from the host (a double division on the device is a long software routine)
   const __half* p_planes;      // [32 K-groups][Mp slots][8 channels]; frame r lives in slot r + kHalo
@@ -250,18 +250,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
 
   if (warp == 0) {
     // ------------------------------------------------------------ p loader (K-group planes, tile + halo)
-    if (lane == 0) {
+    {
       int g = 0;
       for (int tile = first; tile < tile_end; tile += stride) {
         for (int j = 0; j < 8; ++j, ++g) {
           const int s = g % kPStages, u = g / kPStages;
-          if (u > 0) mbar_wait(p_empty + s, (u - 1) & 1, 100 + j);
-          DTL(0, g);
-          mbar_expect_tx(p_full + s, kPChunkBytes);
+          if (u > 0) {
+            mbar_wait(p_empty + s, (u - 1) & 1, 100 + j);
+            // The chunk that held this stage (kPStages back) is consumed, and p is read exactly once: its lines are dead but dirty
+            // (conv1 wrote them) - they would sit in the L2 until evicted and then be written to DRAM. discard.L2 drops them, which
+            // leaves the L2 to the residual stream. Only the 15 lines per plane no other tile reads (frames r0 + 4 .. r0 + 123:
+            // the neighbours' halos are the first and the last line), and never a tile with rows past M (their slots are the
+            // zero padding that no kernel rewrites).
+            const int gp = g - kPStages, tp = first + (gp >> 3) * stride, jp = gp & 7;
+            if (p.discard && (tp + 1) * kTileM <= p.M) {
 #pragma unroll
-          for (int kg = 0; kg < 4; ++kg)   // frames r0 - 4 .. r0 + 131 = slots r0 .. r0 + 135
-            bulk_copy_g2s(smem + kOffP + s * kPChunkBytes + kg * kPlaneBytes,
-                          p.p_planes + ((size_t)(j * 4 + kg) * p.Mp + (size_t)tile * kTileM) * 8, kPlaneBytes, p_full + s);
+              for (int q = 0; q < 2; ++q) {
+                const int idx = lane + 32 * q;          // 60 lines: 4 planes x 15
+                if (idx < 60) {
+                  const int kg = idx / 15, ln = 1 + idx % 15;
+                  const __half* a = p.p_planes + ((size_t)(jp * 4 + kg) * p.Mp + (size_t)tp * kTileM) * 8 + ln * 64;
+                  asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory");
+                }
+              }
+            }
+          }
+          if (lane == 0) {
+            DTL(0, g);
+            mbar_expect_tx(p_full + s, kPChunkBytes);
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg)   // frames r0 - 4 .. r0 + 131 = slots r0 .. r0 + 135
+              bulk_copy_g2s(smem + kOffP + s * kPChunkBytes + kg * kPlaneBytes,
+                            p.p_planes + ((size_t)(j * 4 + kg) * p.Mp + (size_t)tile * kTileM) * 8, kPlaneBytes, p_full + s);
+          }
+          __syncwarp();
         }
       }
     }
@@ -740,7 +762,7 @@ cudaError_t dconv_mma2_setup() {
 
 void launch_dconv_mma2(const DconvMmaParams& c, cudaStream_t st) {
   DmParams p{};
-  p.M = c.M; p.T = c.T; p.ntiles = (c.M + kTileM - 1) / kTileM; p.Mp = c.Mp; p.dil = c.dil; p.slope2 = c.slope2; p.inv_n = 1.0 / ((double)kC * c.T);
+  p.M = c.M; p.T = c.T; p.ntiles = (c.M + kTileM - 1) / kTileM; p.Mp = c.Mp; p.dil = c.dil; p.slope2 = c.slope2; p.discard = c.discard; p.inv_n = 1.0 / ((double)kC * c.T);
   p.p_planes = c.p_planes; p.st_p = c.st_p; p.tap_img2 = c.tap_img2; p.swc = c.swc; p.w16 = c.w16; p.bog = c.bog;
   p.w_img = c.w_img; p.racc = c.racc; p.rowsum = c.rowsum; p.colsum = c.colsum; p.st_q = c.st_q;
   p.racc_tmap = *reinterpret_cast<const CUtensorMap*>(c.racc_tmap);

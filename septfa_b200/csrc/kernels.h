@@ -82,6 +82,7 @@ struct DconvMmaParams {
   const void* w_tmap;       // host pointer to a CUtensorMap over w_img ([2048 rows][64 halves], box 256 x 64), or nullptr
   __half* racc; float* rowsum; double* colsum; Stat2* st_q;
   const void* racc_tmap = nullptr;   // dconv_mma2.cu: host pointer to a CUtensorMap over racc ([M rows][256 halves], box 64 x 32, SWIZZLE_128B)
+  int discard = 0;          // dconv_mma2.cu: drop the consumed lines of p from the L2 (discard.global.L2)
 };
 
 // TCN.output (model/model.py:322-325,357): logits = Wo GN(PReLU(y)) + bo, N = 514 padded to 576.
@@ -139,6 +140,7 @@ struct ResidParams {
   Stat2* st_w;         // [B] stats of the new stream (recursive only)
   const __half* w_half_in = nullptr;   // half-stream mode (cluster-resident kernel only): the stream before the block as fp16 ...
   __half* w_half_out = nullptr;        // ... and after it; a null pointer means the fp32 buffer `w`
+  int discard = 0;                     // cluster-resident kernel: drop the consumed lines of racc from the L2
 };
 
 // ---- launchers ---------------------------------------------------------------------------
@@ -252,6 +254,7 @@ struct LaunchCtx {
   int dconv_late_trigger = 1;  // dconv triggers its (persistent) dependent at the start of its epilogue
   int fused_pdl = 1;           // the cluster-resident residual kernel launches programmatically after dconv
   int dconv_mma = 1;           // tensor-core depthwise + res_out kernel (dconv_mma.cu) when applicable
+  int l2_discard = 1;          // consumed hand-off buffers (p in the pair dconv kernel, racc in the cluster residual kernel) are discarded from the L2
   int dconv_pair = 1;          // ... on CTA pairs (cta_group::2 MMAs, res_out weights resident in shared memory: dconv_mma2.cu)
   int dconv_desc_swap = 0;     // bring-up: exchange LBO / SBO of its no-swizzle descriptors
   int dconv_w_tmap = 1;        // stream the res_out weight image with tensor-map TMA loads (0: linear bulk copies)

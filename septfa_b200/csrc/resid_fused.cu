@@ -52,6 +52,7 @@ struct FusedParams {
   const double* colsum;     // [B,256]
   TfParams tf;
   int T, B, Tc;             // Tc = frames per CTA
+  int discard;              // drop the consumed racc lines from the L2
   double inv_T, inv_HT, inv_CT;   // 1 / T, 1 / (512 T), 1 / (256 T): computed on the host (a double division is a long software routine,
                                   // and every thread of every CTA ran one before its first gate stage, thread 0 one per utterance)
   int mode;                 // LnMode
@@ -258,6 +259,12 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
     }
     FTL(8 + it * 8 + 1);
     mbar_wait(&full, it & 1, 700);   // the tile has landed (every thread observes the barrier itself)
+    if (p.discard) {
+      // racc is read exactly once, by this CTA, and it is in shared memory now: its lines in the L2 are dead but dirty (the
+      // dconv kernel wrote them) - dropped here they are neither written to DRAM nor in the residual stream's way
+      const uint8_t* rg = reinterpret_cast<const uint8_t*>(p.racc + ((int64_t)b * p.T + t0) * kC);
+      for (int l = tid; l < nt * 4; l += kPersistThreads) asm volatile("discard.global.L2 [%0], 128;" ::"l"(rg + (size_t)l * 128) : "memory");
+    }
     FTL(8 + it * 8 + 2);
 
     // ---- statistics of v = y + gt (G1 r + G2)  (recursive)  |  gt (G1 r + G2)  (residual) over the whole utterance
@@ -484,7 +491,7 @@ bool launch_resid_fused(const ResidParams& rp, const GateParams& gp, cudaStream_
   p.w_out = rp.w_half_out ? rp.w_half_out : static_cast<void*>(rp.w);
   p.racc = reinterpret_cast<const __half*>(rp.racc); p.norm = rp.norm;
   p.st_q = gp.st_q; p.s3 = gp.s3; p.c03 = gp.c03; p.rowsum = gp.rowsum; p.colsum = gp.colsum; p.tf = gp.tf;
-  p.T = rp.T; p.B = rp.B; p.Tc = (rp.T + cs - 1) / cs;
+  p.T = rp.T; p.B = rp.B; p.Tc = (rp.T + cs - 1) / cs; p.discard = rp.discard;
   p.inv_T = 1.0 / (double)rp.T; p.inv_HT = 1.0 / ((double)kH * rp.T); p.inv_CT = 1.0 / ((double)kC * rp.T);
   p.mode = rp.mode; p.g_a = rp.g_a; p.b_a = rp.b_a; p.st_w = rp.st_w;
   const int in_half = rp.w_half_in ? 1 : 0, out_half = rp.w_half_out ? 1 : 0, variant = in_half * 2 + out_half;

@@ -507,6 +507,10 @@ int septfa_set_option(septfa_handle* h, const char* name, int value) {
     h->lctx.dconv_mma = value ? 1 : 0;
     return 0;
   }
+  if (std::strcmp(name, "l2_discard") == 0) {
+    h->lctx.l2_discard = value ? 1 : 0;
+    return 0;
+  }
   if (std::strcmp(name, "dconv_pair") == 0) {
     h->lctx.dconv_pair = value ? 1 : 0;
     return 0;
@@ -945,6 +949,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
       DconvMmaParams dm{reinterpret_cast<const __half*>(ws.p), Mp, st_p, d.tap_img, d.tap_img2, d.swc, d.w16, d.bog, d.a2, d.dil, M, T, B, d.w3_img, d.tmap_ok ? &d.w3_tmap : nullptr,
                         reinterpret_cast<__half*>(ws.racc), ws.rowsum, colsum, st_q};
       dm.racc_tmap = pair ? &racc_tmap : nullptr;
+      dm.discard = h->lctx.l2_discard;
       if (pair) launch_dconv_mma2(dm, st); else launch_dconv_mma(dm, st);
     } else if (tc_dconv) {
       launch_tc_dconv(dc, st);
@@ -956,7 +961,7 @@ int septfa_forward(septfa_handle* h, const float* x, int B, int64_t L, const sep
     GateParams gp{st_q, (tc_dconv && !split) ? d.s3_tc : d.s3_ref, d.c03, ws.rowsum, colsum, d.tf, M, T, B, ws.ra, ws.rb, ws.gf, ws.gt, ws.mt};
     ResidParams rp{};
     rp.w = ws.w; rp.norm = norm; rp.racc = ws.racc; rp.racc_half = half_io; rp.ra = ws.ra; rp.rb = ws.rb; rp.gf = ws.gf; rp.gt = ws.gt;
-    rp.M = M; rp.T = T; rp.B = B; rp.mode = h->ln_mode; rp.st_v = st_v; rp.st_w = st_w;
+    rp.M = M; rp.T = T; rp.B = B; rp.mode = h->ln_mode; rp.st_v = st_v; rp.st_w = st_w; rp.discard = h->lctx.l2_discard;
     if (stream_half) { rp.w_half_in = i > 0 ? ws.wh : nullptr; rp.w_half_out = i + 1 < h->nblk ? ws.wh : nullptr; }
     if (h->ln_mode == LN_RECURSIVE) { rp.g_a = d.lf_g; rp.b_a = d.lf_b; }        // model.py:347-348
     else if (h->ln_mode == LN_RESIDUAL) { rp.g_a = d.lm_g; rp.b_a = d.lm_b; }    // model.py:349-350
