@@ -251,6 +251,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
   if (warp == 0) {
     // ------------------------------------------------------------ p loader (K-group planes, tile + halo)
     {
+      auto discard_chunk = [&](int gp) {   // whole warp: the 60 lines (4 planes x 15) of chunk gp that no other tile reads
+        const int tp = first + (gp >> 3) * stride, jp = gp & 7;
+        if (p.discard && (tp + 1) * kTileM <= p.M) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int idx = lane + 32 * q;
+            if (idx < 60) {
+              const int kg = idx / 15, ln = 1 + idx % 15;
+              const __half* a = p.p_planes + ((size_t)(jp * 4 + kg) * p.Mp + (size_t)tp * kTileM) * 8 + ln * 64;
+              asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory");
+            }
+          }
+        }
+      };
       int g = 0;
       for (int tile = first; tile < tile_end; tile += stride) {
         for (int j = 0; j < 8; ++j, ++g) {
@@ -262,18 +276,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
             // leaves the L2 to the residual stream. Only the 15 lines per plane no other tile reads (frames r0 + 4 .. r0 + 123:
             // the neighbours' halos are the first and the last line), and never a tile with rows past M (their slots are the
             // zero padding that no kernel rewrites).
-            const int gp = g - kPStages, tp = first + (gp >> 3) * stride, jp = gp & 7;
-            if (p.discard && (tp + 1) * kTileM <= p.M) {
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const int idx = lane + 32 * q;          // 60 lines: 4 planes x 15
-                if (idx < 60) {
-                  const int kg = idx / 15, ln = 1 + idx % 15;
-                  const __half* a = p.p_planes + ((size_t)(jp * 4 + kg) * p.Mp + (size_t)tp * kTileM) * 8 + ln * 64;
-                  asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory");
-                }
-              }
-            }
+            discard_chunk(g - kPStages);
           }
           if (lane == 0) {
             DTL(0, g);
@@ -285,6 +288,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1) k_dcon
           }
           __syncwarp();
         }
+      }
+      for (int gp = max(0, g - kPStages); gp < g; ++gp) {   // the chunks still in the ring when the loop ends
+        mbar_wait(p_empty + gp % kPStages, (gp / kPStages) & 1, 110);
+        discard_chunk(gp);
       }
     }
     __syncwarp();
