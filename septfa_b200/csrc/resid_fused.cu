@@ -348,6 +348,8 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
       }
     }
     float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+    uint64_t keep_policy;   // the new stream is read twice more (conv1, then this kernel again): last in line for eviction
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
     uint8_t* wout = reinterpret_cast<uint8_t*>(p.w_out) + (((int64_t)b * p.T + t0) * kC + c0) * (OUT_H ? 2 : 4);
     for (int i0 = rg; i0 < nt; i0 += 4 * kRowGroups)
 #pragma unroll
@@ -369,7 +371,9 @@ __global__ void __launch_bounds__(kPersistThreads, 4) k_resid_persist(FusedParam
         *reinterpret_cast<uint2*>(wout + (int64_t)i * kC * 2) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
       } else {
-        *reinterpret_cast<float4*>(wout + (int64_t)i * kC * 4) = make_float4(o0.x, o0.y, o1.x, o1.y);
+        asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(wout + (int64_t)i * kC * 4), "f"(o0.x), "f"(o0.y), "f"(o1.x),
+                     "f"(o1.y), "l"(keep_policy)
+                     : "memory");
       }
       s2 = __fadd2_rn(s2, __fadd2_rn(o0, o1));
       q2 = __ffma2_rn(o0, o0, q2);
