@@ -198,3 +198,47 @@ def test_reference_bytecode_build_matches_source(tmp_path):
         assert r.stdout.strip().endswith(kind)
         res[kind] = np.load(out)
     assert np.array_equal(res["source"], res["bytecode"])
+
+
+def test_cli_host_preprocessing_and_writers_match_reference_golden(tmp_path):
+    """The host side of ``only_inference.py`` either side of the forward, without a GPU: ``read_mixture`` (stereo int16
+    wav -> channel 0 -> float32 -> min-max normalise, only_inference.py:68-83) must reproduce the ``Mixed_0.wav`` the
+    UNMODIFIED reference script wrote for the same file (tests/golden/cli_with_vad_ps32.npz); ``save_audio``
+    (Our_utils/utlis_inference.py:24-37) round-trips float32 and writes 16-bit PCM for ``-ps 16``; ``save_vad``
+    (:39-46) writes the 0.5-thresholded decisions of batch item 0; ``parse_dictionary`` (only_inference.py:17-23)."""
+    import argparse
+    from scipy.io.wavfile import read, write
+    from conftest import load_golden
+    from septfa_b200 import inference
+    g, meta = load_golden("cli_with_vad_ps32")
+    wav = tmp_path / "mix.wav"
+    write(str(wav), 16000, synth.make_cli_wav(meta["weight_seed"], fs=16000))
+    with contextlib.redirect_stdout(io.StringIO()) as said:
+        x = inference.read_mixture(str(wav))
+    assert "not mono" in said.getvalue()
+    assert x.dtype == torch.float32 and tuple(x.shape) == (1, 48000)
+    assert np.abs(x[0].numpy() - g["Mixed_0"]).max() <= 1e-6
+    assert abs(x.max().item() - 0.9) < 1e-6 and abs(x.min().item() + 0.9) < 1e-6
+    # writers
+    sep = torch.stack([torch.from_numpy(g["Speaker_0"]), torch.from_numpy(g["Speaker_1"])])[None]
+    inference.save_audio(x, sep, str(tmp_path / "o32"), 32)
+    for name in ("Speaker_0", "Speaker_1"):
+        sr, a = read(str(tmp_path / "o32" / f"{name}.wav"))
+        assert sr == 16000 and a.dtype == np.float32 and np.array_equal(a, g[name])
+    sr, m = read(str(tmp_path / "o32" / "Mixed_0.wav"))
+    assert np.array_equal(m, x[0].numpy())
+    inference.save_audio(x, sep, str(tmp_path / "o16"), 16)
+    sr, a16 = read(str(tmp_path / "o16" / "Speaker_1.wav"))
+    assert sr == 16000 and a16.dtype == np.int16 and np.abs(a16 / 32767.0 - g["Speaker_1"]).max() <= 0.5 / 32767 + 1e-7
+    vad = torch.tensor([[[0.2, 0.5, 0.7, 0.49], [0.9, 0.1, 0.5, 0.0]]])
+    inference.save_vad(vad, str(tmp_path / "vad"))
+    inference.save_vad(vad[:, :, None], str(tmp_path / "vad4"))            # [B, 2, 1, T] of return_smoothed_vad
+    for d in ("vad", "vad4"):
+        files = sorted(p.name for p in (tmp_path / d).iterdir())
+        assert [f.rsplit(".", 1)[0] for f in files] == ["estimated_vad_0", "estimated_vad_1"]
+        if files[0].endswith(".npy"):
+            assert np.array_equal(np.load(str(tmp_path / d / files[0])), [0, 1, 1, 0])
+            assert np.array_equal(np.load(str(tmp_path / d / files[1])), [1, 0, 1, 0])
+    assert inference.parse_dictionary('{"filter_signals_by_smo_vad": true}') == {"filter_signals_by_smo_vad": True}
+    with pytest.raises(argparse.ArgumentTypeError):
+        inference.parse_dictionary("{not json")
