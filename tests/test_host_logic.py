@@ -242,3 +242,13 @@ def test_cli_host_preprocessing_and_writers_match_reference_golden(tmp_path):
     assert inference.parse_dictionary('{"filter_signals_by_smo_vad": true}') == {"filter_signals_by_smo_vad": True}
     with pytest.raises(argparse.ArgumentTypeError):
         inference.parse_dictionary("{not json")
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md's entry-point table names every symbol include/septfa.h declares (and nothing the header lacks)."""
+    header = open(os.path.join(ROOT, "include", "septfa.h")).read()
+    declared = set(re.findall(r"\b(septfa_[a-z0-9_]+)\s*\(", header))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    table = doc.split("### Entry points and the reference interface each one stands for")[1].split("## 3. Build")[0]
+    listed = set(re.findall(r"`(septfa_[a-z0-9_]+)`", "\n".join(l.split("|")[1] for l in table.splitlines() if l.startswith("| `"))))
+    assert listed == declared, (sorted(declared - listed), sorted(listed - declared))
