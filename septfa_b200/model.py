@@ -94,6 +94,10 @@ class SeparationModel(nn.Module):
         self.materialize = {"estimated_stfts": True, "mask_per_speaker": True, "spectrum": True, "masks_b": True}
         self.engine = _lib.ENGINE_TCGEN05_F16
         self.last_launch_count = 0
+        # Opt-in guard (costs a device reduction and a host sync per forward): raise if a forward returns non-finite
+        # samples. In the fast mode p and racc travel between the block kernels as fp16 (|x| <= 65504): a checkpoint with
+        # extreme weight_g could overflow there; set_option("precision", 2) keeps them in fp32.
+        self.check_finite = False
 
     # -- weights ---------------------------------------------------------------------------
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -189,6 +193,10 @@ class SeparationModel(nn.Module):
                                       p(est), p(mask), p(spec), p(logits), p(h.workspace), h.workspace.numel(), stream)
             _lib.check(h.ptr, rc)
             self.last_launch_count = h.lib.septfa_last_launch_count(h.ptr)
+            if self.check_finite and not bool(torch.isfinite(out).all()):
+                raise RuntimeError("septfa_b200: the forward returned non-finite samples - a non-finite or constant input, or "
+                                   "half-precision overflow of the tensors between the block kernels (extreme weight_g): "
+                                   "try model.set_option('precision', 2)")
         self.spectrum = spec
         self.masks_b = logits
         self.mask_per_speaker = mask

@@ -913,3 +913,22 @@ def test_separate_files_batched_pcm_pipeline(cuda_models, tmp_path):
         assert (vads[pth] - ref_vad[0].cpu()).abs().max().item() < 1e-3
 
 
+
+
+def test_check_finite_guard(cuda_models):
+    """SeparationModel.check_finite (opt-in): a forward that returns non-finite samples raises instead of handing them on
+    (here forced with a NaN in one input sample; the motivating case is fp16 overflow between the block kernels)."""
+    m = cuda_models(synth.CONFIG_WITH_VAD, 9, 0)
+    x = torch.from_numpy(synth.make_mixtures(2, 33000, 77)).cuda()
+    m.check_finite = True
+    try:
+        out, _, _ = m(x, {})
+        assert torch.isfinite(out).all()
+        x[1, 5000] = float("nan")
+        with pytest.raises(RuntimeError, match="non-finite"):
+            m(x, {})
+        m.check_finite = False
+        out, _, _ = m(x, {})                       # without the guard: the reference's behaviour, NaNs are handed on
+        assert torch.isfinite(out[0]).all() and not torch.isfinite(out[1]).all()
+    finally:
+        m.check_finite = False
